@@ -1,0 +1,330 @@
+// fdf_capi.cu -- the C ABI of libfdf_cuda.so (include/fdf.h): context, argument checking, TMA
+// tensor-map encoding, staging for the host-memory entry points.  No torch types, no CPU fallback:
+// every entry point either runs the sm_100a kernels or returns an error status.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/fdf.h"
+#include "fdf_kernels.cuh"
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <typename T>
+struct DeviceBuffer {
+    T *ptr = nullptr;
+    size_t count = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= count) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        count = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ptr), n * sizeof(T));
+        if (e == cudaSuccess) count = n;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        count = 0;
+    }
+};
+
+}  // namespace
+
+struct fdf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    EncodeTiledFn encode = nullptr;
+    DeviceBuffer<uint8_t> workspace;            // ticket | flags | status[]
+    DeviceBuffer<uint8_t> staged_frames;        // host-path input staging (pitched to 16 bytes)
+    DeviceBuffer<fdf_point> staged_points;      // host-path output staging
+    DeviceBuffer<unsigned long long> staged_offsets;
+    unsigned long long *pinned_offsets = nullptr;
+    size_t pinned_offsets_count = 0;
+    uint64_t launches = 0;
+    char error[512] = {0};
+};
+
+namespace {
+
+constexpr size_t kWorkspaceHeader = 64;  // ticket at +0, flags at +4, status words from +64
+
+fdf_status fail(fdf_ctx *ctx, fdf_status st, const char *fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->error, sizeof(ctx->error), fmt, ap);
+        va_end(ap);
+    }
+    return st;
+}
+
+#define FDF_CUDA(ctx, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(ctx, FDF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                   \
+    } while (0)
+
+fdf_status check_config(fdf_ctx *ctx, uint8_t count, uint8_t nms) {
+    // fast_simd.rs:302-305 asserts count >= 9; count > 16 panics at :797-801
+    if (count < 9 || count > 16) return fail(ctx, FDF_ERR_INVALID_COUNT, "count must be in 9..=16, got %u", count);
+    if (nms > FDF_NMS_SUM_ABSOLUTE) return fail(ctx, FDF_ERR_INVALID_NMS, "unknown nms mode %u", nms);
+    return FDF_OK;
+}
+
+// strip height: tall strips (less halo) when there is enough work to fill the GPU, short otherwise
+int choose_scored_rows(uint32_t n_frames, uint32_t h, int mode) {
+    const long long rows = (long long)h - 2 * fdf::first_out_row(mode);
+    const long long strips32 = (rows + fdf::out_rows(mode, 32) - 1) / fdf::out_rows(mode, 32);
+    return (long long)n_frames * strips32 >= 2 * 148 ? 32 : 16;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *fdf_version(void) { return "fdf-b200 0.1 (sm_100a)"; }
+
+const char *fdf_status_string(fdf_status status) {
+    switch (status) {
+        case FDF_OK: return "ok";
+        case FDF_ERR_INVALID_COUNT: return "count must be in 9..=16";
+        case FDF_ERR_INVALID_NMS: return "unknown non-maximal-suppression mode";
+        case FDF_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case FDF_ERR_CAPACITY: return "output capacity too small";
+        case FDF_ERR_CUDA: return "CUDA error";
+        case FDF_ERR_NO_DEVICE: return "no usable sm_100 device";
+        case FDF_ERR_INTERNAL: return "device-side consistency check failed";
+    }
+    return "unknown status";
+}
+
+const char *fdf_last_error(const fdf_ctx *ctx) { return ctx ? ctx->error : "null context"; }
+
+uint64_t fdf_kernel_launches(const fdf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+fdf_status fdf_create(int device, fdf_ctx **out_ctx) {
+    if (!out_ctx) return FDF_ERR_INVALID_ARGUMENT;
+    *out_ctx = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return FDF_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FDF_ERR_NO_DEVICE;
+    if (prop.major != 10) return FDF_ERR_NO_DEVICE;  // the only code in this library is sm_100a SASS
+    fdf_ctx *ctx = new (std::nothrow) fdf_ctx();
+    if (!ctx) return FDF_ERR_INTERNAL;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return FDF_ERR_CUDA;
+    }
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return FDF_ERR_CUDA;
+    }
+    ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    *out_ctx = ctx;
+    return FDF_OK;
+}
+
+void fdf_destroy(fdf_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->workspace.release();
+    ctx->staged_frames.release();
+    ctx->staged_points.release();
+    ctx->staged_offsets.release();
+    if (ctx->pinned_offsets) cudaFreeHost(ctx->pinned_offsets);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h,
+                             uint32_t pitch, uint64_t frame_stride, uint8_t threshold, uint8_t count, uint8_t nms,
+                             fdf_point *d_out, size_t cap, uint64_t *d_offsets, void *stream_handle) {
+    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
+    fdf_status st = check_config(ctx, count, nms);
+    if (st != FDF_OK) return st;
+    if (!d_offsets || (!d_out && cap > 0)) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null output pointer");
+    cudaStream_t stream = stream_handle ? reinterpret_cast<cudaStream_t>(stream_handle) : ctx->stream;
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    const int mode = nms;
+    const long long rows = (long long)h - 2 * fdf::first_out_row(mode);
+    if (n_frames == 0 || w < 7 || h < 7 || rows <= 0) {  // nothing can be a keypoint
+        FDF_CUDA(ctx, cudaMemsetAsync(d_offsets, 0, ((size_t)n_frames + 1) * sizeof(uint64_t), stream));
+        return FDF_OK;
+    }
+    if (!d_frames) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null frame pointer");
+    if (pitch < w) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "pitch %u < width %u", pitch, w);
+    if (n_frames > 1 && frame_stride < (uint64_t)pitch * h)
+        return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "frame_stride smaller than one frame");
+    if (n_frames == 1) frame_stride = (((uint64_t)pitch * h) + 15ull) & ~15ull;
+    if ((reinterpret_cast<uintptr_t>(d_frames) & 15u) || (pitch & 15u) || (frame_stride & 15ull))
+        return fail(ctx, FDF_ERR_INVALID_ARGUMENT,
+                    "device frames need a 16-byte aligned base, pitch and frame_stride (TMA tensor map)");
+
+    const int sr = choose_scored_rows(n_frames, h, mode);
+    fdf::DetectParams p;
+    p.w = w;
+    p.h = h;
+    p.n_frames = n_frames;
+    p.strips_per_frame = (uint32_t)((rows + fdf::out_rows(mode, sr) - 1) / fdf::out_rows(mode, sr));
+    p.chunks_per_strip = (w - 3 + fdf::kChunkW - 1) / fdf::kChunkW;
+    p.words_per_row = (w + 31) / 32;
+    p.threshold = threshold;
+    p.count = count;
+    p.cap = cap;
+    p.out = reinterpret_cast<uint2 *>(d_out);
+    p.offsets = reinterpret_cast<unsigned long long *>(d_offsets);
+
+    const size_t smem = fdf::detect_smem_bytes(mode, sr, p.words_per_row);
+    if (smem > 227 * 1024) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "image too wide (%u) for the strip bit plane", w);
+    const unsigned long long items = (unsigned long long)n_frames * p.strips_per_frame;
+    if (items > 0x7fffffffull) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "batch too large");
+
+    const size_t ws_bytes = kWorkspaceHeader + (size_t)items * sizeof(unsigned long long);
+    FDF_CUDA(ctx, ctx->workspace.reserve(ws_bytes));
+    FDF_CUDA(ctx, cudaMemsetAsync(ctx->workspace.ptr, 0, ws_bytes, stream));
+    p.ticket = reinterpret_cast<uint32_t *>(ctx->workspace.ptr);
+    p.flags = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + 4);
+    p.status = reinterpret_cast<unsigned long long *>(ctx->workspace.ptr + kWorkspaceHeader);
+
+    // frames as a 3-D u8 tensor (x, y, frame); box = one tile; out-of-bounds elements read as 0
+    CUtensorMap tmap;
+    const cuuint64_t dims[3] = {w, h, n_frames};
+    const cuuint64_t strides[2] = {pitch, frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)fdf::kTileW, (cuuint32_t)fdf::tile_rows(sr), 1u};
+    const cuuint32_t elem_strides[3] = {1u, 1u, 1u};
+    CUresult cr = ctx->encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(d_frames), dims, strides,
+                              box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(ctx, FDF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+
+    FDF_CUDA(ctx, fdf::launch_detect(mode, sr, tmap, p, stream));
+    ctx->launches += 1;
+    return FDF_OK;
+}
+
+fdf_status fdf_check_device_flags(fdf_ctx *ctx, uint32_t *flags) {
+    if (!ctx || !flags) return FDF_ERR_INVALID_ARGUMENT;
+    *flags = 0;
+    if (!ctx->workspace.ptr) return FDF_OK;
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    FDF_CUDA(ctx, cudaDeviceSynchronize());
+    FDF_CUDA(ctx, cudaMemcpy(flags, ctx->workspace.ptr + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return FDF_OK;
+}
+
+fdf_status fdf_detect_batch(fdf_ctx *ctx, const uint8_t *frames, uint32_t n_frames, uint32_t w, uint32_t h,
+                            uint32_t pitch, uint64_t frame_stride, uint8_t threshold, uint8_t count, uint8_t nms,
+                            fdf_point *out, size_t cap, uint64_t *offsets) {
+    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
+    fdf_status st = check_config(ctx, count, nms);
+    if (st != FDF_OK) return st;
+    if (!offsets || (!out && cap > 0)) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null output pointer");
+    if (n_frames == 0 || w < 7 || h < 7) {
+        memset(offsets, 0, ((size_t)n_frames + 1) * sizeof(uint64_t));
+        return FDF_OK;
+    }
+    if (!frames) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null frame pointer");
+    if (pitch < w) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "pitch %u < width %u", pitch, w);
+    if (n_frames == 1) frame_stride = (uint64_t)pitch * h;
+    if (frame_stride < (uint64_t)pitch * h) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "frame_stride smaller than one frame");
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    // stage the frames with a 16-byte multiple pitch (TMA requirement); one copy when the layout allows
+    const uint32_t dpitch = (w + 15u) & ~15u;
+    const uint64_t dstride = (uint64_t)dpitch * h;
+    FDF_CUDA(ctx, ctx->staged_frames.reserve((size_t)dstride * n_frames));
+    if (pitch == dpitch && frame_stride == dstride) {
+        FDF_CUDA(ctx, cudaMemcpyAsync(ctx->staged_frames.ptr, frames, (size_t)dstride * n_frames,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    } else if (frame_stride == (uint64_t)pitch * h) {
+        FDF_CUDA(ctx, cudaMemcpy2DAsync(ctx->staged_frames.ptr, dpitch, frames, pitch, w, (size_t)h * n_frames,
+                                        cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        for (uint32_t f = 0; f < n_frames; f++)
+            FDF_CUDA(ctx, cudaMemcpy2DAsync(ctx->staged_frames.ptr + (size_t)f * dstride, dpitch,
+                                            frames + (size_t)f * frame_stride, pitch, w, h, cudaMemcpyHostToDevice,
+                                            ctx->stream));
+    }
+    const size_t worst = (size_t)n_frames * (size_t)(w - 6) * (size_t)(h - 6);
+    const size_t dcap = cap < worst ? cap : worst;
+    FDF_CUDA(ctx, ctx->staged_points.reserve(dcap ? dcap : 1));
+    FDF_CUDA(ctx, ctx->staged_offsets.reserve((size_t)n_frames + 1));
+    if (ctx->pinned_offsets_count < (size_t)n_frames + 1) {
+        if (ctx->pinned_offsets) cudaFreeHost(ctx->pinned_offsets);
+        ctx->pinned_offsets = nullptr;
+        ctx->pinned_offsets_count = 0;
+        FDF_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(&ctx->pinned_offsets),
+                                     ((size_t)n_frames + 1) * sizeof(unsigned long long)));
+        ctx->pinned_offsets_count = (size_t)n_frames + 1;
+    }
+
+    st = fdf_detect_device(ctx, ctx->staged_frames.ptr, n_frames, w, h, dpitch, dstride, threshold, count, nms,
+                           ctx->staged_points.ptr, dcap, reinterpret_cast<uint64_t *>(ctx->staged_offsets.ptr),
+                           ctx->stream);
+    if (st != FDF_OK) return st;
+    FDF_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_offsets, ctx->staged_offsets.ptr,
+                                  ((size_t)n_frames + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    uint32_t *flags_dev = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + 4);
+    uint32_t flags = 0;
+    FDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(offsets, ctx->pinned_offsets, ((size_t)n_frames + 1) * sizeof(uint64_t));
+    const uint64_t found = offsets[n_frames];
+    const size_t ncopy = found < dcap ? (size_t)found : dcap;
+    if (ncopy)
+        FDF_CUDA(ctx, cudaMemcpyAsync(out, ctx->staged_points.ptr, ncopy * sizeof(fdf_point), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+    if (ctx->workspace.ptr)
+        FDF_CUDA(ctx, cudaMemcpyAsync(&flags, flags_dev, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+    FDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flags) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x (look-back or TMA wait timed out)", flags);
+    if (found > cap) return fail(ctx, FDF_ERR_CAPACITY, "%llu keypoints found, capacity %zu", (unsigned long long)found, cap);
+    return FDF_OK;
+}
+
+fdf_status fdf_detect(fdf_ctx *ctx, const uint8_t *img, uint32_t w, uint32_t h, uint32_t pitch, uint8_t threshold,
+                      uint8_t count, uint8_t nms, fdf_point *out, size_t cap, size_t *n_out) {
+    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
+    if (!n_out) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null n_out");
+    *n_out = 0;
+    uint64_t offsets[2] = {0, 0};
+    fdf_status st = fdf_detect_batch(ctx, img, 1, w, h, pitch, (uint64_t)pitch * h, threshold, count, nms, out, cap,
+                                     offsets);
+    if (st == FDF_OK || st == FDF_ERR_CAPACITY) *n_out = (size_t)offsets[1];
+    return st;
+}
+
+fdf_status fdf_synth_frames_device(fdf_ctx *ctx, uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h,
+                                   uint32_t pitch, uint64_t frame_stride, uint64_t seed, uint32_t first_frame,
+                                   uint32_t kind, uint32_t amp, void *stream_handle) {
+    if (!ctx || !d_frames) return FDF_ERR_INVALID_ARGUMENT;
+    if (pitch < w || kind > 1) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "bad synth arguments");
+    cudaStream_t stream = stream_handle ? reinterpret_cast<cudaStream_t>(stream_handle) : ctx->stream;
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    FDF_CUDA(ctx, fdf::launch_synth(d_frames, n_frames, w, h, pitch, frame_stride, seed, first_frame, kind, amp, stream));
+    ctx->launches += 1;
+    return FDF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,46 @@
+// fdf_kernels.cuh -- launch interface between the C ABI (fdf_capi.cu) and the kernels (fdf_kernels.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fdf {
+
+// Geometry shared by host and device.  A frame is cut into STRIPS of full-width rows; one CTA
+// owns one strip and walks it left to right in CHUNKS.  For every chunk a 256-byte-wide tile
+// (chunk + halo) is staged into shared memory by one TMA 3-D tiled load.
+constexpr int kThreads = 256;   // threads per CTA
+constexpr int kTileW = 256;     // tile width in bytes = TMA box inner extent (the maximum)
+constexpr int kChunkW = 240;    // output columns per chunk
+constexpr int kHaloX = 8;       // tile starts 8 px left of the chunk (4 needed; 8 keeps words aligned)
+
+// scored rows per strip (SR) -> staged rows, emitted rows
+__host__ __device__ constexpr int tile_rows(int sr) { return sr + 6; }                             // +-3 ring rows
+__host__ __device__ constexpr int out_rows(int mode, int sr) { return mode == 0 ? sr : sr - 2; }  // NMS needs a 1-row score halo
+__host__ __device__ constexpr int first_out_row(int mode) { return mode == 0 ? 3 : 4; }          // fast_simd.rs:342 / :589-596
+
+struct DetectParams {
+    uint32_t w, h, n_frames;
+    uint32_t strips_per_frame;
+    uint32_t chunks_per_strip;
+    uint32_t words_per_row;  // ceil(w / 32): bit-plane words per row
+    uint32_t threshold, count;
+    unsigned long long cap;  // capacity of out, in points
+    uint2 *out;              // fdf_point[cap], packed over the whole batch, row-major per frame
+    unsigned long long *offsets;  // n_frames + 1
+    unsigned long long *status;   // n_frames * strips_per_frame look-back words (zeroed per launch)
+    uint32_t *ticket;             // zeroed per launch
+    uint32_t *flags;              // zeroed per launch; bit 0 look-back timeout, bit 1 TMA wait timeout
+};
+
+size_t detect_smem_bytes(int mode, int sr, uint32_t words_per_row);
+
+// Enqueues the detection kernel for (mode, sr) on `stream`.  tmap describes the frames as a 3-D
+// u8 tensor (x, y, frame) with box (kTileW, tile_rows(sr), 1).
+cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream);
+
+cudaError_t launch_synth(uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t pitch,
+                         unsigned long long frame_stride, unsigned long long seed, uint32_t first_frame,
+                         uint32_t kind, uint32_t amp, cudaStream_t stream);
+
+}  // namespace fdf

@@ -1,0 +1,214 @@
+// fdf_strip.cuh -- the per-thread bodies of the detection kernel's phases.
+//
+// They are `__host__ __device__` and take the thread index as an argument: fdf_kernels.cu calls
+// them with threadIdx.x between its barriers, and tests/host/strip_emulator.cpp runs the very same
+// code thread by thread on the CPU (TMA replaced by a zero-filled copy) so that the tiling,
+// halo, validity and NMS-row rules are checked against the oracle without a GPU.
+//
+// Geometry (see fdf_kernels.cuh): a strip has SR scored rows; tile row 0 is image row
+// ys0 - 3 where ys0 is the image row of scored row 0; tile column 0 is image column xt0 = x0 - 8
+// where x0 is the chunk's first output column.
+#pragma once
+#include "fdf_core.cuh"
+#include "fdf_kernels.cuh"
+
+namespace fdf {
+
+FDF_HD uint32_t atomic_add_u32(uint32_t *p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    uint32_t old = *p;
+    *p = old + v;
+    return old;
+#endif
+}
+
+FDF_HD void atomic_or_u32(uint32_t *p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+
+FDF_HD int lowest_set_bit(uint32_t m) {  // m != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs(m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
+
+struct ChunkGeo {
+    int w, h;   // image size
+    int ys0;    // image row of scored row 0
+    int y0;     // first image row this strip emits
+    int x0;     // first image column this chunk emits
+    int xt0;    // image column of tile column 0
+    int ww;     // bit-plane words per row
+};
+
+template <int MODE>
+FDF_HD ChunkGeo make_geo(int w, int h, int ww, int strip, int chunk, int sr) {
+    ChunkGeo g;
+    g.w = w;
+    g.h = h;
+    g.ww = ww;
+    g.y0 = first_out_row(MODE) + strip * out_rows(MODE, sr);
+    g.ys0 = g.y0 - (MODE == NMS_OFF ? 0 : 1);
+    g.x0 = chunk * kChunkW;
+    g.xt0 = g.x0 - kHaloX;
+    return g;
+}
+
+// ---- phase A: dense filter, 16 centres per thread and row (replaces fast_simd.rs:368-520) -------
+// Pushes (scored row << 8 | tile column) of every centre that passes the necessary-condition
+// filter and lies inside the image's centre range and this chunk's scored columns.
+template <int MODE, int SR>
+FDF_HD void phase_a(int tid, const uint8_t *tile, uint16_t *queue, uint32_t *qcount, const ChunkGeo &g,
+                    uint32_t kbias) {
+    constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;
+    const int q = tid & 15;   // which 16-pixel group of the 256-wide tile row
+    const int r0 = tid >> 4;  // first scored row of this thread
+    const int xlo = max(3, g.x0 - HS), xhi = min(g.w - 3, g.x0 + kChunkW + HS);
+    uint32_t vm[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t m = 0u;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int x = g.xt0 + q * 16 + k * 4 + b;
+            if (x >= xlo && x < xhi) m |= 0x80u << (8 * b);
+        }
+        vm[k] = m;
+    }
+    for (int rr = r0; rr < SR; rr += kThreads / 16) {
+        const int y = g.ys0 + rr;
+        if (y < 3 || y >= g.h - 3) continue;  // fast_simd.rs:342
+        const uint8_t *rowp = tile + (rr + 3) * kTileW + q * 16;
+        const uint4 C = *reinterpret_cast<const uint4 *>(rowp);
+        const uint4 N = *reinterpret_cast<const uint4 *>(rowp - 3 * kTileW);
+        const uint4 S = *reinterpret_cast<const uint4 *>(rowp + 3 * kTileW);
+        const uint32_t cl = q > 0 ? *reinterpret_cast<const uint32_t *>(rowp - 4) : 0u;
+        const uint32_t cr = q < 15 ? *reinterpret_cast<const uint32_t *>(rowp + 16) : 0u;
+        // east = pixel x+3, west = pixel x-3 of the same row: byte-shifted views of the row words
+        const uint32_t e0 = byte_perm(C.x, C.y, 0x6543), e1 = byte_perm(C.y, C.z, 0x6543);
+        const uint32_t e2 = byte_perm(C.z, C.w, 0x6543), e3 = byte_perm(C.w, cr, 0x6543);
+        const uint32_t w0 = byte_perm(cl, C.x, 0x4321), w1 = byte_perm(C.x, C.y, 0x4321);
+        const uint32_t w2 = byte_perm(C.y, C.z, 0x4321), w3 = byte_perm(C.z, C.w, 0x4321);
+        uint32_t f[4];
+        f[0] = filter4(C.x, N.x, S.x, e0, w0, kbias, vm[0]);
+        f[1] = filter4(C.y, N.y, S.y, e1, w1, kbias, vm[1]);
+        f[2] = filter4(C.z, N.z, S.z, e2, w2, kbias, vm[2]);
+        f[3] = filter4(C.w, N.w, S.w, e3, w3, kbias, vm[3]);
+        if ((f[0] | f[1] | f[2] | f[3]) != 0u) {
+            const int cnt = popc32(f[0]) + popc32(f[1]) + popc32(f[2]) + popc32(f[3]);
+            uint32_t slot = atomic_add_u32(qcount, (uint32_t)cnt);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t m = f[k];
+                while (m) {
+                    const int bit = lowest_set_bit(m);  // 7, 15, 23 or 31
+                    m &= m - 1u;
+                    queue[slot++] = (uint16_t)((rr << 8) | (q * 16 + k * 4 + (bit >> 3)));
+                }
+            }
+        }
+    }
+}
+
+// ---- phase B: exact segment test (+ score) per candidate (replaces fast_simd.rs:115-297, 623-749)
+// Off mode: sets the keypoint's bit in the strip bit plane.  NMS modes: writes the score into the
+// score plane and marks the queue entry as a confirmed keypoint (bit 15).
+template <int MODE, int SR>
+FDF_HD void phase_b(int tid, uint32_t qn, const uint8_t *tile, uint16_t *queue, uint16_t *plane, uint32_t *bits,
+                    const ChunkGeo &g, int t, int n) {
+    for (uint32_t i = (uint32_t)tid; i < qn; i += kThreads) {
+        const uint32_t ent = queue[i];
+        const int rr = (int)(ent >> 8), j = (int)(ent & 0xffu);
+        const uint8_t *pc = tile + (rr + 3) * kTileW + j;
+        const int cv = pc[0];
+        int ring[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) ring[k] = pc[FDF_RING_DY(k) * kTileW + FDF_RING_DX(k)];
+        const RingMasks rm = ring_masks(cv, ring, t);
+        const bool arc_bright = has_arc(rm.bright, n);
+        const bool arc_dark = has_arc(rm.dark, n);
+        if (arc_bright || arc_dark) {
+            if (MODE == NMS_OFF) {
+                const int x = g.xt0 + j;
+                atomic_or_u32(&bits[rr * g.ww + (x >> 5)], 1u << (x & 31));
+            } else {
+                const uint32_t sc = (MODE == NMS_MAX_THRESHOLD) ? score_max_threshold(cv, ring, n, arc_bright)
+                                                                : score_sum_abs(cv, ring, t);
+                plane[rr * kTileW + j] = (uint16_t)sc;
+                queue[i] = (uint16_t)(ent | 0x8000u);
+            }
+        }
+    }
+}
+
+// ---- NMS pass: strict maximum over the 8 neighbours (replaces fast_simd.rs:588-616) ------------
+// Only this chunk's own columns and this strip's own rows are emitted; rows 3 and h-4 are scored
+// (they act as neighbours) but never emitted (fast_simd.rs:589-596, opencv_compat.rs:238-240).
+template <int MODE, int SR>
+FDF_HD void nms_pass(int tid, uint32_t qn, const uint16_t *queue, const uint16_t *plane, uint32_t *bits,
+                     const ChunkGeo &g) {
+    for (uint32_t i = (uint32_t)tid; i < qn; i += kThreads) {
+        const uint32_t ent = queue[i];
+        if (!(ent & 0x8000u)) continue;
+        const int rr = (int)((ent >> 8) & 0x7fu), j = (int)(ent & 0xffu);
+        const int y = g.ys0 + rr;
+        if (rr < 1 || rr > SR - 2 || j < kHaloX || j >= kHaloX + kChunkW || y >= g.h - 4) continue;
+        const uint16_t *pp = plane + rr * kTileW + j;
+        const uint32_t s = pp[0];
+        const bool keep = s > pp[-kTileW - 1] && s > pp[-kTileW] && s > pp[-kTileW + 1] && s > pp[-1] && s > pp[1] &&
+                          s > pp[kTileW - 1] && s > pp[kTileW] && s > pp[kTileW + 1];
+        if (keep) {
+            const int x = g.xt0 + j;
+            atomic_or_u32(&bits[(rr - 1) * g.ww + (x >> 5)], 1u << (x & 31));
+        }
+    }
+}
+
+// ---- emission: this thread's contiguous share of the strip bit plane ------------------------------
+struct EmitRange {
+    int begin, end;  // word indices into bits[out_rows * ww]
+};
+
+FDF_HD EmitRange emit_range(int tid, int nwords) {
+    const int wpt = (nwords + kThreads - 1) / kThreads;
+    EmitRange r;
+    r.begin = min(tid * wpt, nwords);
+    r.end = min(r.begin + wpt, nwords);
+    return r;
+}
+
+FDF_HD uint32_t emit_count(const uint32_t *bits, EmitRange r) {
+    uint32_t cnt = 0;
+    for (int i = r.begin; i < r.end; i++) cnt += (uint32_t)popc32(bits[i]);
+    return cnt;
+}
+
+// writes the points of this thread's words, in row-major order, starting at index o
+FDF_HD void emit_points(const uint32_t *bits, EmitRange r, const ChunkGeo &g, unsigned long long o,
+                        unsigned long long cap, uint2 *out) {
+    for (int i = r.begin; i < r.end; i++) {
+        uint32_t m = bits[i];
+        if (m == 0u) continue;
+        const int row = i / g.ww;
+        const uint32_t xw = (uint32_t)(i - row * g.ww) * 32u, y = (uint32_t)(g.y0 + row);
+        while (m) {
+            const int b = lowest_set_bit(m);
+            m &= m - 1u;
+            if (o < cap) {
+                out[o].x = xw + (uint32_t)b;
+                out[o].y = y;
+            }
+            o++;
+        }
+    }
+}
+
+}  // namespace fdf

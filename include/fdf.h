@@ -1,0 +1,118 @@
+/*
+ * fdf.h -- C ABI of libfdf_cuda.so, the B200 (sm_100a) FAST-n corner detector.
+ *
+ * This is the drop-in boundary for the detection path of iwanders/feature_detector_fast.  Each
+ * entry point names the reference interface it replaces (paths into the reference checkout).
+ * Plain pointers and sizes only; nothing here unwinds or throws: every call returns an fdf_status.
+ *
+ * Semantics reproduced bit for bit (see DESIGN.md / SURVEY.md section 3.1): centres
+ * x in [3, w-3), y in [3, h-3); brighter <=> p > c+t, darker <=> p < c-t (strict); keypoint <=>
+ * a cyclic run of >= count ring pixels all brighter or all darker; NMS keeps a keypoint iff its
+ * score is strictly greater than its 8 neighbours' and never emits rows 3 and h-4; output is
+ * row-major (y, then x).
+ */
+#ifndef FDF_H
+#define FDF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* lib.rs:15-20  `pub struct Point { pub x: u32, pub y: u32 }`  (#[repr(C)] mirror) */
+typedef struct fdf_point {
+    uint32_t x;
+    uint32_t y;
+} fdf_point;
+
+/* lib.rs:25-36  `pub enum NonMaximalSuppression { Off, MaxThreshold, SumAbsolute }`
+ * numbered like fast_simd.rs:74-76 (NONMAX_DISABLED / NONMAX_MAX_THRESHOLD / NONMAX_SUM_ABSOLUTE) */
+enum {
+    FDF_NMS_OFF = 0,
+    FDF_NMS_MAX_THRESHOLD = 1,
+    FDF_NMS_SUM_ABSOLUTE = 2
+};
+
+typedef enum fdf_status {
+    FDF_OK = 0,
+    FDF_ERR_INVALID_COUNT = 1,   /* count outside 9..=16: the reference panics (fast_simd.rs:302-305, :797-801) */
+    FDF_ERR_INVALID_NMS = 2,     /* nms not one of FDF_NMS_* */
+    FDF_ERR_INVALID_ARGUMENT = 3,/* null pointer, pitch < width, misaligned device buffer, ... */
+    FDF_ERR_CAPACITY = 4,        /* output buffer too small; *n_out / offsets[n_frames] hold the needed size */
+    FDF_ERR_CUDA = 5,            /* a CUDA call failed; see fdf_last_error() */
+    FDF_ERR_NO_DEVICE = 6,       /* no usable sm_100 device */
+    FDF_ERR_INTERNAL = 7         /* device-side consistency check failed (look-back timeout) */
+} fdf_status;
+
+/* One context per host thread and device: owns a stream, the scan workspace and the staging
+ * buffers of the host-memory entry points.  Not thread-safe; create one per thread (the reference
+ * function is pure and re-entrant: lib.rs:62-64). */
+typedef struct fdf_ctx fdf_ctx;
+
+fdf_status fdf_create(int device, fdf_ctx **out_ctx);
+void fdf_destroy(fdf_ctx *ctx);
+
+/*
+ * Replaces `feature_detector_fast::detect(img: &GrayImage, config: &Config) -> Vec<Point>`
+ * (lib.rs:62-64), `Config::detect` (lib.rs:54-59) and `fast_simd::detector` (fast_simd.rs:847-859).
+ *
+ * img: HOST memory, h rows of w bytes, `pitch` bytes between rows (GrayImage: pitch == w,
+ * fast_simd.rs:307-308, 330).  threshold / count / nms are Config's three fields (lib.rs:38-52).
+ * Writes up to `cap` points to the HOST array `out` in the reference's order and the number found
+ * to *n_out.  If more than cap were found, returns FDF_ERR_CAPACITY with *n_out = number found
+ * (the first cap points are valid).  w < 7 or h < 7 yields 0 points.
+ */
+fdf_status fdf_detect(fdf_ctx *ctx, const uint8_t *img, uint32_t w, uint32_t h, uint32_t pitch,
+                      uint8_t threshold, uint8_t count, uint8_t nms, fdf_point *out, size_t cap,
+                      size_t *n_out);
+
+/*
+ * The same detector over a batch of n_frames equally sized frames in HOST memory (frame f starts
+ * at frames + f * frame_stride).  Output is CSR: the points of frame f are
+ * out[offsets[f] .. offsets[f+1]) ; offsets has n_frames + 1 entries, offsets[0] == 0.
+ * The timed region of an end-to-end measurement is exactly one call of this function
+ * (host->device copy, kernels, device->host copy of offsets and points).
+ */
+fdf_status fdf_detect_batch(fdf_ctx *ctx, const uint8_t *frames, uint32_t n_frames, uint32_t w,
+                            uint32_t h, uint32_t pitch, uint64_t frame_stride, uint8_t threshold,
+                            uint8_t count, uint8_t nms, fdf_point *out, size_t cap,
+                            uint64_t *offsets);
+
+/*
+ * Device-resident, asynchronous form (what a GPU producer upstream of the detector calls):
+ * d_frames, d_out and d_offsets are DEVICE pointers; work is enqueued on `stream` (a
+ * cudaStream_t; NULL = the context's own stream) and the call returns without synchronising.
+ * d_frames must be 16-byte aligned with pitch and frame_stride multiples of 16 (TMA tensor-map
+ * requirements); otherwise FDF_ERR_INVALID_ARGUMENT.  d_offsets receives n_frames + 1 entries;
+ * if offsets[n_frames] > cap the points beyond cap were dropped.
+ * Uses the context's scan workspace: calls on one context must be stream-ordered.
+ */
+fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_frames, uint32_t w,
+                             uint32_t h, uint32_t pitch, uint64_t frame_stride, uint8_t threshold,
+                             uint8_t count, uint8_t nms, fdf_point *d_out, size_t cap,
+                             uint64_t *d_offsets, void *stream);
+
+/* Fills device memory with the synthetic frames used by the tests and the benchmark (bit-identical
+ * to oracle/fdf_oracle.c: fdf_oracle_synth_frame).  Frame f of the output is generator frame
+ * first_frame + f.  kind 0 = scene, 1 = uniform noise; amp = noise amplitude of kind 0. */
+fdf_status fdf_synth_frames_device(fdf_ctx *ctx, uint8_t *d_frames, uint32_t n_frames, uint32_t w,
+                                   uint32_t h, uint32_t pitch, uint64_t frame_stride, uint64_t seed,
+                                   uint32_t first_frame, uint32_t kind, uint32_t amp, void *stream);
+
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t fdf_kernel_launches(const fdf_ctx *ctx);
+
+/* Device-side flags of the last fdf_detect_device-family call on this context, read back with a
+ * synchronising copy: 0 = clean, bit 0 = look-back wait timed out (result invalid). */
+fdf_status fdf_check_device_flags(fdf_ctx *ctx, uint32_t *flags);
+
+const char *fdf_last_error(const fdf_ctx *ctx);
+const char *fdf_status_string(fdf_status status);
+const char *fdf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDF_H */

@@ -1,0 +1,153 @@
+// strip_emulator.cpp -- runs the detection kernel's per-thread phase bodies (fdf_strip.cuh, the
+// same source the GPU executes) thread by thread on the CPU, with the TMA load replaced by a
+// zero-filled copy and the decoupled look-back replaced by a running offset.  TEST CODE ONLY:
+// it exists so the tiling / halo / validity / NMS-row logic and the SWAR arithmetic can be checked
+// against the oracle in the CPU-only test tier.  It is not a CPU fallback: the product library
+// never contains or calls it.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../feature_detector_fast_b200/csrc/fdf_strip.cuh"
+#include "../../oracle/fdf_oracle.h"
+
+namespace {
+
+using namespace fdf;
+
+template <int MODE, int SR>
+int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2 *out, size_t cap) {
+    constexpr int OUT_R = out_rows(MODE, SR);
+    constexpr int TR = tile_rows(SR);
+    const long long rows = (long long)h - 2 * first_out_row(MODE);
+    if (w < 7 || h < 7 || rows <= 0) return 0;
+    const int S = (int)((rows + OUT_R - 1) / OUT_R);
+    const int NC = (w - 3 + kChunkW - 1) / kChunkW;
+    const int WW = (w + 31) / 32;
+    alignas(16) static uint8_t tile[tile_rows(64) * kTileW];
+    std::vector<uint16_t> plane((size_t)SR * kTileW), queue((size_t)SR * kTileW);
+    std::vector<uint32_t> bits((size_t)OUT_R * WW);
+    const uint32_t kbias = filter_kbias((uint32_t)t);
+    unsigned long long total = 0;
+    for (int strip = 0; strip < S; strip++) {
+        std::fill(bits.begin(), bits.end(), 0u);
+        for (int c = 0; c < NC; c++) {
+            const ChunkGeo g = make_geo<MODE>(w, h, WW, strip, c, SR);
+            const int ty0 = g.ys0 - 3;
+            for (int r = 0; r < TR; r++)      // what the TMA tiled load delivers: zero fill outside the image
+                for (int j = 0; j < kTileW; j++) {
+                    const int y = ty0 + r, x = g.xt0 + j;
+                    tile[r * kTileW + j] = (y >= 0 && y < h && x >= 0 && x < w) ? img[(size_t)y * pitch + x] : 0;
+                }
+            std::fill(plane.begin(), plane.end(), (uint16_t)0);
+            uint32_t qcount = 0;
+            for (int tid = 0; tid < kThreads; tid++) phase_a<MODE, SR>(tid, tile, queue.data(), &qcount, g, kbias);
+            for (int tid = 0; tid < kThreads; tid++)
+                phase_b<MODE, SR>(tid, qcount, tile, queue.data(), plane.data(), bits.data(), g, t, n);
+            if (MODE != NMS_OFF)
+                for (int tid = 0; tid < kThreads; tid++)
+                    nms_pass<MODE, SR>(tid, qcount, queue.data(), plane.data(), bits.data(), g);
+        }
+        const ChunkGeo g0 = make_geo<MODE>(w, h, WW, strip, 0, SR);
+        for (int tid = 0; tid < kThreads; tid++) {
+            const EmitRange er = emit_range(tid, OUT_R * WW);
+            const uint32_t cnt = emit_count(bits.data(), er);
+            emit_points(bits.data(), er, g0, total, cap, out);
+            total += cnt;
+        }
+    }
+    return (int64_t)total;
+}
+
+uint64_t splitmix(uint64_t &s) {
+    s += 0x9E3779B97F4A7C15ULL;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t fdf_emulate_detect(const uint8_t *img, uint32_t w, uint32_t h, uint32_t pitch, uint8_t t, uint8_t n,
+                           uint8_t nms, int sr, fdf_oracle_point *out, size_t cap) {
+    uint2 *o = reinterpret_cast<uint2 *>(out);
+#define CASE(M, S) \
+    if (nms == M && sr == S) return emulate<M, S>(img, (int)w, (int)h, (int)pitch, t, n, o, cap);
+    CASE(0, 16) CASE(0, 32) CASE(1, 16) CASE(1, 32) CASE(2, 16) CASE(2, 32)
+#undef CASE
+    return -1;
+}
+
+// Random (centre, ring, t, n) vectors: device-side arithmetic of fdf_core.cuh against the oracle.
+// Returns the number of disagreements (0 expected).  `style` biases the vectors towards arcs.
+int64_t fdf_core_check(uint64_t iterations, uint64_t seed) {
+    int64_t bad = 0;
+    uint64_t s = seed;
+    for (uint64_t it = 0; it < iterations; it++) {
+        const uint64_t r0 = splitmix(s), r1 = splitmix(s), r2 = splitmix(s);
+        const int style = (int)(r0 & 3);
+        const int c = (int)((r0 >> 8) & 0xff);
+        int t = (int)((r0 >> 16) & 0xff);
+        if (style != 0) t &= 0x3f;
+        const int n = 9 + (int)((r0 >> 24) % 8);
+        uint8_t ring8[16];
+        int ring[16];
+        // style 0: uniform random; 1..3: an arc of random length / sign with jitter plus background
+        const int arc_len = (int)((r0 >> 32) % 17), arc_start = (int)((r0 >> 40) & 15);
+        const int sign = ((r0 >> 44) & 1) ? 1 : -1;
+        for (int i = 0; i < 16; i++) {
+            int v;
+            const int rnd = (int)((i < 8 ? (r1 >> (8 * i)) : (r2 >> (8 * (i - 8)))) & 0xff);
+            if (style == 0) {
+                v = rnd;
+            } else {
+                const bool in_arc = ((i - arc_start) & 15) < arc_len;
+                const int jitter = (rnd & 7) - 3;
+                v = in_arc ? c + sign * (t + 1 + (rnd >> 5) * (style == 3 ? 9 : 1)) + (style == 2 ? jitter : 0)
+                           : c + jitter * (style == 3 ? 5 : 1);
+                v = v < 0 ? 0 : (v > 255 ? 255 : v);
+            }
+            ring8[i] = (uint8_t)v;
+            ring[i] = v;
+        }
+        // oracle
+        uint8_t neg[16], pos[16];
+        for (int i = 0; i < 16; i++) {
+            const int d = c - ring[i];
+            neg[i] = d < 0 && -d > t;
+            pos[i] = d > 0 && d > t;
+        }
+        const bool kp_bright = fdf_oracle_consecutive(neg, 16, n), kp_dark = fdf_oracle_consecutive(pos, 16, n);
+        // device arithmetic
+        const RingMasks rm = ring_masks(c, ring, t);
+        uint32_t mb = 0, md = 0;
+        for (int i = 0; i < 16; i++) {
+            mb |= (uint32_t)neg[i] << i;
+            md |= (uint32_t)pos[i] << i;
+        }
+        if ((rm.bright & 0xffffu) != mb || (rm.dark & 0xffffu) != md) bad++;
+        const bool ab = has_arc(rm.bright & 0xffffu, n), ad = has_arc(rm.dark & 0xffffu, n);
+        if (ab != kp_bright || ad != kp_dark) bad++;
+        if (score_sum_abs(c, ring, t) != fdf_oracle_score_sum_abs_px((uint8_t)c, ring8, (uint8_t)t)) bad++;
+        if (ab || ad) {
+            if (score_max_threshold(c, ring, n, ab) != fdf_oracle_score_max_threshold_px((uint8_t)c, ring8, (uint8_t)n))
+                bad++;
+            // the filter must pass every keypoint: put the centre in each byte lane in turn
+            for (int lane = 0; lane < 4; lane++) {
+                const uint32_t other = (uint32_t)splitmix(s);
+                auto put = [&](int v) { return (other & ~(0xffu << (8 * lane))) | ((uint32_t)v << (8 * lane)); };
+                const uint32_t f = filter4(put(c), put(ring[0]), put(ring[8]), put(ring[4]), put(ring[12]),
+                                           filter_kbias((uint32_t)t), 0x80808080u);
+                if (!((f >> (8 * lane + 7)) & 1u)) bad++;
+            }
+        }
+    }
+    return bad;
+}
+
+}  // extern "C"
