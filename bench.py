@@ -1,0 +1,356 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the FAST-n detection path on B200, one JSON line on stdout (rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[4]): a batch of synthetic 3840x2160 grey frames, threshold 20, count 9,
+max-threshold NMS.  One "step" = one pass of the detection path over this rank's resident batch
+(512 frames per GPU; frames are independent units, so ranks share nothing on the data path and the job is
+weak-scaled: N GPUs process N x 512 frames per step) followed, for N > 1, by the path's only exchange
+step: one NCCL all-gather of per-frame keypoint counts -> global CSR offsets.
+
+  value        Mpix/s, whole job, frames already resident in HBM when the timed region starts
+  e2e          same metric through the C-ABI call `fdf_detect_batch` on HOST (pinned) buffers: host->device
+               copy of the frames and device->host copy of offsets + keypoints inside the timed region
+  roofline     dominant kernel (fdf_detect_kernel): algorithmic bytes (W*H per frame read once + 8 B per
+               keypoint + 8 B per frame offset) / CUDA-event duration of the launch, against the measured
+               HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline AVX2 port of the reference's fast_simd.rs (oracle/fdf_avx2_port.cpp) on the host cores,
+               bounded sample of the same frames (rank 0, N = 1 only); reported, not the target
+
+`--impl reference` times that CPU port alone (the reference crate is Rust and cannot be built in this
+image, so the port stands in for it), with all host threads, on bounded samples of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 3840, 2160
+THRESHOLD, COUNT, NMS = 20, 9, 1
+FRAMES_PER_GPU = 512
+SEED = 20240
+METRIC = "Mpixels/sec (FAST-n detection; also 1080p frames/sec and HBM GB/s vs peak)"
+WORKLOAD = "configs[4]: 512 synthetic 3840x2160 frames per GPU, t=20, n=9, max-threshold NMS"
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def committed_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        return d.get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+        except Exception:
+            return out
+        sm, reasons, smax = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def time_cpu_port(frames_np, n_threads, min_seconds, oracle):
+    """AVX2 port over `frames_np` (F, H, W) with n_threads workers, repeated for >= min_seconds."""
+    f = frames_np.shape[0]
+    reps, t0 = 0, time.perf_counter()
+    counts = None
+    while True:
+        counts, _ = oracle.port_detect_many(frames_np, THRESHOLD, COUNT, NMS, n_threads=n_threads, want_hashes=False)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
+    return (reps * f * W * H) / dt / 1e6, dt, reps, counts
+
+
+def run_reference_arm(args, rank):
+    """CPU port of the reference path, all host threads, bounded samples of the same workload."""
+    if rank != 0:
+        return 0
+    import numpy as np
+
+    import oracle
+
+    oracle.build()
+    cores = host_threads()
+    n = max(cores, 8)
+    frames = np.zeros((n, H, W), np.uint8)
+    for f in range(n):
+        frames[f] = oracle.synth_frame(W, H, SEED, f, 0, 4)
+    pad = np.zeros(frames.size + 64, np.uint8)
+    pad[: frames.size] = frames.reshape(-1)
+    frames = pad[: frames.size].reshape(n, H, W)
+    for _ in range(args.warmup):
+        oracle.port_detect_many(frames, THRESHOLD, COUNT, NMS, n_threads=cores, want_hashes=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.port_detect_many(frames, THRESHOLD, COUNT, NMS, n_threads=cores, want_hashes=False)
+    dt = time.perf_counter() - t0
+    mpix = args.steps * n * W * H / dt / 1e6
+    sample = f"{n} of the workload's 3840x2160 frames per step, one frame per thread, {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(mpix, 2), "unit": "Mpix/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": n, "width": W, "height": H, "threshold": THRESHOLD,
+                   "count": COUNT, "nms": "max_threshold",
+                   "note": "CPU port of fast_simd.rs (the Rust reference cannot be built here: no cargo/rustc)"},
+        "cpu_baseline": {"value": round(mpix, 2), "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(mpix, 2), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "fps_1080p_equiv": round(mpix * 1e6 / (1920 * 1080), 1),
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU (default: the named config)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import feature_detector_fast_b200 as fdf
+    from feature_detector_fast_b200 import sharding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    det = fdf.Detector(local_rank)
+    cfg = fdf.Config(THRESHOLD, COUNT, fdf.NonMaximalSuppression.MaxThreshold)
+    F = args.frames
+    n_total = F * world
+    frames = det.synth_frames(F, W, H, seed=SEED, first_frame=rank * F, kind=0, amp=4)
+    cap = F * 100000  # ~2.4x the expected keypoints of this workload (about 42k per 4K frame); checked below
+    points = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+    offsets = torch.empty(F + 1, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        det.detect_device(frames, cfg, points=points, offsets=offsets)
+        if world > 1:
+            counts = sharding.counts_from_offsets(offsets)
+            return sharding.global_offsets(sharding.gather_frame_counts(counts, n_total))
+        return offsets
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    found = int(offsets[-1].item())
+    if found > cap or det.device_flags() != 0:
+        raise SystemExit(f"bench.py: invalid run (found {found} > cap {cap} or device flags set)")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: exactly K steps, CUDA events, max over ranks --------------------
+    sampler = ClockSampler(local_rank)
+    launches0 = det.kernel_launches
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0.record()
+    for i in range(args.steps):
+        k_ev[i][0].record()
+        det.detect_device(frames, cfg, points=points, offsets=offsets)
+        k_ev[i][1].record()
+        if world > 1:
+            counts = sharding.counts_from_offsets(offsets)
+            sharding.global_offsets(sharding.gather_frame_counts(counts, n_total))
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = det.kernel_launches - launches0
+    total_ms = ev0.elapsed_time(ev1)
+    kern_ms = sum(a.elapsed_time(b) for a, b in k_ev) / args.steps
+    if world > 1:
+        tt = torch.tensor([total_ms, kern_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms, kern_ms = float(tt[0]), float(tt[1])
+    ms_per_step = total_ms / args.steps
+    mpix = n_total * W * H / (ms_per_step * 1e-3) / 1e6
+
+    peak, peak_src = measured_hbm_peak()
+    algo_bytes = F * W * H + 8 * found + 8 * (F + 1)
+    achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": committed_traffic(), "peak_source": peak_src,
+                "kernel": "fdf_detect_kernel<MaxThreshold,32>", "kernel_ms": round(kern_ms, 4),
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "read_only_frac": round(F * W * H / (kern_ms * 1e-3) / 1e9 / peak, 4)}
+
+    # ---- end to end through the C ABI with host (pinned) buffers ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_frames = torch.empty((F, H, W), dtype=torch.uint8, pin_memory=True)
+        h_frames.copy_(frames)
+        h_points = torch.empty((cap, 2), dtype=torch.int32, pin_memory=True)
+        h_offsets = torch.empty(F + 1, dtype=torch.int64, pin_memory=True)
+        torch.cuda.synchronize()
+        e2e_steps = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            det.detect_batch_pinned(h_frames.data_ptr(), F, W, H, cfg, h_points.data_ptr(), cap, h_offsets.data_ptr())
+            return int(h_offsets[F])  # the device->host read of the step's result
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            k = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt[0])
+        assert k == found, "end-to-end path found a different number of keypoints"
+        e2e = {"value": round(n_total * W * H * e2e_steps / dt / 1e6, 1), "unit": "Mpix/s",
+               "h2d_bytes_per_step": F * W * H, "d2h_bytes_per_step": 8 * (F + 1) + 8 * found + 4,
+               "steps": e2e_steps, "ms_per_step": round(dt / e2e_steps * 1e3, 3),
+               "api": "fdf_detect_batch (C ABI, pinned host buffers)"}
+        del h_frames, h_points
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only), which also re-checks the GPU counts ---------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        oracle.build()
+        cores = host_threads()
+        n_s = min(F, max(8, 2 * cores))
+        sample = frames[:n_s].cpu().numpy()
+        pad = np.zeros(sample.size + 64, np.uint8)
+        pad[: sample.size] = sample.reshape(-1)
+        sample = pad[: sample.size].reshape(n_s, H, W)
+        one_mpix, _, _, _ = time_cpu_port(sample[:4], 1, 4.0, oracle)
+        all_mpix, dt_all, reps, counts = time_cpu_port(sample, cores, 8.0, oracle)
+        gpu_counts = (offsets[1:n_s + 1] - offsets[:n_s]).cpu().numpy()
+        if not (gpu_counts == counts).all():
+            raise SystemExit("bench.py: GPU keypoint counts differ from the CPU port on the sampled frames")
+        cpu = {"value": round(all_mpix, 1), "unit": "Mpix/s", "cores": cores, "kind": "port",
+               "sample": f"{n_s} of the batch's frames x {reps} passes, one frame per thread ({dt_all:.1f} s); "
+                         f"single thread on 4 frames: {one_mpix:.1f} Mpix/s",
+               "single_thread_value": round(one_mpix, 1), "counts_match_gpu": True}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(mpix, 1), "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu": F, "width": W, "height": H, "threshold": THRESHOLD,
+                       "count": COUNT, "nms": "max_threshold", "keypoints_per_step_rank0": found,
+                       "l2": "inputs larger than L2 (4.2 GB per GPU per step vs 126 MB)",
+                       "collective": "all_gather of per-frame counts (NCCL)" if world > 1 else "none (1 GPU)"},
+            "fps_1080p_equiv": round(mpix * 1e6 / (1920 * 1080), 1),
+            "fps_4k": round(mpix * 1e6 / (W * H), 1),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    det.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -263,7 +263,7 @@ int fdf_avx2_port_detect_batch(const uint8_t *frames, uint32_t n_frames, uint32_
     if (nms > FDF_ORACLE_NMS_SUM_ABSOLUTE) return -2;
     if (n_threads == 0) n_threads = 1;
     auto worker = [&](uint32_t k) {
-        std::vector<fdf_oracle_point> pts((size_t)w * h / 4 + 16);
+        std::vector<fdf_oracle_point> pts((size_t)w * h / 64 + 16);
         for (uint32_t f = k; f < n_frames; f += n_threads) {
             const uint8_t *img = frames + (size_t)f * frame_stride;
             int64_t c = fdf_avx2_port_detect(img, w, h, pitch, t, n, nms, pts.data(), pts.size());

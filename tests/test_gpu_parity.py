@@ -1,0 +1,208 @@
+"""Parity of the CUDA path against the oracle and the reference's golden vectors, through the C ABI.
+
+Bit-exact (integer work): keypoint sets AND order must be identical.  Needs a B200: `-m gpu`."""
+import numpy as np
+import pytest
+
+from conftest import same_points
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(t, n, nms):
+    import feature_detector_fast_b200 as fdf
+
+    return fdf.Config(threshold=t, count=n, non_maximal_supression=fdf.NonMaximalSuppression(nms))
+
+
+def test_library_loaded_is_the_in_tree_cuda_build(detector):
+    import feature_detector_fast_b200 as fdf
+
+    assert fdf.LIB_PATH.endswith("feature_detector_fast_b200/lib/libfdf_cuda.so")
+    assert detector.kernel_launches == 0 or detector.kernel_launches > 0
+
+
+def test_shipped_golden_renders(detector, golden):
+    """tests/compare.rs configs on media/Screenshot315_torch_grey.png against the shipped renders."""
+    before = detector.kernel_launches
+    assert same_points(detector.detect_array(golden["grey"], _cfg(16, 9, 0)), golden["rust_off"])
+    assert same_points(detector.detect_array(golden["grey"], _cfg(16, 9, 1)), golden["rust_nonmax"])
+    assert detector.kernel_launches == before + 2  # the CUDA kernels really ran
+    assert detector.device_flags() == 0
+
+
+def test_compare_rs_configs_against_oracle(detector, oracle_mod, golden):
+    # tests/compare.rs:66-114 (+ the Off variants and the threshold extremes)
+    for t, n, nms in [(16, 9, 0), (16, 9, 1), (16, 9, 2), (16, 12, 2), (32, 12, 2), (16, 12, 0), (16, 16, 0),
+                      (0, 9, 1), (0, 9, 2), (255, 9, 0), (130, 10, 1), (127, 9, 2), (128, 9, 2)]:
+        got = detector.detect_array(golden["grey"], _cfg(t, n, nms))
+        assert same_points(got, oracle_mod.detect(golden["grey"], t, n, nms)), (t, n, nms)
+
+
+def test_public_detect_returns_points(golden):
+    import feature_detector_fast_b200 as fdf
+
+    cfg = fdf.Config(16, 9, fdf.NonMaximalSuppression.MaxThreshold)
+    pts = fdf.detect(golden["grey"], cfg)
+    assert pts == [fdf.Point(int(x), int(y)) for x, y in golden["rust_nonmax"]]
+    assert cfg.detect(golden["grey"]) == pts
+
+
+def test_known_answer_vector(detector, oracle_mod):
+    # fast_simd.rs:950-1022: 128x128 black image, centre (64,64)=17 with the hand ring -> keypoint
+    ring = [37, 37, 39, 39, 37, 42, 43, 16, 14, 13, 15, 16, 15, 38, 37, 38]
+    img = np.zeros((128, 128), np.uint8)
+    img[64, 64] = 17
+    for (dx, dy), v in zip(oracle_mod.circle().tolist(), ring):
+        img[64 + dy, 64 + dx] = v
+    got = detector.detect_array(img, _cfg(16, 9, 0))
+    assert [64, 64] in got.tolist()
+    assert same_points(got, oracle_mod.detect(img, 16, 9, 0))
+
+
+@pytest.mark.parametrize("n", range(9, 17))
+def test_count_sweep_1080p(detector, oracle_mod, n):
+    """BASELINE config 4: n = 9..16 on synthetic 1080p noise+edge frames, all three modes."""
+    img = oracle_mod.synth_frame(1920, 1080, seed=4, frame=n, kind=0, amp=6)
+    for nms in (0, 1, 2):
+        got = detector.detect_array(img, _cfg(16, n, nms))
+        assert same_points(got, oracle_mod.port_detect(img, 16, n, nms)), (n, nms)
+    # the scalar oracle itself on one mode (the port is validated against it in the CPU tier)
+    assert same_points(detector.detect_array(img, _cfg(16, n, 1)), oracle_mod.detect(img, 16, n, 1))
+
+
+def test_1080p_three_modes(detector, oracle_mod):
+    """BASELINE configs 1-3 (t=16, n=9, Off / MaxThreshold / SumAbsolute) on a synthetic 1080p frame."""
+    img = oracle_mod.synth_frame(1920, 1080, seed=1234, frame=0, kind=0, amp=4)
+    for nms in (0, 1, 2):
+        assert same_points(detector.detect_array(img, _cfg(16, 9, nms)), oracle_mod.detect(img, 16, 9, nms))
+
+
+def test_widths_heights_and_tiny_images(detector, oracle_mod):
+    for w, h in [(7, 7), (8, 8), (9, 9), (16, 9), (6, 30), (30, 6), (31, 17), (239, 20), (240, 21), (241, 22),
+                 (247, 33), (248, 34), (255, 35), (256, 36), (257, 37), (300, 38), (479, 39), (481, 40),
+                 (487, 64), (70, 65), (70, 66), (70, 67), (70, 68), (70, 69), (1000, 70)]:
+        img = oracle_mod.synth_frame(w, h, seed=w * 1000 + h, frame=0, kind=1)
+        for nms in (0, 1, 2):
+            got = detector.detect_array(img, _cfg(30, 9, nms))
+            assert same_points(got, oracle_mod.detect(img, 30, 9, nms)), (w, h, nms)
+
+
+def test_pitch_larger_than_width(detector, oracle_mod):
+    big = oracle_mod.synth_frame(400, 100, seed=9, frame=0, kind=0, amp=8)
+    view = big[:, 13:313]  # 300 wide, pitch 400, misaligned start
+    assert same_points(detector.detect_array(view, _cfg(16, 9, 1)),
+                       oracle_mod.detect(np.ascontiguousarray(view), 16, 9, 1))
+
+
+def test_uniform_noise_dense_keypoints(detector, oracle_mod):
+    img = oracle_mod.synth_frame(640, 480, seed=1, frame=0, kind=1)
+    for t, nms in [(16, 0), (16, 1), (16, 2), (0, 0), (60, 2)]:
+        assert same_points(detector.detect_array(img, _cfg(t, 9, nms)), oracle_mod.port_detect(img, t, 9, nms))
+
+
+def test_exact_ties_binary_image(detector, oracle_mod):
+    rng = np.random.default_rng(3)
+    img = (rng.integers(0, 2, (200, 520)) * 200).astype(np.uint8)
+    for nms in (0, 1, 2):
+        assert same_points(detector.detect_array(img, _cfg(50, 9, nms)), oracle_mod.detect(img, 50, 9, nms))
+
+
+def test_invalid_count_panics_like_the_reference(detector):
+    import feature_detector_fast_b200 as fdf
+
+    img = np.zeros((32, 32), np.uint8)
+    for bad in (8, 17, 0, 255):  # fast_simd.rs:302-305 and :797-801
+        with pytest.raises(fdf.FdfPanic):
+            detector.detect_array(img, _cfg(16, bad, 0))
+
+
+def test_capacity_overflow_reports_needed_size(detector, oracle_mod):
+    import feature_detector_fast_b200 as fdf
+
+    img = oracle_mod.synth_frame(320, 200, seed=2, frame=0, kind=1)
+    want = oracle_mod.detect(img, 16, 9, 0)
+    assert len(want) > 100
+    with pytest.raises(fdf.FdfError) as ei:
+        detector.detect_array(img, _cfg(16, 9, 0), cap=100)
+    assert ei.value.status == 4
+
+
+def test_batch_csr_output(detector, oracle_mod):
+    frames = np.stack([oracle_mod.synth_frame(400, 130, seed=77, frame=f, kind=0, amp=5) for f in range(9)])
+    for nms in (0, 1, 2):
+        pts, offs = detector.detect_batch(frames, _cfg(20, 9, nms))
+        assert offs[0] == 0 and len(offs) == 10 and offs[-1] == len(pts)
+        for f in range(9):
+            assert same_points(pts[int(offs[f]):int(offs[f + 1])], oracle_mod.detect(frames[f], 20, 9, nms)), (f, nms)
+
+
+def test_gpu_generator_equals_oracle_generator(detector, oracle_mod):
+    for kind, amp in [(0, 4), (0, 9), (1, 0)]:
+        dev = detector.synth_frames(3, 333, 77, seed=5, first_frame=2, kind=kind, amp=amp)
+        host = dev.cpu().numpy()
+        for f in range(3):
+            assert np.array_equal(host[f], oracle_mod.synth_frame(333, 77, 5, 2 + f, kind, amp))
+
+
+def test_device_resident_path(detector, oracle_mod):
+    import torch
+
+    frames = detector.synth_frames(6, 1920, 1080, seed=31, first_frame=0, kind=0, amp=4)
+    pts, offs = detector.detect_device(frames, _cfg(20, 9, 1))
+    torch.cuda.synchronize()
+    assert detector.device_flags() == 0
+    offs_h = offs.cpu().numpy()
+    pts_h = pts[: int(offs_h[-1])].cpu().numpy().astype(np.uint32)
+    host = frames.cpu().numpy()
+    for f in range(6):
+        assert same_points(pts_h[offs_h[f]:offs_h[f + 1]], oracle_mod.port_detect(host[f], 20, 9, 1)), f
+
+
+def test_misaligned_device_buffer_is_rejected(detector):
+    import torch
+
+    import feature_detector_fast_b200 as fdf
+
+    frames = torch.zeros((2, 50, 301), dtype=torch.uint8, device="cuda")  # pitch 301: not a multiple of 16
+    with pytest.raises(fdf.FdfError) as ei:
+        detector.detect_device(frames, _cfg(16, 9, 0))
+    assert ei.value.status == 3
+
+
+def test_4k_batch_config5_sample(detector, oracle_mod):
+    """BASELINE config 5 geometry (3840x2160, t=20, n=9, MaxThreshold) on a 24-frame resident batch:
+    every frame's keypoint count and compare.rs-format hash equal the AVX2 port's; three frames are also
+    compared point by point."""
+    import torch
+
+    n = 24
+    frames = detector.synth_frames(n, 3840, 2160, seed=2024, first_frame=0, kind=0, amp=4)
+    pts, offs = detector.detect_device(frames, _cfg(20, 9, 1))
+    torch.cuda.synchronize()
+    assert detector.device_flags() == 0
+    offs_h = offs.cpu().numpy()
+    pts_h = pts[: int(offs_h[-1])].cpu().numpy().astype(np.uint32)
+    host = frames.cpu().numpy()
+    counts, hashes = oracle_mod.port_detect_many(host, 20, 9, 1, n_threads=8)
+    assert (np.diff(offs_h) == counts).all()
+    for f in range(n):
+        assert oracle_mod.hash_points(pts_h[offs_h[f]:offs_h[f + 1]]) == int(hashes[f]), f
+    for f in (0, 11, 23):
+        assert same_points(pts_h[offs_h[f]:offs_h[f + 1]], oracle_mod.port_detect(host[f], 20, 9, 1))
+    # size-independent properties: row-major order inside every frame, centres inside the NMS emit range
+    for f in range(n):
+        p = pts_h[offs_h[f]:offs_h[f + 1]].astype(np.int64)
+        key = p[:, 1] * 3840 + p[:, 0]
+        assert (np.diff(key) > 0).all()
+        assert p[:, 0].min() >= 3 and p[:, 0].max() < 3840 - 3 and p[:, 1].min() >= 4 and p[:, 1].max() <= 2160 - 5
+
+
+def test_idempotent_and_order_independent_of_batching(detector, oracle_mod):
+    """Detecting a frame alone, or as part of a batch, gives the same list (the look-back only adds offsets)."""
+    frames = np.stack([oracle_mod.synth_frame(960, 540, seed=8, frame=f, kind=0, amp=4) for f in range(5)])
+    pts, offs = detector.detect_batch(frames, _cfg(16, 9, 2))
+    for f in range(5):
+        alone = detector.detect_array(frames[f], _cfg(16, 9, 2))
+        assert same_points(pts[int(offs[f]):int(offs[f + 1])], alone)
+        assert same_points(alone, detector.detect_array(frames[f], _cfg(16, 9, 2)))
