@@ -163,7 +163,7 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     fdf_status st = check_config(ctx, count, nms);
     if (st != FDF_OK) return st;
     if (!d_offsets || (!d_out && cap > 0)) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null output pointer");
-    cudaStream_t stream = stream_handle ? reinterpret_cast<cudaStream_t>(stream_handle) : ctx->stream;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_handle);  // NULL = the default stream
     FDF_CUDA(ctx, cudaSetDevice(ctx->device));
 
     const int mode = nms;
@@ -187,7 +187,7 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     p.h = h;
     p.n_frames = n_frames;
     p.strips_per_frame = (uint32_t)((rows + fdf::out_rows(mode, sr) - 1) / fdf::out_rows(mode, sr));
-    p.chunks_per_strip = (w - 3 + fdf::kChunkW - 1) / fdf::kChunkW;
+    p.chunks_per_strip = (uint32_t)fdf::chunks_per_row((int)w);
     p.words_per_row = (w + 31) / 32;
     p.threshold = threshold;
     p.count = count;
@@ -320,7 +320,7 @@ fdf_status fdf_synth_frames_device(fdf_ctx *ctx, uint8_t *d_frames, uint32_t n_f
                                    uint32_t kind, uint32_t amp, void *stream_handle) {
     if (!ctx || !d_frames) return FDF_ERR_INVALID_ARGUMENT;
     if (pitch < w || kind > 1) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "bad synth arguments");
-    cudaStream_t stream = stream_handle ? reinterpret_cast<cudaStream_t>(stream_handle) : ctx->stream;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_handle);  // NULL = the default stream
     FDF_CUDA(ctx, cudaSetDevice(ctx->device));
     FDF_CUDA(ctx, fdf::launch_synth(d_frames, n_frames, w, h, pitch, frame_stride, seed, first_frame, kind, amp, stream));
     ctx->launches += 1;

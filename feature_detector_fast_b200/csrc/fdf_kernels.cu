@@ -193,7 +193,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         const int pre = NC < 2 ? NC : 2;
         for (int c = 0; c < pre; c++) {
             mbar_expect_tx(&full_bar[c], (uint32_t)L::tile_bytes);
-            tma_load_3d(tiles + c * L::tile_bytes, &tmap, c * kChunkW - kHaloX, ty0, (int)frame, &full_bar[c]);
+            tma_load_3d(tiles + c * L::tile_bytes, &tmap, c * kChunkW - kTileLead, ty0, (int)frame, &full_bar[c]);
         }
     }
     for (int i = tid; i < OUT_R * WW; i += kThreads) bits[i] = 0u;
@@ -223,7 +223,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
 
         if (tid == 0 && c + 2 < NC) {
             mbar_expect_tx(&full_bar[stage], (uint32_t)L::tile_bytes);
-            tma_load_3d(tiles + stage * L::tile_bytes, &tmap, (c + 2) * kChunkW - kHaloX, ty0, (int)frame,
+            tma_load_3d(tiles + stage * L::tile_bytes, &tmap, (c + 2) * kChunkW - kTileLead, ty0, (int)frame,
                         &full_bar[stage]);
         }
         if (MODE != NMS_OFF) {

@@ -11,8 +11,13 @@ namespace fdf {
 // (chunk + halo) is staged into shared memory by one TMA 3-D tiled load.
 constexpr int kThreads = 256;   // threads per CTA
 constexpr int kTileW = 256;     // tile width in bytes = TMA box inner extent (the maximum)
-constexpr int kChunkW = 240;    // output columns per chunk
-constexpr int kHaloX = 8;       // tile starts 8 px left of the chunk (4 needed; 8 keeps words aligned)
+constexpr int kChunkW = 240;    // output columns per chunk (the last chunk of a row may take one more)
+constexpr int kTileLead = 16;   // chunk c's tile starts at image column c*kChunkW - kTileLead: TMA needs the
+                                // innermost start coordinate 16-byte aligned (an unaligned one faults)
+constexpr int kLeftHalo = 12;   // the chunk's first output column is tile column 12: left halo 12, right halo 4
+                                // (4 = 3 ring pixels + 1 NMS neighbour)
+
+__host__ __device__ constexpr int chunks_per_row(int w) { return (w + kChunkW - 1) / kChunkW; }
 
 // scored rows per strip (SR) -> staged rows, emitted rows
 __host__ __device__ constexpr int tile_rows(int sr) { return sr + 6; }                             // +-3 ring rows

@@ -6,8 +6,10 @@
 // halo, validity and NMS-row rules are checked against the oracle without a GPU.
 //
 // Geometry (see fdf_kernels.cuh): a strip has SR scored rows; tile row 0 is image row
-// ys0 - 3 where ys0 is the image row of scored row 0; tile column 0 is image column xt0 = x0 - 8
-// where x0 is the chunk's first output column.
+// ys0 - 3 where ys0 is the image row of scored row 0; tile column 0 is image column xt0,
+// where x0 = xt0 + 12 is the chunk's first output column; xt0 = 240*chunk - 16 is a multiple of 16
+// because TMA needs the box's innermost start coordinate 16-byte aligned.  A chunk emits columns
+// [x0, x1): 240 of them, except that the row's last chunk runs to the image's last centre column.
 #pragma once
 #include "fdf_core.cuh"
 #include "fdf_kernels.cuh"
@@ -45,7 +47,8 @@ struct ChunkGeo {
     int ys0;    // image row of scored row 0
     int y0;     // first image row this strip emits
     int x0;     // first image column this chunk emits
-    int xt0;    // image column of tile column 0
+    int x1;     // one past the last image column this chunk emits
+    int xt0;    // image column of tile column 0 (a multiple of 16)
     int ww;     // bit-plane words per row
 };
 
@@ -57,8 +60,9 @@ FDF_HD ChunkGeo make_geo(int w, int h, int ww, int strip, int chunk, int sr) {
     g.ww = ww;
     g.y0 = first_out_row(MODE) + strip * out_rows(MODE, sr);
     g.ys0 = g.y0 - (MODE == NMS_OFF ? 0 : 1);
-    g.x0 = chunk * kChunkW;
-    g.xt0 = g.x0 - kHaloX;
+    g.xt0 = chunk * kChunkW - kTileLead;
+    g.x0 = g.xt0 + kLeftHalo;
+    g.x1 = (chunk == chunks_per_row(w) - 1) ? w - 3 : g.x0 + kChunkW;
     return g;
 }
 
@@ -71,7 +75,7 @@ FDF_HD void phase_a(int tid, const uint8_t *tile, uint16_t *queue, uint32_t *qco
     constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;
     const int q = tid & 15;   // which 16-pixel group of the 256-wide tile row
     const int r0 = tid >> 4;  // first scored row of this thread
-    const int xlo = max(3, g.x0 - HS), xhi = min(g.w - 3, g.x0 + kChunkW + HS);
+    const int xlo = max(3, g.x0 - HS), xhi = min(g.w - 3, g.x1 + HS);
     uint32_t vm[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -159,8 +163,8 @@ FDF_HD void nms_pass(int tid, uint32_t qn, const uint16_t *queue, const uint16_t
         const uint32_t ent = queue[i];
         if (!(ent & 0x8000u)) continue;
         const int rr = (int)((ent >> 8) & 0x7fu), j = (int)(ent & 0xffu);
-        const int y = g.ys0 + rr;
-        if (rr < 1 || rr > SR - 2 || j < kHaloX || j >= kHaloX + kChunkW || y >= g.h - 4) continue;
+        const int y = g.ys0 + rr, xj = g.xt0 + j;
+        if (rr < 1 || rr > SR - 2 || xj < g.x0 || xj >= g.x1 || y >= g.h - 4) continue;
         const uint16_t *pp = plane + rr * kTileW + j;
         const uint32_t s = pp[0];
         const bool keep = s > pp[-kTileW - 1] && s > pp[-kTileW] && s > pp[-kTileW + 1] && s > pp[-1] && s > pp[1] &&

@@ -83,7 +83,7 @@ fdf_status fdf_detect_batch(fdf_ctx *ctx, const uint8_t *frames, uint32_t n_fram
 /*
  * Device-resident, asynchronous form (what a GPU producer upstream of the detector calls):
  * d_frames, d_out and d_offsets are DEVICE pointers; work is enqueued on `stream` (a
- * cudaStream_t; NULL = the context's own stream) and the call returns without synchronising.
+ * cudaStream_t; NULL = the CUDA default stream) and the call returns without synchronising.
  * d_frames must be 16-byte aligned with pitch and frame_stride multiples of 16 (TMA tensor-map
  * requirements); otherwise FDF_ERR_INVALID_ARGUMENT.  d_offsets receives n_frames + 1 entries;
  * if offsets[n_frames] > cap the points beyond cap were dropped.

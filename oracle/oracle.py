@@ -143,15 +143,18 @@ def port_detect_many(frames: np.ndarray, threshold: int, count: int, nms: int, n
     if frames.dtype != np.uint8 or frames.ndim != 3 or not frames.flags.c_contiguous:
         raise TypeError("frames must be a C-contiguous (F, H, W) uint8 array")
     f, h, w = frames.shape
-    base = frames.base if frames.base is not None else frames
-    slack = base.nbytes - (frames.ctypes.data - base.ctypes.data) - frames.nbytes if base is not frames else 0
-    if slack < 4:
+    # the gathers over-read by <= 3 bytes (S17): always hand the port a buffer with slack after the last frame
+    end = frames.ctypes.data + frames.nbytes
+    owner = frames.base
+    has_slack = isinstance(owner, np.ndarray) and owner.flags.c_contiguous and \
+        owner.ctypes.data + owner.nbytes >= end + 4
+    if has_slack:
+        buf = frames
+        ptr = frames.ctypes.data
+    else:
         buf = np.zeros(frames.size + 64, np.uint8)
         buf[: frames.size] = frames.reshape(-1)
         ptr = buf.ctypes.data
-    else:
-        buf = frames
-        ptr = frames.ctypes.data
     counts = np.zeros(f, np.int64)
     hashes = np.zeros(f, np.uint64) if want_hashes else None
     rc = _lib("libfdf_avx2_port.so").fdf_avx2_port_detect_batch(

@@ -24,7 +24,7 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
     const long long rows = (long long)h - 2 * first_out_row(MODE);
     if (w < 7 || h < 7 || rows <= 0) return 0;
     const int S = (int)((rows + OUT_R - 1) / OUT_R);
-    const int NC = (w - 3 + kChunkW - 1) / kChunkW;
+    const int NC = chunks_per_row(w);
     const int WW = (w + 31) / 32;
     alignas(16) static uint8_t tile[tile_rows(64) * kTileW];
     std::vector<uint16_t> plane((size_t)SR * kTileW), queue((size_t)SR * kTileW);
@@ -36,6 +36,7 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
         for (int c = 0; c < NC; c++) {
             const ChunkGeo g = make_geo<MODE>(w, h, WW, strip, c, SR);
             const int ty0 = g.ys0 - 3;
+            if (g.xt0 % 16 != 0) return -16;  // TMA: innermost box start must be 16-byte aligned
             for (int r = 0; r < TR; r++)      // what the TMA tiled load delivers: zero fill outside the image
                 for (int j = 0; j < kTileW; j++) {
                     const int y = ty0 + r, x = g.xt0 + j;
