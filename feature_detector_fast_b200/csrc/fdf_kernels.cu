@@ -208,8 +208,9 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         uint32_t *qc = &qcount[stage];
 
         if (MODE != NMS_OFF) {
-            uint4 *pz = reinterpret_cast<uint4 *>(plane);
-            for (int i = tid; i < L::plane_bytes / 16; i += kThreads) pz[i] = make_uint4(0u, 0u, 0u, 0u);
+            uint4 *pz = reinterpret_cast<uint4 *>(plane) + tid;
+#pragma unroll
+            for (int i = 0; i < L::plane_bytes / 16 / kThreads; i++) pz[i * kThreads] = make_uint4(0u, 0u, 0u, 0u);
         }
         mbar_wait(&full_bar[stage], (uint32_t)((c >> 1) & 1), p.flags);
 
@@ -233,17 +234,13 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     }
 
     // ---- ordered compaction: bit plane -> packed points ------------------------------------------
-    const ChunkGeo g0 = make_geo<MODE>(W, H, WW, (int)strip, 0, SR);
-    const EmitRange er = emit_range(tid, OUT_R * WW);
-    const uint32_t cnt = emit_count(bits, er);
     const int lane = tid & 31, warp = tid >> 5;
-    uint32_t incl = cnt;
+    const EmitRange er = emit_range(warp, OUT_R * WW);
+    uint32_t cnt = 0;
+    for (int i = er.begin + lane; i < er.end; i += 32) cnt += (uint32_t)__popc(bits[i]);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);  // warp total
+    if (lane == 0) warp_sums[warp] = cnt;
     __syncthreads();
     if (warp == 0) {
         const uint32_t ws = lane < kThreads / 32 ? warp_sums[lane] : 0u;
@@ -263,7 +260,28 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         }
     }
     __syncthreads();
-    emit_points(bits, er, g0, *s_base + warp_sums[warp] + (incl - cnt), p.cap, p.out);
+    if (cnt != 0u) {  // warp-uniform: this warp's range holds keypoints
+        unsigned long long o = *s_base + warp_sums[warp];
+        int i = er.begin + lane;
+        int row = i / WW, col = i - row * WW;
+        for (int base = er.begin; base < er.end; base += 32, i += 32) {
+            const uint32_t m = i < er.end ? bits[i] : 0u;
+            const uint32_t c = (uint32_t)__popc(m);
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (m != 0u) emit_word(m, (uint32_t)col * 32u, (uint32_t)(y0 + row), o + (incl - c), p.cap, p.out);
+            o += __shfl_sync(0xffffffffu, incl, 31);
+            col += 32;
+            while (col >= WW) {
+                col -= WW;
+                row++;
+            }
+        }
+    }
 }
 
 __global__ void fdf_synth_kernel(uint8_t *frames, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t pitch,

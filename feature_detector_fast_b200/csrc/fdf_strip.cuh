@@ -67,26 +67,14 @@ FDF_HD ChunkGeo make_geo(int w, int h, int ww, int strip, int chunk, int sr) {
 }
 
 // ---- phase A: dense filter, 16 centres per thread and row (replaces fast_simd.rs:368-520) -------
-// Pushes (scored row << 8 | tile column) of every centre that passes the necessary-condition
-// filter and lies inside the image's centre range and this chunk's scored columns.
+// Pushes (scored row << 8 | tile column) of every centre of a scorable row that passes the
+// necessary-condition filter.  Column validity (image border, chunk halo) is checked in phase B,
+// where it costs a few instructions per candidate instead of mask set-up per thread and chunk.
 template <int MODE, int SR>
 FDF_HD void phase_a(int tid, const uint8_t *tile, uint16_t *queue, uint32_t *qcount, const ChunkGeo &g,
                     uint32_t kbias) {
-    constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;
     const int q = tid & 15;   // which 16-pixel group of the 256-wide tile row
     const int r0 = tid >> 4;  // first scored row of this thread
-    const int xlo = max(3, g.x0 - HS), xhi = min(g.w - 3, g.x1 + HS);
-    uint32_t vm[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        uint32_t m = 0u;
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const int x = g.xt0 + q * 16 + k * 4 + b;
-            if (x >= xlo && x < xhi) m |= 0x80u << (8 * b);
-        }
-        vm[k] = m;
-    }
     for (int rr = r0; rr < SR; rr += kThreads / 16) {
         const int y = g.ys0 + rr;
         if (y < 3 || y >= g.h - 3) continue;  // fast_simd.rs:342
@@ -101,22 +89,19 @@ FDF_HD void phase_a(int tid, const uint8_t *tile, uint16_t *queue, uint32_t *qco
         const uint32_t e2 = byte_perm(C.z, C.w, 0x6543), e3 = byte_perm(C.w, cr, 0x6543);
         const uint32_t w0 = byte_perm(cl, C.x, 0x4321), w1 = byte_perm(C.x, C.y, 0x4321);
         const uint32_t w2 = byte_perm(C.y, C.z, 0x4321), w3 = byte_perm(C.z, C.w, 0x4321);
-        uint32_t f[4];
-        f[0] = filter4(C.x, N.x, S.x, e0, w0, kbias, vm[0]);
-        f[1] = filter4(C.y, N.y, S.y, e1, w1, kbias, vm[1]);
-        f[2] = filter4(C.z, N.z, S.z, e2, w2, kbias, vm[2]);
-        f[3] = filter4(C.w, N.w, S.w, e3, w3, kbias, vm[3]);
-        if ((f[0] | f[1] | f[2] | f[3]) != 0u) {
-            const int cnt = popc32(f[0]) + popc32(f[1]) + popc32(f[2]) + popc32(f[3]);
-            uint32_t slot = atomic_add_u32(qcount, (uint32_t)cnt);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                uint32_t m = f[k];
-                while (m) {
-                    const int bit = lowest_set_bit(m);  // 7, 15, 23 or 31
-                    m &= m - 1u;
-                    queue[slot++] = (uint16_t)((rr << 8) | (q * 16 + k * 4 + (bit >> 3)));
-                }
+        const uint32_t f0 = filter4(C.x, N.x, S.x, e0, w0, kbias, 0x80808080u);
+        const uint32_t f1 = filter4(C.y, N.y, S.y, e1, w1, kbias, 0x80808080u);
+        const uint32_t f2 = filter4(C.z, N.z, S.z, e2, w2, kbias, 0x80808080u);
+        const uint32_t f3 = filter4(C.w, N.w, S.w, e3, w3, kbias, 0x80808080u);
+        if ((f0 | f1 | f2 | f3) != 0u) {
+            // each f has only bit 7 of its bytes set: bit (8*b + k) of gm <=> byte b of word k
+            uint32_t gm = (f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4);
+            uint32_t slot = atomic_add_u32(qcount, (uint32_t)popc32(gm));
+            const uint32_t ent0 = (uint32_t)((rr << 8) | (q * 16));
+            while (gm) {
+                const uint32_t p = (uint32_t)lowest_set_bit(gm);
+                gm &= gm - 1u;
+                queue[slot++] = (uint16_t)(ent0 + ((p & 7u) << 2) + (p >> 3));
             }
         }
     }
@@ -128,9 +113,14 @@ FDF_HD void phase_a(int tid, const uint8_t *tile, uint16_t *queue, uint32_t *qco
 template <int MODE, int SR>
 FDF_HD void phase_b(int tid, uint32_t qn, const uint8_t *tile, uint16_t *queue, uint16_t *plane, uint32_t *bits,
                     const ChunkGeo &g, int t, int n) {
+    constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;
+    // scored columns: the chunk's own columns plus the NMS score halo, inside the image's centre range
+    const int xlo = max(3, g.x0 - HS), xhi = min(g.w - 3, g.x1 + HS);
     for (uint32_t i = (uint32_t)tid; i < qn; i += kThreads) {
         const uint32_t ent = queue[i];
         const int rr = (int)(ent >> 8), j = (int)(ent & 0xffu);
+        const int x = g.xt0 + j;
+        if (x < xlo || x >= xhi) continue;  // fast_simd.rs:369-371, 559-562
         const uint8_t *pc = tile + (rr + 3) * kTileW + j;
         const int cv = pc[0];
         int ring[16];
@@ -141,7 +131,6 @@ FDF_HD void phase_b(int tid, uint32_t qn, const uint8_t *tile, uint16_t *queue, 
         const bool arc_dark = has_arc(rm.dark, n);
         if (arc_bright || arc_dark) {
             if (MODE == NMS_OFF) {
-                const int x = g.xt0 + j;
                 atomic_or_u32(&bits[rr * g.ww + (x >> 5)], 1u << (x & 31));
             } else {
                 const uint32_t sc = (MODE == NMS_MAX_THRESHOLD) ? score_max_threshold(cv, ring, n, arc_bright)
@@ -176,42 +165,31 @@ FDF_HD void nms_pass(int tid, uint32_t qn, const uint16_t *queue, const uint16_t
     }
 }
 
-// ---- emission: this thread's contiguous share of the strip bit plane ------------------------------
+// ---- emission: bit plane -> points, row-major -----------------------------------------------------
+// The strip's bit plane (out_rows x ww words) is cut into kThreads/32 contiguous ranges, one per warp;
+// a warp walks its range 32 words at a time (one word per lane, warp prefix sum for the offsets).
 struct EmitRange {
     int begin, end;  // word indices into bits[out_rows * ww]
 };
 
-FDF_HD EmitRange emit_range(int tid, int nwords) {
-    const int wpt = (nwords + kThreads - 1) / kThreads;
+FDF_HD EmitRange emit_range(int warp, int nwords) {
+    const int wpw = (nwords + kThreads / 32 - 1) / (kThreads / 32);
     EmitRange r;
-    r.begin = min(tid * wpt, nwords);
-    r.end = min(r.begin + wpt, nwords);
+    r.begin = min(warp * wpw, nwords);
+    r.end = min(r.begin + wpw, nwords);
     return r;
 }
 
-FDF_HD uint32_t emit_count(const uint32_t *bits, EmitRange r) {
-    uint32_t cnt = 0;
-    for (int i = r.begin; i < r.end; i++) cnt += (uint32_t)popc32(bits[i]);
-    return cnt;
-}
-
-// writes the points of this thread's words, in row-major order, starting at index o
-FDF_HD void emit_points(const uint32_t *bits, EmitRange r, const ChunkGeo &g, unsigned long long o,
-                        unsigned long long cap, uint2 *out) {
-    for (int i = r.begin; i < r.end; i++) {
-        uint32_t m = bits[i];
-        if (m == 0u) continue;
-        const int row = i / g.ww;
-        const uint32_t xw = (uint32_t)(i - row * g.ww) * 32u, y = (uint32_t)(g.y0 + row);
-        while (m) {
-            const int b = lowest_set_bit(m);
-            m &= m - 1u;
-            if (o < cap) {
-                out[o].x = xw + (uint32_t)b;
-                out[o].y = y;
-            }
-            o++;
+// writes the points of one bit-plane word (row `y`, columns xw .. xw+31) starting at index o
+FDF_HD void emit_word(uint32_t m, uint32_t xw, uint32_t y, unsigned long long o, unsigned long long cap, uint2 *out) {
+    while (m) {
+        const int b = lowest_set_bit(m);
+        m &= m - 1u;
+        if (o < cap) {
+            out[o].x = xw + (uint32_t)b;
+            out[o].y = y;
         }
+        o++;
     }
 }
 

@@ -52,11 +52,14 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
                     nms_pass<MODE, SR>(tid, qcount, queue.data(), plane.data(), bits.data(), g);
         }
         const ChunkGeo g0 = make_geo<MODE>(w, h, WW, strip, 0, SR);
-        for (int tid = 0; tid < kThreads; tid++) {
-            const EmitRange er = emit_range(tid, OUT_R * WW);
-            const uint32_t cnt = emit_count(bits.data(), er);
-            emit_points(bits.data(), er, g0, total, cap, out);
-            total += cnt;
+        for (int warp = 0; warp < kThreads / 32; warp++) {  // the warps' ranges, in order
+            const EmitRange er = emit_range(warp, OUT_R * WW);
+            for (int i = er.begin; i < er.end; i++) {
+                const uint32_t m = bits[i];
+                const int row = i / WW, col = i - row * WW;
+                emit_word(m, (uint32_t)col * 32u, (uint32_t)(g0.y0 + row), total, cap, out);
+                total += (unsigned long long)__builtin_popcount(m);
+            }
         }
     }
     return (int64_t)total;
