@@ -1,21 +1,24 @@
 // fdf_kernels.cu -- sm_100a kernels of the FAST-n detection path.
 //
-// One kernel does the whole path for a batch of frames (replaces fast_simd.rs:301-620):
+// One persistent kernel does the whole path for a batch of frames (replaces fast_simd.rs:301-620):
 //
-//   work item  = (frame, strip of full-width rows); items are handed out through an atomic ticket
-//                in row-major order, which is what makes the decoupled look-back deadlock-free.
-//   per chunk  : TMA 3-D tiled load (u8 tile 256 x (SR+6), zero-filled outside the image, double
-//                buffered, completion on an mbarrier)                          -> shared memory
+//   work item  = (frame, strip of full-width rows), handed out through an atomic ticket in row-major
+//                order, which is what makes the decoupled look-back deadlock-free.
+//   8 compute warps, per chunk of a strip:
+//     TMA 3-D tiled load (u8 tile 256 x (SR+6), zero-filled outside the image, double buffered,
+//     completion on an mbarrier)                                                -> shared memory
 //     phase A  : dense SWAR filter, 16 centres per thread (LDS.128 + PRMT + VABSDIFF4 + LOP3),
-//                survivors pushed to a shared-memory candidate queue          (fast_simd.rs:368-520)
-//     phase B  : one thread per candidate: 16 ring bytes -> brighter/darker 16-bit masks ->
-//                rotate-AND arc test -> score in registers -> score plane      (fast_simd.rs:115-297,
+//                survivors pushed to the warp's own candidate queue            (fast_simd.rs:368-520)
+//     phase B  : one lane per candidate: 16 ring bytes -> brighter/darker 16-bit masks ->
+//                rotate-AND arc test -> score in registers -> tagged score plane (fast_simd.rs:115-297,
 //                                                                                623-749)
+//     one named barrier, then
 //     NMS pass : strict 3x3 maximum on the shared-memory score plane          (fast_simd.rs:588-616)
-//                survivors set one bit in the strip's shared-memory bit plane
-//   per strip  : popcount of the bit plane, block scan, decoupled look-back over all earlier items
-//                of the whole batch, then the bits are expanded to (x, y) points at their final
-//                position: output is packed and row-major per frame (fast_simd.rs:550, 596-613).
+//                survivors set one bit in the strip's shared-memory bit plane (double buffered)
+//   1 emit warp, per finished strip (while the compute warps already work on the next one):
+//     popcount of the bit plane, decoupled look-back over all earlier items of the whole batch,
+//     then the bits are expanded to (x, y) points at their final position: output is packed and
+//     row-major per frame (fast_simd.rs:550, 596-613).
 #include "fdf_kernels.cuh"
 
 #include "fdf_core.cuh"
@@ -46,6 +49,15 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// barrier among the compute warps only (the emit warp never joins it)
+__device__ __forceinline__ void bar_compute() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory");
 }
 
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
@@ -100,12 +112,13 @@ struct Layout {
     static constexpr int TR = tile_rows(SR);
     static constexpr int tile_bytes = TR * kTileW;  // one TMA box
     static constexpr int plane_off = 2 * tile_bytes;
-    static constexpr int plane_bytes = (MODE == NMS_OFF) ? 0 : SR * kTileW * 2;  // u16 scores
+    static constexpr int plane_bytes = (MODE == NMS_OFF) ? 0 : SR * kPlaneW * 2;  // u16: tag << 12 | score
     static constexpr int queue_off = plane_off + plane_bytes;
-    static constexpr int queue_bytes = SR * kTileW * 2;  // u16 entries, worst case every scored pixel
+    static constexpr int queue_per_warp = (SR / kComputeWarps) * kTileW;  // entries: every pixel of the warp's rows
+    static constexpr int queue_bytes = kComputeWarps * queue_per_warp * 2;
     static constexpr int misc_off = queue_off + queue_bytes;
     static constexpr int misc_bytes = 128;
-    static constexpr int bits_off = misc_off + misc_bytes;
+    static constexpr int bits_off = misc_off + misc_bytes;  // two bit planes of out_rows x words_per_row words
     static_assert(tile_bytes % 128 == 0, "TMA destination must stay 128-byte aligned");
     static_assert(SR % 16 == 0 && SR <= 64, "phase A walks rows in steps of 16; queue entries hold 6 row bits");
 };
@@ -161,125 +174,147 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     uint8_t *tiles = smem;
     uint16_t *plane = reinterpret_cast<uint16_t *>(smem + L::plane_off);
     uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L::queue_off);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::misc_off);            // [2]
-    uint32_t *qcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 16);         // [2]
-    uint32_t *s_item = reinterpret_cast<uint32_t *>(smem + L::misc_off + 24);
-    uint32_t *warp_sums = reinterpret_cast<uint32_t *>(smem + L::misc_off + 32);      // [8]
-    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 64);
-    uint32_t *bits = reinterpret_cast<uint32_t *>(smem + L::bits_off);                 // [OUT_R][words_per_row]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::misc_off);             // [2] tile landed
+    uint64_t *bits_full = reinterpret_cast<uint64_t *>(smem + L::misc_off + 16);       // [2] strip finished
+    uint64_t *bits_empty = reinterpret_cast<uint64_t *>(smem + L::misc_off + 32);      // [2] strip emitted
+    uint32_t *qcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 48);          // [8] per-warp queue fill
+    uint32_t *s_item = reinterpret_cast<uint32_t *>(smem + L::misc_off + 80);          // [2] item of each bit plane
+    uint32_t *bits = reinterpret_cast<uint32_t *>(smem + L::bits_off);                  // [2][OUT_R][words_per_row]
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = (int)p.w, H = (int)p.h;
+    const int NC = (int)p.chunks_per_strip;
+    const int WW = (int)p.words_per_row;
+    const int nwords = OUT_R * WW;
+    const uint32_t total_items = p.n_frames * p.strips_per_frame;
+
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
         mbar_init(&full_bar[0], 1);
         mbar_init(&full_bar[1], 1);
+        mbar_init(&bits_full[0], kComputeWarps);
+        mbar_init(&bits_full[1], kComputeWarps);
+        mbar_init(&bits_empty[0], 1);
+        mbar_init(&bits_empty[1], 1);
         fence_mbar_init();
-        qcount[0] = 0;
-        qcount[1] = 0;
-        *s_item = atomicAdd(p.ticket, 1u);  // items start in scan order => look-back cannot deadlock
     }
+    for (int i = tid; i < 2 * nwords; i += kThreads) bits[i] = 0u;
     __syncthreads();
-    const uint32_t item = *s_item;
-    const uint32_t frame = item / p.strips_per_frame;
-    const uint32_t strip = item - frame * p.strips_per_frame;
-    const int W = (int)p.w, H = (int)p.h;
-    const int NC = (int)p.chunks_per_strip;
-    const int WW = (int)p.words_per_row;
-    const int y0 = first_out_row(MODE) + (int)strip * OUT_R;  // first row this strip emits
-    const int ys0 = y0 - HS;                                  // image row of scored row 0
-    const int ty0 = ys0 - 3;                                  // image row of tile row 0
 
-    if (tid == 0) {
-        const int pre = NC < 2 ? NC : 2;
-        for (int c = 0; c < pre; c++) {
-            mbar_expect_tx(&full_bar[c], (uint32_t)L::tile_bytes);
-            tma_load_3d(tiles + c * L::tile_bytes, &tmap, c * kChunkW - kTileLead, ty0, (int)frame, &full_bar[c]);
-        }
-    }
-    for (int i = tid; i < OUT_R * WW; i += kThreads) bits[i] = 0u;
-
-    const int t = (int)p.threshold, n = (int)p.count;
-    const uint32_t kbias = filter_kbias(p.threshold);
-
-    for (int c = 0; c < NC; c++) {
-        const int stage = c & 1;
-        const uint8_t *tile = tiles + stage * L::tile_bytes;
-        const ChunkGeo g = make_geo<MODE>(W, H, WW, (int)strip, c, SR);
-        uint32_t *qc = &qcount[stage];
-
-        if (MODE != NMS_OFF) {
-            uint4 *pz = reinterpret_cast<uint4 *>(plane) + tid;
-#pragma unroll
-            for (int i = 0; i < L::plane_bytes / 16 / kThreads; i++) pz[i * kThreads] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        mbar_wait(&full_bar[stage], (uint32_t)((c >> 1) & 1), p.flags);
-
-        phase_a<MODE, SR>(tid, tile, queue, qc, g, kbias);
-        __syncthreads();  // queue complete, plane zeroed
-
-        const uint32_t qn = *qc;
-        if (tid == 0) qcount[stage ^ 1] = 0u;  // for the next chunk; its phase A starts after the next barrier
-        phase_b<MODE, SR>(tid, qn, tile, queue, plane, bits, g, t, n);
-        __syncthreads();  // tile[stage] is free again; score plane complete
-
-        if (tid == 0 && c + 2 < NC) {
-            mbar_expect_tx(&full_bar[stage], (uint32_t)L::tile_bytes);
-            tma_load_3d(tiles + stage * L::tile_bytes, &tmap, (c + 2) * kChunkW - kTileLead, ty0, (int)frame,
-                        &full_bar[stage]);
-        }
-        if (MODE != NMS_OFF) {
-            nms_pass<MODE, SR>(tid, qn, queue, plane, bits, g);
-            __syncthreads();  // plane and queue may be reused
-        }
-    }
-
-    // ---- ordered compaction: bit plane -> packed points ------------------------------------------
-    const int lane = tid & 31, warp = tid >> 5;
-    const EmitRange er = emit_range(warp, OUT_R * WW);
-    uint32_t cnt = 0;
-    for (int i = er.begin + lane; i < er.end; i += 32) cnt += (uint32_t)__popc(bits[i]);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);  // warp total
-    if (lane == 0) warp_sums[warp] = cnt;
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t ws = lane < kThreads / 32 ? warp_sums[lane] : 0u;
-        uint32_t wincl = ws;
-#pragma unroll
-        for (int d = 1; d < kThreads / 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, wincl, d);
-            if (lane >= d) wincl += v;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, wincl, kThreads / 32 - 1);
-        if (lane < kThreads / 32) warp_sums[lane] = wincl - ws;  // exclusive offset of each warp
-        const unsigned long long excl = lookback(p.status, item, total, lane, p.flags);
-        if (lane == 0) {
-            *s_base = excl;
-            if (item == 0) p.offsets[0] = 0ull;
-            if (strip == p.strips_per_frame - 1) p.offsets[frame + 1] = excl + total;
-        }
-    }
-    __syncthreads();
-    if (cnt != 0u) {  // warp-uniform: this warp's range holds keypoints
-        unsigned long long o = *s_base + warp_sums[warp];
-        int i = er.begin + lane;
-        int row = i / WW, col = i - row * WW;
-        for (int base = er.begin; base < er.end; base += 32, i += 32) {
-            const uint32_t m = i < er.end ? bits[i] : 0u;
-            const uint32_t c = (uint32_t)__popc(m);
-            uint32_t incl = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += v;
+    if (warp < kComputeWarps) {
+        // ======================= compute warps =======================
+        const int t = (int)p.threshold, n = (int)p.count;
+        const uint32_t kbias = filter_kbias(p.threshold);
+        uint16_t *wqueue = queue + warp * L::queue_per_warp;
+        uint32_t *wcount = &qcount[warp];
+        uint32_t gc = 0;  // chunks processed by this CTA so far: tile stage = gc & 1, mbarrier parity = (gc >> 1) & 1
+        for (uint32_t it = 0;; it++) {
+            const int buf = (int)(it & 1u);
+            if (tid == 0) {
+                mbar_wait(&bits_empty[buf], ((it >> 1) & 1u) ^ 1u, p.flags);  // bit plane `buf` emitted and zeroed
+                s_item[buf] = atomicAdd(p.ticket, 1u);  // items start in scan order => look-back cannot deadlock
             }
-            if (m != 0u) emit_word(m, (uint32_t)col * 32u, (uint32_t)(y0 + row), o + (incl - c), p.cap, p.out);
-            o += __shfl_sync(0xffffffffu, incl, 31);
-            col += 32;
-            while (col >= WW) {
-                col -= WW;
-                row++;
+            bar_compute();  // also: every warp has finished the previous strip (tiles, plane and queues are free)
+            const uint32_t item = s_item[buf];
+            if (item >= total_items) {
+                if (lane == 0) mbar_arrive(&bits_full[buf]);  // hand the end marker to the emit warp
+                break;
             }
+            const uint32_t frame = item / p.strips_per_frame;
+            const uint32_t strip = item - frame * p.strips_per_frame;
+            const int ty0 = first_out_row(MODE) + (int)strip * OUT_R - HS - 3;  // image row of tile row 0
+            uint32_t *sbits = bits + buf * nwords;
+
+            if (tid == 0) {
+                const int pre = NC < 2 ? NC : 2;
+                for (int c = 0; c < pre; c++) {
+                    const uint32_t stage = (gc + (uint32_t)c) & 1u;
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)L::tile_bytes);
+                    tma_load_3d(tiles + stage * L::tile_bytes, &tmap, c * kChunkW - kTileLead, ty0, (int)frame,
+                                &full_bar[stage]);
+                }
+            }
+            for (int c = 0; c < NC; c++, gc++) {
+                const uint32_t stage = gc & 1u;
+                const uint8_t *tile = tiles + stage * L::tile_bytes;
+                const ChunkGeo g = make_geo<MODE>(W, H, WW, (int)strip, c, SR);
+                const uint32_t tag = (uint32_t)(c % kTagPeriod) + 1u;
+                if (MODE != NMS_OFF && tag == 1u) {  // (re)start the tag sequence on a cleared plane
+                    if (c != 0) bar_compute();        // every warp is done suppressing the previous chunk
+                    uint4 *pz = reinterpret_cast<uint4 *>(plane) + tid;
+#pragma unroll
+                    for (int i = 0; i < L::plane_bytes / 16 / kComputeThreads; i++)
+                        pz[i * kComputeThreads] = make_uint4(0u, 0u, 0u, 0u);
+                    bar_compute();
+                }
+                if (lane == 0) *wcount = 0u;
+                mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags);
+                __syncwarp();
+
+                phase_a<MODE, SR>(warp, lane, tile, wqueue, wcount, g, kbias);
+                __syncwarp();  // the warp's queue is complete
+                const uint32_t qn = *wcount;
+                phase_b<MODE, SR>(lane, qn, tile, wqueue, plane, sbits, g, t, n, tag);
+
+                bar_compute();  // tile[stage] is free again; every warp's scores of this chunk are in the plane
+                if (tid == 0 && c + 2 < NC) {
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)L::tile_bytes);
+                    tma_load_3d(tiles + stage * L::tile_bytes, &tmap, (c + 2) * kChunkW - kTileLead, ty0, (int)frame,
+                                &full_bar[stage]);
+                }
+                if (MODE != NMS_OFF) nms_pass<MODE, SR>(lane, qn, wqueue, plane, sbits, g, tag);
+                __syncwarp();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bits_full[buf]);  // this warp's bits of the strip are set
+        }
+    } else {
+        // ======================= emit warp =======================
+        for (uint32_t it = 0;; it++) {
+            const int buf = (int)(it & 1u);
+            mbar_wait(&bits_full[buf], (it >> 1) & 1u, p.flags);
+            const uint32_t item = s_item[buf];
+            if (item >= total_items) break;
+            const uint32_t frame = item / p.strips_per_frame;
+            const uint32_t strip = item - frame * p.strips_per_frame;
+            const int y0 = first_out_row(MODE) + (int)strip * OUT_R;  // first row this strip emits
+            uint32_t *sbits = bits + buf * nwords;
+
+            uint32_t cnt = 0;
+            for (int i = lane; i < nwords; i += 32) cnt += (uint32_t)__popc(sbits[i]);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);  // strip total
+            unsigned long long o = lookback(p.status, item, cnt, lane, p.flags);
+            if (lane == 0) {
+                if (item == 0) p.offsets[0] = 0ull;
+                if (strip == p.strips_per_frame - 1) p.offsets[frame + 1] = o + cnt;
+            }
+            if (cnt != 0u) {
+                int i = lane;
+                int row = i / WW, col = i - row * WW;
+                for (int base = 0; base < nwords; base += 32, i += 32) {
+                    const uint32_t m = i < nwords ? sbits[i] : 0u;
+                    const uint32_t c = (uint32_t)__popc(m);
+                    uint32_t incl = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += v;
+                    }
+                    if (m != 0u) {
+                        emit_word(m, (uint32_t)col * 32u, (uint32_t)(y0 + row), o + (incl - c), p.cap, p.out);
+                        sbits[i] = 0u;  // leave the plane zeroed for the strip after next
+                    }
+                    o += __shfl_sync(0xffffffffu, incl, 31);
+                    col += 32;
+                    while (col >= WW) {
+                        col -= WW;
+                        row++;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bits_empty[buf]);
         }
     }
 }
@@ -311,7 +346,15 @@ cudaError_t launch_t(const CUtensorMap &tmap, const DetectParams &p, cudaStream_
     if (e != cudaSuccess) return e;
     const unsigned long long items = (unsigned long long)p.n_frames * p.strips_per_frame;
     if (items == 0 || items > 0x7fffffffull) return cudaErrorInvalidValue;
-    kern<<<(unsigned)items, kThreads, smem, stream>>>(tmap, p);
+    // persistent grid: as many CTAs as can be resident at once (each loops over tickets)
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem)) != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    unsigned long long grid = (unsigned long long)sms * (unsigned)per_sm;
+    if (grid > items) grid = items;
+    kern<<<(unsigned)grid, kThreads, smem, stream>>>(tmap, p);
     return cudaGetLastError();
 }
 
@@ -319,9 +362,9 @@ cudaError_t launch_t(const CUtensorMap &tmap, const DetectParams &p, cudaStream_
 
 size_t detect_smem_bytes(int mode, int sr, uint32_t words_per_row) {
     const size_t tile = (size_t)tile_rows(sr) * kTileW;
-    const size_t plane = mode == NMS_OFF ? 0 : (size_t)sr * kTileW * 2;
+    const size_t plane = mode == NMS_OFF ? 0 : (size_t)sr * kPlaneW * 2;
     const size_t queue = (size_t)sr * kTileW * 2;
-    return 2 * tile + plane + queue + 128 + (size_t)out_rows(mode, sr) * words_per_row * 4;
+    return 2 * tile + plane + queue + 128 + 2 * (size_t)out_rows(mode, sr) * words_per_row * 4;
 }
 
 cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream) {

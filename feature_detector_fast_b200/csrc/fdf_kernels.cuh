@@ -6,16 +6,24 @@
 
 namespace fdf {
 
-// Geometry shared by host and device.  A frame is cut into STRIPS of full-width rows; one CTA
-// owns one strip and walks it left to right in CHUNKS.  For every chunk a 256-byte-wide tile
+// Geometry shared by host and device.  A frame is cut into STRIPS of full-width rows; a CTA
+// takes one strip at a time (atomic ticket) and walks it left to right in CHUNKS.  For every chunk a 256-byte-wide tile
 // (chunk + halo) is staged into shared memory by one TMA 3-D tiled load.
-constexpr int kThreads = 256;   // threads per CTA
+constexpr int kComputeWarps = 8;                       // warps that filter / test / score / suppress
+constexpr int kComputeThreads = kComputeWarps * 32;
+constexpr int kThreads = kComputeThreads + 32;         // + one warp that scans and emits finished strips
 constexpr int kTileW = 256;     // tile width in bytes = TMA box inner extent (the maximum)
 constexpr int kChunkW = 240;    // output columns per chunk (the last chunk of a row may take one more)
 constexpr int kTileLead = 16;   // chunk c's tile starts at image column c*kChunkW - kTileLead: TMA needs the
                                 // innermost start coordinate 16-byte aligned (an unaligned one faults)
 constexpr int kLeftHalo = 12;   // the chunk's first output column is tile column 12: left halo 12, right halo 4
                                 // (4 = 3 ring pixels + 1 NMS neighbour)
+
+constexpr int kPlaneW = 512;    // the score plane is indexed by (image column mod 512): two consecutive chunks
+                                // (496 columns) never alias, so chunk c+1 may be scored while chunk c is still
+                                // being suppressed
+constexpr int kTagPeriod = 15;  // score plane entries carry a 4-bit chunk tag (1..15) above the 12-bit score and
+                                // the plane is cleared every 15 chunks: stale entries read as "no keypoint"
 
 __host__ __device__ constexpr int chunks_per_row(int w) { return (w + kChunkW - 1) / kChunkW; }
 

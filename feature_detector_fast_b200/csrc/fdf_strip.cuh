@@ -67,15 +67,17 @@ FDF_HD ChunkGeo make_geo(int w, int h, int ww, int strip, int chunk, int sr) {
 }
 
 // ---- phase A: dense filter, 16 centres per thread and row (replaces fast_simd.rs:368-520) -------
-// Pushes (scored row << 8 | tile column) of every centre of a scorable row that passes the
-// necessary-condition filter.  Column validity (image border, chunk halo) is checked in phase B,
-// where it costs a few instructions per candidate instead of mask set-up per thread and chunk.
+// Every compute warp filters its own rows (thread t = warp*32 + lane handles the 16-pixel group
+// t & 15 of scored rows (t >> 4) + 16k) and pushes (scored row << 8 | tile column) of each centre
+// that passes the necessary-condition filter to ITS OWN queue: phases A and B of a warp need no
+// block-wide barrier.  Column validity (image border, chunk halo) is checked in phase B.
 template <int MODE, int SR>
-FDF_HD void phase_a(int tid, const uint8_t *tile, uint16_t *queue, uint32_t *qcount, const ChunkGeo &g,
+FDF_HD void phase_a(int warp, int lane, const uint8_t *tile, uint16_t *wqueue, uint32_t *wcount, const ChunkGeo &g,
                     uint32_t kbias) {
+    const int tid = warp * 32 + lane;
     const int q = tid & 15;   // which 16-pixel group of the 256-wide tile row
     const int r0 = tid >> 4;  // first scored row of this thread
-    for (int rr = r0; rr < SR; rr += kThreads / 16) {
+    for (int rr = r0; rr < SR; rr += kComputeThreads / 16) {
         const int y = g.ys0 + rr;
         if (y < 3 || y >= g.h - 3) continue;  // fast_simd.rs:342
         const uint8_t *rowp = tile + (rr + 3) * kTileW + q * 16;
@@ -96,28 +98,29 @@ FDF_HD void phase_a(int tid, const uint8_t *tile, uint16_t *queue, uint32_t *qco
         if ((f0 | f1 | f2 | f3) != 0u) {
             // each f has only bit 7 of its bytes set: bit (8*b + k) of gm <=> byte b of word k
             uint32_t gm = (f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4);
-            uint32_t slot = atomic_add_u32(qcount, (uint32_t)popc32(gm));
+            uint32_t slot = atomic_add_u32(wcount, (uint32_t)popc32(gm));
             const uint32_t ent0 = (uint32_t)((rr << 8) | (q * 16));
             while (gm) {
                 const uint32_t p = (uint32_t)lowest_set_bit(gm);
                 gm &= gm - 1u;
-                queue[slot++] = (uint16_t)(ent0 + ((p & 7u) << 2) + (p >> 3));
+                wqueue[slot++] = (uint16_t)(ent0 + ((p & 7u) << 2) + (p >> 3));
             }
         }
     }
 }
 
 // ---- phase B: exact segment test (+ score) per candidate (replaces fast_simd.rs:115-297, 623-749)
-// Off mode: sets the keypoint's bit in the strip bit plane.  NMS modes: writes the score into the
-// score plane and marks the queue entry as a confirmed keypoint (bit 15).
+// One lane per entry of the warp's queue.  Off mode: sets the keypoint's bit in the strip bit plane.
+// NMS modes: writes (tag << 12 | score) into the score plane at (scored row, image column mod 512)
+// and marks the queue entry as a confirmed keypoint (bit 15).
 template <int MODE, int SR>
-FDF_HD void phase_b(int tid, uint32_t qn, const uint8_t *tile, uint16_t *queue, uint16_t *plane, uint32_t *bits,
-                    const ChunkGeo &g, int t, int n) {
+FDF_HD void phase_b(int lane, uint32_t qn, const uint8_t *tile, uint16_t *wqueue, uint16_t *plane, uint32_t *bits,
+                    const ChunkGeo &g, int t, int n, uint32_t tag) {
     constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;
     // scored columns: the chunk's own columns plus the NMS score halo, inside the image's centre range
     const int xlo = max(3, g.x0 - HS), xhi = min(g.w - 3, g.x1 + HS);
-    for (uint32_t i = (uint32_t)tid; i < qn; i += kThreads) {
-        const uint32_t ent = queue[i];
+    for (uint32_t i = (uint32_t)lane; i < qn; i += 32u) {
+        const uint32_t ent = wqueue[i];
         const int rr = (int)(ent >> 8), j = (int)(ent & 0xffu);
         const int x = g.xt0 + j;
         if (x < xlo || x >= xhi) continue;  // fast_simd.rs:369-371, 559-562
@@ -134,9 +137,9 @@ FDF_HD void phase_b(int tid, uint32_t qn, const uint8_t *tile, uint16_t *queue, 
                 atomic_or_u32(&bits[rr * g.ww + (x >> 5)], 1u << (x & 31));
             } else {
                 const uint32_t sc = (MODE == NMS_MAX_THRESHOLD) ? score_max_threshold(cv, ring, n, arc_bright)
-                                                                : score_sum_abs(cv, ring, t);
-                plane[rr * kTileW + j] = (uint16_t)sc;
-                queue[i] = (uint16_t)(ent | 0x8000u);
+                                                                : score_sum_abs(cv, ring, t);  // <= 4080 < 2^12
+                plane[rr * kPlaneW + (x & (kPlaneW - 1))] = (uint16_t)((tag << 12) | sc);
+                wqueue[i] = (uint16_t)(ent | 0x8000u);
             }
         }
     }
@@ -145,41 +148,34 @@ FDF_HD void phase_b(int tid, uint32_t qn, const uint8_t *tile, uint16_t *queue, 
 // ---- NMS pass: strict maximum over the 8 neighbours (replaces fast_simd.rs:588-616) ------------
 // Only this chunk's own columns and this strip's own rows are emitted; rows 3 and h-4 are scored
 // (they act as neighbours) but never emitted (fast_simd.rs:589-596, opencv_compat.rs:238-240).
+// A plane entry counts only if its tag is the current chunk's or newer (the next chunk may already
+// have re-scored the shared halo columns, with identical scores); older entries are stale.
+FDF_HD uint32_t live_score(uint32_t v, uint32_t tag_floor) { return v >= tag_floor ? (v & 0xfffu) : 0u; }
+
 template <int MODE, int SR>
-FDF_HD void nms_pass(int tid, uint32_t qn, const uint16_t *queue, const uint16_t *plane, uint32_t *bits,
-                     const ChunkGeo &g) {
-    for (uint32_t i = (uint32_t)tid; i < qn; i += kThreads) {
-        const uint32_t ent = queue[i];
+FDF_HD void nms_pass(int lane, uint32_t qn, const uint16_t *wqueue, const uint16_t *plane, uint32_t *bits,
+                     const ChunkGeo &g, uint32_t tag) {
+    const uint32_t floor = tag << 12;
+    for (uint32_t i = (uint32_t)lane; i < qn; i += 32u) {
+        const uint32_t ent = wqueue[i];
         if (!(ent & 0x8000u)) continue;
         const int rr = (int)((ent >> 8) & 0x7fu), j = (int)(ent & 0xffu);
-        const int y = g.ys0 + rr, xj = g.xt0 + j;
-        if (rr < 1 || rr > SR - 2 || xj < g.x0 || xj >= g.x1 || y >= g.h - 4) continue;
-        const uint16_t *pp = plane + rr * kTileW + j;
-        const uint32_t s = pp[0];
-        const bool keep = s > pp[-kTileW - 1] && s > pp[-kTileW] && s > pp[-kTileW + 1] && s > pp[-1] && s > pp[1] &&
-                          s > pp[kTileW - 1] && s > pp[kTileW] && s > pp[kTileW + 1];
-        if (keep) {
-            const int x = g.xt0 + j;
-            atomic_or_u32(&bits[(rr - 1) * g.ww + (x >> 5)], 1u << (x & 31));
-        }
+        const int y = g.ys0 + rr, x = g.xt0 + j;
+        if (rr < 1 || rr > SR - 2 || x < g.x0 || x >= g.x1 || y >= g.h - 4) continue;
+        const uint16_t *row = plane + rr * kPlaneW;
+        const int xl = (x - 1) & (kPlaneW - 1), xc = x & (kPlaneW - 1), xr = (x + 1) & (kPlaneW - 1);
+        const uint32_t s = row[xc] & 0xfffu;
+        const bool keep = s > live_score(row[xl - kPlaneW], floor) && s > live_score(row[xc - kPlaneW], floor) &&
+                          s > live_score(row[xr - kPlaneW], floor) && s > live_score(row[xl], floor) &&
+                          s > live_score(row[xr], floor) && s > live_score(row[xl + kPlaneW], floor) &&
+                          s > live_score(row[xc + kPlaneW], floor) && s > live_score(row[xr + kPlaneW], floor);
+        if (keep) atomic_or_u32(&bits[(rr - 1) * g.ww + (x >> 5)], 1u << (x & 31));
     }
 }
 
 // ---- emission: bit plane -> points, row-major -----------------------------------------------------
-// The strip's bit plane (out_rows x ww words) is cut into kThreads/32 contiguous ranges, one per warp;
-// a warp walks its range 32 words at a time (one word per lane, warp prefix sum for the offsets).
-struct EmitRange {
-    int begin, end;  // word indices into bits[out_rows * ww]
-};
-
-FDF_HD EmitRange emit_range(int warp, int nwords) {
-    const int wpw = (nwords + kThreads / 32 - 1) / (kThreads / 32);
-    EmitRange r;
-    r.begin = min(warp * wpw, nwords);
-    r.end = min(r.begin + wpw, nwords);
-    return r;
-}
-
+// One warp walks the strip's bit plane (out_rows x ww words) 32 words at a time: one word per lane,
+// a warp prefix sum gives every lane its output offset.
 // writes the points of one bit-plane word (row `y`, columns xw .. xw+31) starting at index o
 FDF_HD void emit_word(uint32_t m, uint32_t xw, uint32_t y, unsigned long long o, unsigned long long cap, uint2 *out) {
     while (m) {

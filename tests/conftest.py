@@ -40,14 +40,22 @@ def emulator():
     lib.fdf_core_check.restype = C.c_int64
     lib.fdf_core_check.argtypes = [C.c_uint64, C.c_uint64]
 
-    def run(img, t, n, nms, sr):
+    def run(img, t, n, nms, sr, late_nms=None):
+        """late_nms=True emulates the interleaving in which every warp's NMS pass of chunk c runs after phases
+        A+B of chunk c+1 (the furthest the kernel's one barrier per chunk lets warps drift apart); None = both."""
         img = np.ascontiguousarray(img)
         h, w = img.shape
         cap = max(1, w * h)
-        out = np.zeros((cap, 2), np.uint32)
-        k = lib.fdf_emulate_detect(img.ctypes.data, w, h, w, t, n, nms, sr, out.ctypes.data, cap)
-        assert k >= 0
-        return out[:k].copy()
+        results = []
+        for late in ((False, True) if late_nms is None else (late_nms,)):
+            out = np.zeros((cap, 2), np.uint32)
+            k = lib.fdf_emulate_detect(img.ctypes.data, w, h, w, t, n, nms, sr | (1024 if late else 0),
+                                       out.ctypes.data, cap)
+            assert k >= 0, k
+            results.append(out[:k].copy())
+        for r in results[1:]:
+            assert r.shape == results[0].shape and np.array_equal(r, results[0]), "interleavings disagree"
+        return results[0]
 
     run.core_check = lib.fdf_core_check
     return run

@@ -17,49 +17,71 @@ namespace {
 
 using namespace fdf;
 
+// late_nms: run the NMS pass of chunk c only after phases A+B of chunk c+1 -- the most extreme
+// interleaving the kernel's single per-chunk barrier allows (fast warps one chunk ahead).
 template <int MODE, int SR>
-int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2 *out, size_t cap) {
+int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2 *out, size_t cap, bool late_nms) {
     constexpr int OUT_R = out_rows(MODE, SR);
     constexpr int TR = tile_rows(SR);
+    constexpr int QW = (SR / kComputeWarps) * kTileW;
     const long long rows = (long long)h - 2 * first_out_row(MODE);
     if (w < 7 || h < 7 || rows <= 0) return 0;
     const int S = (int)((rows + OUT_R - 1) / OUT_R);
     const int NC = chunks_per_row(w);
     const int WW = (w + 31) / 32;
-    alignas(16) static uint8_t tile[tile_rows(64) * kTileW];
-    std::vector<uint16_t> plane((size_t)SR * kTileW), queue((size_t)SR * kTileW);
+    alignas(16) static uint8_t tiles[2][tile_rows(64) * kTileW];
+    std::vector<uint16_t> plane((size_t)SR * kPlaneW);
+    std::vector<uint16_t> queue[2] = {std::vector<uint16_t>((size_t)kComputeWarps * QW),
+                                      std::vector<uint16_t>((size_t)kComputeWarps * QW)};
+    uint32_t qcount[2][kComputeWarps];
     std::vector<uint32_t> bits((size_t)OUT_R * WW);
     const uint32_t kbias = filter_kbias((uint32_t)t);
     unsigned long long total = 0;
     for (int strip = 0; strip < S; strip++) {
         std::fill(bits.begin(), bits.end(), 0u);
+        auto run_nms = [&](int c) {
+            const ChunkGeo g = make_geo<MODE>(w, h, WW, strip, c, SR);
+            const uint32_t tag = (uint32_t)(c % kTagPeriod) + 1u;
+            for (int warp = 0; warp < kComputeWarps; warp++)
+                for (int lane = 0; lane < 32; lane++)
+                    nms_pass<MODE, SR>(lane, qcount[c & 1][warp], queue[c & 1].data() + warp * QW, plane.data(),
+                                       bits.data(), g, tag);
+        };
         for (int c = 0; c < NC; c++) {
             const ChunkGeo g = make_geo<MODE>(w, h, WW, strip, c, SR);
+            const uint32_t tag = (uint32_t)(c % kTagPeriod) + 1u;
             const int ty0 = g.ys0 - 3;
             if (g.xt0 % 16 != 0) return -16;  // TMA: innermost box start must be 16-byte aligned
+            uint8_t *tile = tiles[c & 1];
             for (int r = 0; r < TR; r++)      // what the TMA tiled load delivers: zero fill outside the image
                 for (int j = 0; j < kTileW; j++) {
                     const int y = ty0 + r, x = g.xt0 + j;
                     tile[r * kTileW + j] = (y >= 0 && y < h && x >= 0 && x < w) ? img[(size_t)y * pitch + x] : 0;
                 }
-            std::fill(plane.begin(), plane.end(), (uint16_t)0);
-            uint32_t qcount = 0;
-            for (int tid = 0; tid < kThreads; tid++) phase_a<MODE, SR>(tid, tile, queue.data(), &qcount, g, kbias);
-            for (int tid = 0; tid < kThreads; tid++)
-                phase_b<MODE, SR>(tid, qcount, tile, queue.data(), plane.data(), bits.data(), g, t, n);
-            if (MODE != NMS_OFF)
-                for (int tid = 0; tid < kThreads; tid++)
-                    nms_pass<MODE, SR>(tid, qcount, queue.data(), plane.data(), bits.data(), g);
+            if (MODE != NMS_OFF && tag == 1u) {  // the kernel's barrier + clear + barrier
+                if (late_nms && c > 0) run_nms(c - 1);
+                std::fill(plane.begin(), plane.end(), (uint16_t)0);
+            }
+            for (int warp = 0; warp < kComputeWarps; warp++) {
+                uint16_t *wq = queue[c & 1].data() + warp * QW;
+                qcount[c & 1][warp] = 0;
+                for (int lane = 0; lane < 32; lane++) phase_a<MODE, SR>(warp, lane, tile, wq, &qcount[c & 1][warp], g, kbias);
+                if (qcount[c & 1][warp] > (uint32_t)QW) return -17;
+                for (int lane = 0; lane < 32; lane++)
+                    phase_b<MODE, SR>(lane, qcount[c & 1][warp], tile, wq, plane.data(), bits.data(), g, t, n, tag);
+            }
+            if (MODE != NMS_OFF) {
+                if (!late_nms) run_nms(c);
+                else if (c > 0 && tag != 1u) run_nms(c - 1);
+                if (late_nms && c == NC - 1) run_nms(c);
+            }
         }
         const ChunkGeo g0 = make_geo<MODE>(w, h, WW, strip, 0, SR);
-        for (int warp = 0; warp < kThreads / 32; warp++) {  // the warps' ranges, in order
-            const EmitRange er = emit_range(warp, OUT_R * WW);
-            for (int i = er.begin; i < er.end; i++) {
-                const uint32_t m = bits[i];
-                const int row = i / WW, col = i - row * WW;
-                emit_word(m, (uint32_t)col * 32u, (uint32_t)(g0.y0 + row), total, cap, out);
-                total += (unsigned long long)__builtin_popcount(m);
-            }
+        for (int i = 0; i < OUT_R * WW; i++) {  // the emit warp's walk, in word order
+            const uint32_t m = bits[i];
+            const int row = i / WW, col = i - row * WW;
+            emit_word(m, (uint32_t)col * 32u, (uint32_t)(g0.y0 + row), total, cap, out);
+            total += (unsigned long long)__builtin_popcount(m);
         }
     }
     return (int64_t)total;
@@ -80,8 +102,10 @@ extern "C" {
 int64_t fdf_emulate_detect(const uint8_t *img, uint32_t w, uint32_t h, uint32_t pitch, uint8_t t, uint8_t n,
                            uint8_t nms, int sr, fdf_oracle_point *out, size_t cap) {
     uint2 *o = reinterpret_cast<uint2 *>(out);
+    const bool late = (sr & 1024) != 0;  // flag bit: emulate the "NMS one chunk late" interleaving
+    sr &= 1023;
 #define CASE(M, S) \
-    if (nms == M && sr == S) return emulate<M, S>(img, (int)w, (int)h, (int)pitch, t, n, o, cap);
+    if (nms == M && sr == S) return emulate<M, S>(img, (int)w, (int)h, (int)pitch, t, n, o, cap, late);
     CASE(0, 16) CASE(0, 32) CASE(1, 16) CASE(1, 32) CASE(2, 16) CASE(2, 32)
 #undef CASE
     return -1;

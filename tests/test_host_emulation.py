@@ -62,6 +62,15 @@ def test_random_images(emulator, oracle_mod):
         assert same_points(emulator(img, t, n, nms, sr), oracle_mod.detect(img, t, n, nms)), (w, h, t, n, nms, sr)
 
 
+def test_wide_image_many_chunks_tag_wrap(emulator, oracle_mod):
+    # more than 15 chunks per row: the score-plane tag sequence restarts (plane cleared) inside a strip
+    img = oracle_mod.synth_frame(3840, 40, seed=77, frame=0, kind=0, amp=4)
+    for nms in (1, 2):
+        assert same_points(emulator(img, 16, 9, nms, 32), oracle_mod.detect(img, 16, 9, nms))
+    img = oracle_mod.synth_frame(4100, 24, seed=78, frame=0, kind=1)
+    assert same_points(emulator(img, 40, 9, 1, 16), oracle_mod.detect(img, 40, 9, 1))
+
+
 def test_saturated_and_flat_images(emulator, oracle_mod):
     for v in (0, 255, 17):
         img = np.full((50, 300), v, np.uint8)
