@@ -44,7 +44,8 @@ struct fdf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     EncodeTiledFn encode = nullptr;
-    DeviceBuffer<uint8_t> workspace;            // ticket | flags | status[]
+    DeviceBuffer<uint8_t> workspace;            // tickets | flags | cursor | scan status | per-strip count/src/dst
+    DeviceBuffer<fdf_point> staging;            // per-strip ordered runs before the gather
     DeviceBuffer<uint8_t> staged_frames;        // host-path input staging (pitched to 16 bytes)
     DeviceBuffer<fdf_point> staged_points;      // host-path output staging
     DeviceBuffer<unsigned long long> staged_offsets;
@@ -148,6 +149,7 @@ void fdf_destroy(fdf_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->workspace.release();
+    ctx->staging.release();
     ctx->staged_frames.release();
     ctx->staged_points.release();
     ctx->staged_offsets.release();
@@ -200,12 +202,26 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     const unsigned long long items = (unsigned long long)n_frames * p.strips_per_frame;
     if (items > 0x7fffffffull) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "batch too large");
 
-    const size_t ws_bytes = kWorkspaceHeader + (size_t)items * sizeof(unsigned long long);
+    // workspace: [header 64 B: ticket, flags, scan ticket, cursor][scan status][zeroed up to here per launch]
+    //            [item_src][item_dst][item_count]
+    const size_t scan_tiles = ((size_t)items + fdf::kScanTile - 1) / fdf::kScanTile;
+    const size_t zeroed_bytes = kWorkspaceHeader + scan_tiles * sizeof(unsigned long long);
+    const size_t src_off = (zeroed_bytes + 15) & ~(size_t)15;
+    const size_t dst_off = src_off + (size_t)items * sizeof(unsigned long long);
+    const size_t cnt_off = dst_off + (size_t)items * sizeof(unsigned long long);
+    const size_t ws_bytes = cnt_off + (size_t)items * sizeof(uint32_t);
     FDF_CUDA(ctx, ctx->workspace.reserve(ws_bytes));
-    FDF_CUDA(ctx, cudaMemsetAsync(ctx->workspace.ptr, 0, ws_bytes, stream));
+    FDF_CUDA(ctx, ctx->staging.reserve(cap ? cap : 1));
+    FDF_CUDA(ctx, cudaMemsetAsync(ctx->workspace.ptr, 0, zeroed_bytes, stream));
     p.ticket = reinterpret_cast<uint32_t *>(ctx->workspace.ptr);
     p.flags = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + 4);
-    p.status = reinterpret_cast<unsigned long long *>(ctx->workspace.ptr + kWorkspaceHeader);
+    p.scan_ticket = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + 8);
+    p.cursor = reinterpret_cast<unsigned long long *>(ctx->workspace.ptr + 16);
+    p.scan_status = reinterpret_cast<unsigned long long *>(ctx->workspace.ptr + kWorkspaceHeader);
+    p.item_src = reinterpret_cast<unsigned long long *>(ctx->workspace.ptr + src_off);
+    p.item_dst = reinterpret_cast<unsigned long long *>(ctx->workspace.ptr + dst_off);
+    p.item_count = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + cnt_off);
+    p.staging = reinterpret_cast<uint2 *>(ctx->staging.ptr);
 
     // frames as a 3-D u8 tensor (x, y, frame); box = one tile; out-of-bounds elements read as 0
     CUtensorMap tmap;
@@ -219,7 +235,8 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     if (cr != CUDA_SUCCESS) return fail(ctx, FDF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
 
     FDF_CUDA(ctx, fdf::launch_detect(mode, sr, tmap, p, stream));
-    ctx->launches += 1;
+    FDF_CUDA(ctx, fdf::launch_compact(p, stream));
+    ctx->launches += 3;  // detection, scan, gather
     return FDF_OK;
 }
 

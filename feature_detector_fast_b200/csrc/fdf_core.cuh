@@ -99,8 +99,9 @@ FDF_HD int max3i(int a, int b, int c) { return max(a, max(b, c)); }
 FDF_HD uint32_t filter_kbias(uint32_t t) { return t < 128u ? (0x7fu - t) * 0x01010101u : 0u; }
 
 FDF_HD uint32_t pair_exceeds(uint32_t a, uint32_t b, uint32_t c, uint32_t kbias) {
-    uint32_t m = absdiff4(a, c) | absdiff4(b, c);
-    return ((m & 0x7f7f7f7fu) + kbias) | m;  // bit 7 of each byte is the flag
+    const uint32_t da = absdiff4(a, c), db = absdiff4(b, c);
+    const uint32_t x = ((da | db) & 0x7f7f7f7fu) + kbias;  // LOP3, IADD
+    return x | da | db;                                    // LOP3; bit 7 of each byte is the flag
 }
 
 // Returns candidate flags in bit 7 of each byte, already ANDed with `valid` (0x80 per byte that

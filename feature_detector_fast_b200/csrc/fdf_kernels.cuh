@@ -19,11 +19,12 @@ constexpr int kTileLead = 16;   // chunk c's tile starts at image column c*kChun
 constexpr int kLeftHalo = 12;   // the chunk's first output column is tile column 12: left halo 12, right halo 4
                                 // (4 = 3 ring pixels + 1 NMS neighbour)
 
-constexpr int kPlaneW = 512;    // the score plane is indexed by (image column mod 512): two consecutive chunks
-                                // (496 columns) never alias, so chunk c+1 may be scored while chunk c is still
-                                // being suppressed
-constexpr int kTagPeriod = 15;  // score plane entries carry a 4-bit chunk tag (1..15) above the 12-bit score and
-                                // the plane is cleared every 15 chunks: stale entries read as "no keypoint"
+constexpr int kTagPeriod = 15;  // score plane entries carry a 4-bit chunk tag (1..15) above the 12-bit score; the
+                                // plane is cleared at every strip start and every 15 chunks, so entries of
+                                // earlier chunks simply read as "no keypoint" and no per-chunk clear is needed
+constexpr int kQueueCap = 2048; // candidate queue entries per chunk (typical fill: ~200); more -> fallback below
+constexpr int kKlistCap = 1024; // confirmed keypoints per chunk the list NMS handles; more -> dense NMS
+constexpr int kGroupRows = 8;   // fallback for dense content: filter kGroupRows x 256 <= kQueueCap centres at a time
 
 __host__ __device__ constexpr int chunks_per_row(int w) { return (w + kChunkW - 1) / kChunkW; }
 
@@ -38,19 +39,34 @@ struct DetectParams {
     uint32_t chunks_per_strip;
     uint32_t words_per_row;  // ceil(w / 32): bit-plane words per row
     uint32_t threshold, count;
-    unsigned long long cap;  // capacity of out, in points
+    unsigned long long cap;  // capacity of out (and of staging), in points
     uint2 *out;              // fdf_point[cap], packed over the whole batch, row-major per frame
-    unsigned long long *offsets;  // n_frames + 1
-    unsigned long long *status;   // n_frames * strips_per_frame look-back words (zeroed per launch)
-    uint32_t *ticket;             // zeroed per launch
-    uint32_t *flags;              // zeroed per launch; bit 0 look-back timeout, bit 1 TMA wait timeout
+    uint2 *staging;          // fdf_point[cap]: each strip's ordered run at a bump-allocated position
+    unsigned long long *offsets;      // n_frames + 1
+    unsigned long long *cursor;       // staging bump allocator (zeroed per launch)
+    uint32_t *item_count;             // [items] keypoints of each (frame, strip)
+    unsigned long long *item_src;     // [items] where the strip's run sits in staging
+    unsigned long long *item_dst;     // [items] where it goes in out (exclusive scan of item_count)
+    unsigned long long *scan_status;  // look-back words of the scan kernel's tiles (zeroed per launch)
+    uint32_t *ticket;                 // strip tickets of the detection kernel (zeroed per launch)
+    uint32_t *scan_ticket;            // tile tickets of the scan kernel (zeroed per launch)
+    uint32_t *flags;                  // zeroed per launch; bit 0 look-back timeout, bit 1 TMA wait timeout
 };
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItemsPerThread = 8;
+constexpr int kScanTile = kScanThreads * kScanItemsPerThread;  // strips per scan tile
 
 size_t detect_smem_bytes(int mode, int sr, uint32_t words_per_row);
 
 // Enqueues the detection kernel for (mode, sr) on `stream`.  tmap describes the frames as a 3-D
 // u8 tensor (x, y, frame) with box (kTileW, tile_rows(sr), 1).
 cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream);
+
+// Ordered compaction, off the detection kernel's critical path: an exclusive scan of the per-strip counts
+// (single pass, decoupled look-back between scan tiles) and a gather of every strip's run to its final,
+// row-major position.  Two launches.
+cudaError_t launch_compact(const DetectParams &p, cudaStream_t stream);
 
 cudaError_t launch_synth(uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t pitch,
                          unsigned long long frame_stride, unsigned long long seed, uint32_t first_frame,

@@ -67,19 +67,19 @@ FDF_HD ChunkGeo make_geo(int w, int h, int ww, int strip, int chunk, int sr) {
 }
 
 // ---- phase A: dense filter, 16 centres per thread and row (replaces fast_simd.rs:368-520) -------
-// Every compute warp filters its own rows (thread t = warp*32 + lane handles the 16-pixel group
-// t & 15 of scored rows (t >> 4) + 16k) and pushes (scored row << 8 | tile column) of each centre
-// that passes the necessary-condition filter to ITS OWN queue: phases A and B of a warp need no
-// block-wide barrier.  Column validity (image border, chunk halo) is checked in phase B.
+// Thread t handles the 16-pixel group t & 15 of scored rows (t >> 4) + 16k inside [row_lo, row_hi) and
+// pushes (scored row << 8 | tile column) of each centre that passes the necessary-condition filter to the
+// CTA's candidate queue.  Column validity (image border, chunk halo) is checked in phase B.  When the queue
+// is full the entries are dropped but still counted: *qcount > kQueueCap tells the caller to redo the chunk
+// in row groups.
 template <int MODE, int SR>
-FDF_HD void phase_a(int warp, int lane, const uint8_t *tile, uint16_t *wqueue, uint32_t *wcount, const ChunkGeo &g,
-                    uint32_t kbias) {
-    const int tid = warp * 32 + lane;
+FDF_HD void phase_a(int tid, const uint8_t *tile, uint16_t *queue, uint32_t *qcount, const ChunkGeo &g,
+                    uint32_t kbias, int row_lo, int row_hi) {
     const int q = tid & 15;   // which 16-pixel group of the 256-wide tile row
     const int r0 = tid >> 4;  // first scored row of this thread
     for (int rr = r0; rr < SR; rr += kComputeThreads / 16) {
         const int y = g.ys0 + rr;
-        if (y < 3 || y >= g.h - 3) continue;  // fast_simd.rs:342
+        if (y < 3 || y >= g.h - 3 || rr < row_lo || rr >= row_hi) continue;  // fast_simd.rs:342
         const uint8_t *rowp = tile + (rr + 3) * kTileW + q * 16;
         const uint4 C = *reinterpret_cast<const uint4 *>(rowp);
         const uint4 N = *reinterpret_cast<const uint4 *>(rowp - 3 * kTileW);
@@ -98,29 +98,33 @@ FDF_HD void phase_a(int warp, int lane, const uint8_t *tile, uint16_t *wqueue, u
         if ((f0 | f1 | f2 | f3) != 0u) {
             // each f has only bit 7 of its bytes set: bit (8*b + k) of gm <=> byte b of word k
             uint32_t gm = (f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4);
-            uint32_t slot = atomic_add_u32(wcount, (uint32_t)popc32(gm));
-            const uint32_t ent0 = (uint32_t)((rr << 8) | (q * 16));
-            while (gm) {
-                const uint32_t p = (uint32_t)lowest_set_bit(gm);
-                gm &= gm - 1u;
-                wqueue[slot++] = (uint16_t)(ent0 + ((p & 7u) << 2) + (p >> 3));
+            const uint32_t cnt = (uint32_t)popc32(gm);
+            uint32_t slot = atomic_add_u32(qcount, cnt);
+            if (slot + cnt <= (uint32_t)kQueueCap) {
+                const uint32_t ent0 = (uint32_t)((rr << 8) | (q * 16));
+                while (gm) {
+                    const uint32_t p = (uint32_t)lowest_set_bit(gm);
+                    gm &= gm - 1u;
+                    queue[slot++] = (uint16_t)(ent0 + ((p & 7u) << 2) + (p >> 3));
+                }
             }
         }
     }
 }
 
 // ---- phase B: exact segment test (+ score) per candidate (replaces fast_simd.rs:115-297, 623-749)
-// One lane per entry of the warp's queue.  Off mode: sets the keypoint's bit in the strip bit plane.
-// NMS modes: writes (tag << 12 | score) into the score plane at (scored row, image column mod 512)
-// and marks the queue entry as a confirmed keypoint (bit 15).
+// One thread per queue entry.  Off mode: sets the keypoint's bit in the strip bit plane.  NMS modes: writes
+// (tag << 12 | score) into the score plane at (scored row, tile column) and appends the entry to the
+// chunk's keypoint list (entries beyond kKlistCap are only counted: the caller then runs the dense NMS).
 template <int MODE, int SR>
-FDF_HD void phase_b(int lane, uint32_t qn, const uint8_t *tile, uint16_t *wqueue, uint16_t *plane, uint32_t *bits,
-                    const ChunkGeo &g, int t, int n, uint32_t tag) {
+FDF_HD void phase_b(int tid, uint32_t qn, const uint8_t *tile, const uint16_t *queue, uint16_t *plane,
+                    uint16_t *klist, uint32_t *kcount, uint32_t *bits, const ChunkGeo &g, int t, int n,
+                    uint32_t tag) {
     constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;
     // scored columns: the chunk's own columns plus the NMS score halo, inside the image's centre range
     const int xlo = max(3, g.x0 - HS), xhi = min(g.w - 3, g.x1 + HS);
-    for (uint32_t i = (uint32_t)lane; i < qn; i += 32u) {
-        const uint32_t ent = wqueue[i];
+    for (uint32_t i = (uint32_t)tid; i < qn; i += (uint32_t)kComputeThreads) {
+        const uint32_t ent = queue[i];
         const int rr = (int)(ent >> 8), j = (int)(ent & 0xffu);
         const int x = g.xt0 + j;
         if (x < xlo || x >= xhi) continue;  // fast_simd.rs:369-371, 559-562
@@ -138,38 +142,49 @@ FDF_HD void phase_b(int lane, uint32_t qn, const uint8_t *tile, uint16_t *wqueue
             } else {
                 const uint32_t sc = (MODE == NMS_MAX_THRESHOLD) ? score_max_threshold(cv, ring, n, arc_bright)
                                                                 : score_sum_abs(cv, ring, t);  // <= 4080 < 2^12
-                plane[rr * kPlaneW + (x & (kPlaneW - 1))] = (uint16_t)((tag << 12) | sc);
-                wqueue[i] = (uint16_t)(ent | 0x8000u);
+                plane[rr * kTileW + j] = (uint16_t)((tag << 12) | sc);
+                const uint32_t k = atomic_add_u32(kcount, 1u);
+                if (k < (uint32_t)kKlistCap) klist[k] = (uint16_t)ent;
             }
         }
     }
 }
 
-// ---- NMS pass: strict maximum over the 8 neighbours (replaces fast_simd.rs:588-616) ------------
+// ---- NMS: strict maximum over the 8 neighbours (replaces fast_simd.rs:588-616) -------------------
 // Only this chunk's own columns and this strip's own rows are emitted; rows 3 and h-4 are scored
 // (they act as neighbours) but never emitted (fast_simd.rs:589-596, opencv_compat.rs:238-240).
-// A plane entry counts only if its tag is the current chunk's or newer (the next chunk may already
-// have re-scored the shared halo columns, with identical scores); older entries are stale.
+// A plane entry belongs to the current chunk iff its tag does; anything else is stale = "no keypoint".
 FDF_HD uint32_t live_score(uint32_t v, uint32_t tag_floor) { return v >= tag_floor ? (v & 0xfffu) : 0u; }
 
 template <int MODE, int SR>
-FDF_HD void nms_pass(int lane, uint32_t qn, const uint16_t *wqueue, const uint16_t *plane, uint32_t *bits,
+FDF_HD void nms_one(int rr, int j, const uint16_t *plane, uint32_t *bits, const ChunkGeo &g, uint32_t floor) {
+    const int y = g.ys0 + rr, x = g.xt0 + j;
+    if (rr < 1 || rr > SR - 2 || x < g.x0 || x >= g.x1 || y >= g.h - 4) return;
+    const uint16_t *pp = plane + rr * kTileW + j;
+    const uint32_t s = live_score(pp[0], floor);
+    if (s == 0u) return;
+    const bool keep = s > live_score(pp[-kTileW - 1], floor) && s > live_score(pp[-kTileW], floor) &&
+                      s > live_score(pp[-kTileW + 1], floor) && s > live_score(pp[-1], floor) &&
+                      s > live_score(pp[1], floor) && s > live_score(pp[kTileW - 1], floor) &&
+                      s > live_score(pp[kTileW], floor) && s > live_score(pp[kTileW + 1], floor);
+    if (keep) atomic_or_u32(&bits[(rr - 1) * g.ww + (x >> 5)], 1u << (x & 31));
+}
+
+// the chunk's keypoint list (the common case)
+template <int MODE, int SR>
+FDF_HD void nms_list(int tid, uint32_t kn, const uint16_t *klist, const uint16_t *plane, uint32_t *bits,
                      const ChunkGeo &g, uint32_t tag) {
-    const uint32_t floor = tag << 12;
-    for (uint32_t i = (uint32_t)lane; i < qn; i += 32u) {
-        const uint32_t ent = wqueue[i];
-        if (!(ent & 0x8000u)) continue;
-        const int rr = (int)((ent >> 8) & 0x7fu), j = (int)(ent & 0xffu);
-        const int y = g.ys0 + rr, x = g.xt0 + j;
-        if (rr < 1 || rr > SR - 2 || x < g.x0 || x >= g.x1 || y >= g.h - 4) continue;
-        const uint16_t *row = plane + rr * kPlaneW;
-        const int xl = (x - 1) & (kPlaneW - 1), xc = x & (kPlaneW - 1), xr = (x + 1) & (kPlaneW - 1);
-        const uint32_t s = row[xc] & 0xfffu;
-        const bool keep = s > live_score(row[xl - kPlaneW], floor) && s > live_score(row[xc - kPlaneW], floor) &&
-                          s > live_score(row[xr - kPlaneW], floor) && s > live_score(row[xl], floor) &&
-                          s > live_score(row[xr], floor) && s > live_score(row[xl + kPlaneW], floor) &&
-                          s > live_score(row[xc + kPlaneW], floor) && s > live_score(row[xr + kPlaneW], floor);
-        if (keep) atomic_or_u32(&bits[(rr - 1) * g.ww + (x >> 5)], 1u << (x & 31));
+    for (uint32_t i = (uint32_t)tid; i < kn; i += (uint32_t)kComputeThreads) {
+        const uint32_t ent = klist[i];
+        nms_one<MODE, SR>((int)(ent >> 8), (int)(ent & 0xffu), plane, bits, g, tag << 12);
+    }
+}
+
+// every cell of the plane (only when the list overflowed: very dense content)
+template <int MODE, int SR>
+FDF_HD void nms_dense(int tid, const uint16_t *plane, uint32_t *bits, const ChunkGeo &g, uint32_t tag) {
+    for (int i = tid; i < SR * kTileW; i += kComputeThreads) {
+        if (plane[i] >= (tag << 12)) nms_one<MODE, SR>(i / kTileW, i % kTileW, plane, bits, g, tag << 12);
     }
 }
 

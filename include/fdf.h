@@ -62,7 +62,8 @@ void fdf_destroy(fdf_ctx *ctx);
  * fast_simd.rs:307-308, 330).  threshold / count / nms are Config's three fields (lib.rs:38-52).
  * Writes up to `cap` points to the HOST array `out` in the reference's order and the number found
  * to *n_out.  If more than cap were found, returns FDF_ERR_CAPACITY with *n_out = number found
- * (the first cap points are valid).  w < 7 or h < 7 yields 0 points.
+ * (the contents of `out` are then unspecified: call again with room for *n_out points).
+ * w < 7 or h < 7 yields 0 points.
  */
 fdf_status fdf_detect(fdf_ctx *ctx, const uint8_t *img, uint32_t w, uint32_t h, uint32_t pitch,
                       uint8_t threshold, uint8_t count, uint8_t nms, fdf_point *out, size_t cap,
@@ -86,8 +87,9 @@ fdf_status fdf_detect_batch(fdf_ctx *ctx, const uint8_t *frames, uint32_t n_fram
  * cudaStream_t; NULL = the CUDA default stream) and the call returns without synchronising.
  * d_frames must be 16-byte aligned with pitch and frame_stride multiples of 16 (TMA tensor-map
  * requirements); otherwise FDF_ERR_INVALID_ARGUMENT.  d_offsets receives n_frames + 1 entries;
- * if offsets[n_frames] > cap the points beyond cap were dropped.
- * Uses the context's scan workspace: calls on one context must be stream-ordered.
+ * if offsets[n_frames] > cap the output is incomplete (its contents are unspecified).
+ * Uses the context's workspace and staging buffer (cap points): calls on one context must be
+ * stream-ordered.
  */
 fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_frames, uint32_t w,
                              uint32_t h, uint32_t pitch, uint64_t frame_stride, uint8_t threshold,
@@ -101,7 +103,8 @@ fdf_status fdf_synth_frames_device(fdf_ctx *ctx, uint8_t *d_frames, uint32_t n_f
                                    uint32_t h, uint32_t pitch, uint64_t frame_stride, uint64_t seed,
                                    uint32_t first_frame, uint32_t kind, uint32_t amp, void *stream);
 
-/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+/* Number of kernels this context has launched so far (bench.py's gpu_launches): three per detection call
+ * (detection, offset scan, gather) and one per synthetic-frame call. */
 uint64_t fdf_kernel_launches(const fdf_ctx *ctx);
 
 /* Device-side flags of the last fdf_detect_device-family call on this context, read back with a

@@ -36,26 +36,21 @@ def emulator():
     lib = C.CDLL(entry.build_host_emulator())
     lib.fdf_emulate_detect.restype = C.c_int64
     lib.fdf_emulate_detect.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, C.c_uint8,
-                                       C.c_uint8, C.c_int, C.c_void_p, C.c_size_t]
+                                       C.c_uint8, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.fdf_core_check.restype = C.c_int64
     lib.fdf_core_check.argtypes = [C.c_uint64, C.c_uint64]
 
-    def run(img, t, n, nms, sr, late_nms=None):
-        """late_nms=True emulates the interleaving in which every warp's NMS pass of chunk c runs after phases
-        A+B of chunk c+1 (the furthest the kernel's one barrier per chunk lets warps drift apart); None = both."""
+    def run(img, t, n, nms, sr, want_fallbacks=False):
+        """Runs the kernel's phase bodies on the CPU.  want_fallbacks: also return how many chunks took the
+        queue-overflow (row group) path and the dense-NMS path."""
         img = np.ascontiguousarray(img)
         h, w = img.shape
         cap = max(1, w * h)
-        results = []
-        for late in ((False, True) if late_nms is None else (late_nms,)):
-            out = np.zeros((cap, 2), np.uint32)
-            k = lib.fdf_emulate_detect(img.ctypes.data, w, h, w, t, n, nms, sr | (1024 if late else 0),
-                                       out.ctypes.data, cap)
-            assert k >= 0, k
-            results.append(out[:k].copy())
-        for r in results[1:]:
-            assert r.shape == results[0].shape and np.array_equal(r, results[0]), "interleavings disagree"
-        return results[0]
+        out = np.zeros((cap, 2), np.uint32)
+        fb = np.zeros(2, np.int32)
+        k = lib.fdf_emulate_detect(img.ctypes.data, w, h, w, t, n, nms, sr, out.ctypes.data, cap, fb.ctypes.data)
+        assert k >= 0, k
+        return (out[:k].copy(), fb.tolist()) if want_fallbacks else out[:k].copy()
 
     run.core_check = lib.fdf_core_check
     return run

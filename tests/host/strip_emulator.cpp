@@ -17,64 +17,90 @@ namespace {
 
 using namespace fdf;
 
-// late_nms: run the NMS pass of chunk c only after phases A+B of chunk c+1 -- the most extreme
-// interleaving the kernel's single per-chunk barrier allows (fast warps one chunk ahead).
+// Mirrors the kernel's per-chunk schedule: phase A (with the previous chunk's list NMS in the same barrier
+// interval), barrier, phase B (or the row-group fallback when the queue overflowed), barrier, then either
+// the dense NMS (list overflow) or a deferred list NMS.  `small_caps` has no effect on the code paths (the
+// capacities are compile-time); dense inputs reach the fallbacks by themselves.
 template <int MODE, int SR>
-int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2 *out, size_t cap, bool late_nms) {
+int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2 *out, size_t cap, int *fallbacks) {
     constexpr int OUT_R = out_rows(MODE, SR);
     constexpr int TR = tile_rows(SR);
-    constexpr int QW = (SR / kComputeWarps) * kTileW;
     const long long rows = (long long)h - 2 * first_out_row(MODE);
     if (w < 7 || h < 7 || rows <= 0) return 0;
     const int S = (int)((rows + OUT_R - 1) / OUT_R);
     const int NC = chunks_per_row(w);
     const int WW = (w + 31) / 32;
-    alignas(16) static uint8_t tiles[2][tile_rows(64) * kTileW];
-    std::vector<uint16_t> plane((size_t)SR * kPlaneW);
-    std::vector<uint16_t> queue[2] = {std::vector<uint16_t>((size_t)kComputeWarps * QW),
-                                      std::vector<uint16_t>((size_t)kComputeWarps * QW)};
-    uint32_t qcount[2][kComputeWarps];
+    alignas(16) static uint8_t tile[tile_rows(64) * kTileW];
+    std::vector<uint16_t> plane((size_t)SR * kTileW), queue(kQueueCap), klists(2 * kKlistCap);
+    uint32_t qcount[2] = {0, 0}, kcount[2] = {0, 0};
     std::vector<uint32_t> bits((size_t)OUT_R * WW);
     const uint32_t kbias = filter_kbias((uint32_t)t);
     unsigned long long total = 0;
+    uint32_t gc = 0;
     for (int strip = 0; strip < S; strip++) {
         std::fill(bits.begin(), bits.end(), 0u);
-        auto run_nms = [&](int c) {
-            const ChunkGeo g = make_geo<MODE>(w, h, WW, strip, c, SR);
-            const uint32_t tag = (uint32_t)(c % kTagPeriod) + 1u;
-            for (int warp = 0; warp < kComputeWarps; warp++)
-                for (int lane = 0; lane < 32; lane++)
-                    nms_pass<MODE, SR>(lane, qcount[c & 1][warp], queue[c & 1].data() + warp * QW, plane.data(),
-                                       bits.data(), g, tag);
-        };
-        for (int c = 0; c < NC; c++) {
+        bool nms_pending = false;
+        uint32_t pend_kn = 0;
+        for (int c = 0; c < NC; c++, gc++) {
+            const uint32_t cp = gc & 1u;
             const ChunkGeo g = make_geo<MODE>(w, h, WW, strip, c, SR);
             const uint32_t tag = (uint32_t)(c % kTagPeriod) + 1u;
             const int ty0 = g.ys0 - 3;
             if (g.xt0 % 16 != 0) return -16;  // TMA: innermost box start must be 16-byte aligned
-            uint8_t *tile = tiles[c & 1];
+            if (MODE != NMS_OFF && c == 0) std::fill(plane.begin(), plane.end(), (uint16_t)0);
+            // the deferred NMS of chunk c-1 reads the plane before this chunk's tile is touched
+            if (MODE != NMS_OFF && nms_pending) {
+                const ChunkGeo gp = make_geo<MODE>(w, h, WW, strip, c - 1, SR);
+                for (int tid = 0; tid < kComputeThreads; tid++)
+                    nms_list<MODE, SR>(tid, pend_kn, klists.data() + (cp ^ 1u) * kKlistCap, plane.data(), bits.data(), gp,
+                                       (uint32_t)((c - 1) % kTagPeriod) + 1u);
+                nms_pending = false;
+            }
             for (int r = 0; r < TR; r++)      // what the TMA tiled load delivers: zero fill outside the image
                 for (int j = 0; j < kTileW; j++) {
                     const int y = ty0 + r, x = g.xt0 + j;
                     tile[r * kTileW + j] = (y >= 0 && y < h && x >= 0 && x < w) ? img[(size_t)y * pitch + x] : 0;
                 }
-            if (MODE != NMS_OFF && tag == 1u) {  // the kernel's barrier + clear + barrier
-                if (late_nms && c > 0) run_nms(c - 1);
-                std::fill(plane.begin(), plane.end(), (uint16_t)0);
-            }
-            for (int warp = 0; warp < kComputeWarps; warp++) {
-                uint16_t *wq = queue[c & 1].data() + warp * QW;
-                qcount[c & 1][warp] = 0;
-                for (int lane = 0; lane < 32; lane++) phase_a<MODE, SR>(warp, lane, tile, wq, &qcount[c & 1][warp], g, kbias);
-                if (qcount[c & 1][warp] > (uint32_t)QW) return -17;
-                for (int lane = 0; lane < 32; lane++)
-                    phase_b<MODE, SR>(lane, qcount[c & 1][warp], tile, wq, plane.data(), bits.data(), g, t, n, tag);
+            for (int tid = 0; tid < kComputeThreads; tid++)
+                phase_a<MODE, SR>(tid, tile, queue.data(), &qcount[cp], g, kbias, 0, SR);
+            const uint32_t qn = qcount[cp];
+            qcount[cp ^ 1u] = 0;
+            kcount[cp ^ 1u] = 0;
+            if (MODE != NMS_OFF && c != 0 && tag == 1u) std::fill(plane.begin(), plane.end(), (uint16_t)0);
+            bool dense = false;
+            if (qn <= (uint32_t)kQueueCap) {
+                for (int tid = 0; tid < kComputeThreads; tid++)
+                    phase_b<MODE, SR>(tid, qn, tile, queue.data(), plane.data(), klists.data() + cp * kKlistCap, &kcount[cp],
+                                      bits.data(), g, t, n, tag);
+            } else {
+                dense = true;
+                if (fallbacks) fallbacks[0]++;
+                for (int lo = 0; lo < SR; lo += kGroupRows) {
+                    qcount[cp] = 0;
+                    for (int tid = 0; tid < kComputeThreads; tid++)
+                        phase_a<MODE, SR>(tid, tile, queue.data(), &qcount[cp], g, kbias, lo, lo + kGroupRows);
+                    if (qcount[cp] > (uint32_t)kQueueCap) return -18;
+                    for (int tid = 0; tid < kComputeThreads; tid++)
+                        phase_b<MODE, SR>(tid, qcount[cp], tile, queue.data(), plane.data(), klists.data() + cp * kKlistCap,
+                                          &kcount[cp], bits.data(), g, t, n, tag);
+                }
             }
             if (MODE != NMS_OFF) {
-                if (!late_nms) run_nms(c);
-                else if (c > 0 && tag != 1u) run_nms(c - 1);
-                if (late_nms && c == NC - 1) run_nms(c);
+                const uint32_t kn = kcount[cp];
+                if (dense || kn > (uint32_t)kKlistCap) {
+                    if (fallbacks) fallbacks[1]++;
+                    for (int tid = 0; tid < kComputeThreads; tid++) nms_dense<MODE, SR>(tid, plane.data(), bits.data(), g, tag);
+                } else {
+                    nms_pending = true;
+                    pend_kn = kn;
+                }
             }
+        }
+        if (MODE != NMS_OFF && nms_pending) {
+            const ChunkGeo gp = make_geo<MODE>(w, h, WW, strip, NC - 1, SR);
+            for (int tid = 0; tid < kComputeThreads; tid++)
+                nms_list<MODE, SR>(tid, pend_kn, klists.data() + ((gc - 1u) & 1u) * kKlistCap, plane.data(), bits.data(), gp,
+                                   (uint32_t)((NC - 1) % kTagPeriod) + 1u);
         }
         const ChunkGeo g0 = make_geo<MODE>(w, h, WW, strip, 0, SR);
         for (int i = 0; i < OUT_R * WW; i++) {  // the emit warp's walk, in word order
@@ -100,12 +126,11 @@ uint64_t splitmix(uint64_t &s) {
 extern "C" {
 
 int64_t fdf_emulate_detect(const uint8_t *img, uint32_t w, uint32_t h, uint32_t pitch, uint8_t t, uint8_t n,
-                           uint8_t nms, int sr, fdf_oracle_point *out, size_t cap) {
+                           uint8_t nms, int sr, fdf_oracle_point *out, size_t cap, int *fallbacks) {
     uint2 *o = reinterpret_cast<uint2 *>(out);
-    const bool late = (sr & 1024) != 0;  // flag bit: emulate the "NMS one chunk late" interleaving
-    sr &= 1023;
+    if (fallbacks) fallbacks[0] = fallbacks[1] = 0;  // [0] queue overflow -> row groups, [1] dense NMS
 #define CASE(M, S) \
-    if (nms == M && sr == S) return emulate<M, S>(img, (int)w, (int)h, (int)pitch, t, n, o, cap, late);
+    if (nms == M && sr == S) return emulate<M, S>(img, (int)w, (int)h, (int)pitch, t, n, o, cap, fallbacks);
     CASE(0, 16) CASE(0, 32) CASE(1, 16) CASE(1, 32) CASE(2, 16) CASE(2, 32)
 #undef CASE
     return -1;

@@ -71,6 +71,18 @@ def test_wide_image_many_chunks_tag_wrap(emulator, oracle_mod):
     assert same_points(emulator(img, 40, 9, 1, 16), oracle_mod.detect(img, 40, 9, 1))
 
 
+def test_dense_content_takes_the_fallback_paths(emulator, oracle_mod):
+    # uniform noise at a low threshold: > 2048 candidates per chunk (row-group path) and > 1024 keypoints per
+    # chunk (dense NMS path); both must be exercised and still match the oracle bit for bit
+    img = oracle_mod.synth_frame(520, 80, seed=5, frame=0, kind=1)
+    for nms in (0, 1, 2):
+        got, fb = emulator(img, 3, 9, nms, 32, want_fallbacks=True)
+        assert same_points(got, oracle_mod.detect(img, 3, 9, nms))
+        assert fb[0] > 0 and (nms == 0 or fb[1] > 0), fb
+    got, fb = emulator(oracle_mod.synth_frame(520, 80, 6, 0, 0, 4), 16, 9, 1, 32, want_fallbacks=True)
+    assert fb == [0, 0]  # realistic content never leaves the fast path
+
+
 def test_saturated_and_flat_images(emulator, oracle_mod):
     for v in (0, 255, 17):
         img = np.full((50, 300), v, np.uint8)
