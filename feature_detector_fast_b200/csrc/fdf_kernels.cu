@@ -4,7 +4,7 @@
 //
 //   work item  = (frame, strip of full-width rows), handed out through an atomic ticket in row-major
 //                order, which is what makes the decoupled look-back deadlock-free.
-//   8 compute warps, per chunk of a strip (two named barriers per chunk):
+//   8 warps, per chunk of a strip (two block barriers per chunk):
 //     TMA 3-D tiled load (u8 tile 256 x (SR+6), zero-filled outside the image, double buffered,
 //     issued two chunks ahead -- across strip boundaries --, completion on an mbarrier)  -> shared memory
 //     phase A  : dense SWAR filter, 16 centres per thread (LDS.128 + PRMT + VABSDIFF4 + LOP3),
@@ -14,10 +14,10 @@
 //                rotate-AND arc test -> score in registers -> tagged score plane + keypoint list
 //                                                                     (fast_simd.rs:115-297, 623-749)
 //     NMS pass : strict 3x3 maximum on the shared-memory score plane          (fast_simd.rs:588-616)
-//                survivors set one bit in the strip's shared-memory bit plane (double buffered)
-//   1 emit warp, per finished strip (while the compute warps already work on the next one):
-//     popcount of the bit plane (warp prefix sums), then the bits are expanded to (x, y) points, in
-//     row-major order, into a bump-allocated run of the staging buffer; (count, position) is recorded.
+//                survivors set one bit in the strip's shared-memory bit plane
+//   per finished strip: popcount of the bit plane (warp + block prefix sums), then the bits are expanded
+//     to (x, y) points, in row-major order, into a bump-allocated run of the staging buffer;
+//     (count, position) is recorded.  The next strip's first tiles are already in flight.
 //
 // Two small kernels finish the ordered compaction (fast_simd.rs:550, 596-613: output is row-major):
 //   fdf_scan_kernel   : exclusive prefix sum of the per-strip counts in (frame, strip) order -- block scan
@@ -126,7 +126,7 @@ struct Layout {
     static constexpr int klist_bytes = (MODE == NMS_OFF) ? 0 : 2 * kKlistCap * 2;  // two lists (chunk parity)
     static constexpr int misc_off = klist_off + klist_bytes;
     static constexpr int misc_bytes = 128;
-    static constexpr int bits_off = misc_off + misc_bytes;  // two bit planes of out_rows x words_per_row words
+    static constexpr int bits_off = misc_off + misc_bytes;  // bit plane of out_rows x words_per_row words
     static_assert(tile_bytes % 128 == 0, "TMA destination must stay 128-byte aligned");
     static_assert(SR % 16 == 0 && SR <= 64, "phase A walks rows in steps of 16; queue entries hold 6 row bits");
     static_assert(kGroupRows * kTileW <= kQueueCap, "a row group must always fit the candidate queue");
@@ -173,7 +173,7 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long *statu
 
 // ---- the detection kernel ----------------------------------------------------------------------
 template <int MODE, int SR>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p) {
     using L = Layout<MODE, SR>;
     constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;  // score halo (rows and columns) needed by the 3x3 NMS
@@ -185,13 +185,12 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L::queue_off);
     uint16_t *klists = reinterpret_cast<uint16_t *>(smem + L::klist_off);               // [2][kKlistCap]
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::misc_off);             // [2] tile landed
-    uint64_t *bits_full = reinterpret_cast<uint64_t *>(smem + L::misc_off + 16);       // [2] strip finished
-    uint64_t *bits_empty = reinterpret_cast<uint64_t *>(smem + L::misc_off + 32);      // [2] strip emitted
-    uint32_t *qcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 48);          // [2] queue fill (chunk parity)
-    uint32_t *kcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 56);          // [2] keypoints of the chunk
-    uint32_t *s_item = reinterpret_cast<uint32_t *>(smem + L::misc_off + 64);          // [2] item of each bit plane
-    uint32_t *s_ticket = reinterpret_cast<uint32_t *>(smem + L::misc_off + 72);        // [4] prefetched tickets
-    uint32_t *bits = reinterpret_cast<uint32_t *>(smem + L::bits_off);                  // [2][OUT_R][words_per_row]
+    uint32_t *qcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 16);          // [2] queue fill (chunk parity)
+    uint32_t *kcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 24);          // [2] keypoints of the chunk
+    uint32_t *s_ticket = reinterpret_cast<uint32_t *>(smem + L::misc_off + 32);        // [2] next strip's ticket
+    uint32_t *warp_sums = reinterpret_cast<uint32_t *>(smem + L::misc_off + 48);       // [8]
+    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 80);
+    uint32_t *bits = reinterpret_cast<uint32_t *>(smem + L::bits_off);                  // [OUT_R][words_per_row]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = (int)p.w, H = (int)p.h;
@@ -204,194 +203,178 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         tma_prefetch_desc(&tmap);
         mbar_init(&full_bar[0], 1);
         mbar_init(&full_bar[1], 1);
-        mbar_init(&bits_full[0], 1);
-        mbar_init(&bits_full[1], 1);
-        mbar_init(&bits_empty[0], 1);
-        mbar_init(&bits_empty[1], 1);
         fence_mbar_init();
         qcount[0] = qcount[1] = 0u;
         kcount[0] = kcount[1] = 0u;
-        s_ticket[0] = atomicAdd(p.ticket, 1u);  // items start in scan order => look-back cannot deadlock
+        s_ticket[0] = atomicAdd(p.ticket, 1u);
     }
-    for (int i = tid; i < 2 * nwords; i += kThreads) bits[i] = 0u;
+    for (int i = tid; i < nwords; i += kThreads) bits[i] = 0u;
     __syncthreads();
 
-    if (warp < kComputeWarps) {
-        // ======================= compute warps =======================
-        const int t = (int)p.threshold, n = (int)p.count;
-        const uint32_t kbias = filter_kbias(p.threshold);
-        const int ahead = NC >= 2 ? 2 : 1;  // tiles requested this many chunks ahead (never beyond the next strip)
-        // `nxt` is the ticket of the strip after `cur`.  Thread 0 draws it as late as the tile look-ahead allows
-        // (a drawn ticket that is not being worked on yet delays every later item's look-back) and publishes
-        // it through s_ticket[2 + parity]; the other threads pick it up at the end of the strip.
-        uint32_t cur = s_ticket[0], nxt = 0xffffffffu;
-        bool have_nxt = false;
-        uint32_t gc = 0;  // chunks processed by this CTA so far: tile stage = gc & 1, mbarrier parity = (gc >> 1) & 1
+    const int t = (int)p.threshold, n = (int)p.count;
+    const uint32_t kbias = filter_kbias(p.threshold);
+    const int ahead = NC >= 2 ? 2 : 1;  // tiles requested this many chunks ahead (never beyond the next strip)
+    // `nxt` is the ticket of the strip after `cur`.  Thread 0 draws it when the tile look-ahead first needs
+    // it and publishes it through s_ticket[1 - parity]; everybody picks it up at the end of the strip.
+    uint32_t cur = s_ticket[0], nxt = 0xffffffffu;
+    bool have_nxt = false;
+    uint32_t gc = 0;  // chunks processed by this CTA so far: tile stage = gc & 1, mbarrier parity = (gc >> 1) & 1
 
-        // request the tile of chunk c of the current strip (c < NC) or of chunk c - NC of the next strip
-        auto request_tile = [&](int c, uint32_t stream_index) {
-            uint32_t item = cur;
-            if (c >= NC) {
-                if (c - NC >= NC) return;
-                if (!have_nxt) {
-                    nxt = atomicAdd(p.ticket, 1u);
-                    have_nxt = true;
-                }
-                item = nxt;
-                c -= NC;
+    // request the tile of chunk c of the current strip (c < NC) or of chunk c - NC of the next strip
+    auto request_tile = [&](int c, uint32_t stream_index) {
+        uint32_t item = cur;
+        if (c >= NC) {
+            if (c - NC >= NC) return;
+            if (!have_nxt) {
+                nxt = atomicAdd(p.ticket, 1u);
+                have_nxt = true;
             }
-            if (item >= total_items) return;
-            const uint32_t frame = item / p.strips_per_frame;
-            const uint32_t strip = item - frame * p.strips_per_frame;
-            const int ty0 = first_out_row(MODE) + (int)strip * OUT_R - HS - 3;  // image row of tile row 0
-            const uint32_t stage = stream_index & 1u;
-            mbar_expect_tx(&full_bar[stage], (uint32_t)L::tile_bytes);
-            tma_load_3d(tiles + stage * L::tile_bytes, &tmap, c * kChunkW - kTileLead, ty0, (int)frame,
-                        &full_bar[stage]);
-        };
-        if (tid == 0)
-            for (int c = 0; c < ahead; c++) request_tile(c, (uint32_t)c);
-
-        for (uint32_t it = 0;; it++) {
-            const int buf = (int)(it & 1u);
-            if (tid == 0) {
-                mbar_wait(&bits_empty[buf], ((it >> 1) & 1u) ^ 1u, p.flags);  // bit plane `buf` emitted and zeroed
-                s_item[buf] = cur;
-                if (cur >= total_items) mbar_arrive(&bits_full[buf]);  // hand the end marker to the emit warp
-            }
-            if (cur >= total_items) break;
-            const uint32_t frame = cur / p.strips_per_frame;
-            const uint32_t strip = cur - frame * p.strips_per_frame;
-            uint32_t *sbits = bits + buf * nwords;
-            bool nms_pending = false;  // the NMS pass of the previous chunk still has to run
-            uint32_t pend_kn = 0;
-
-            for (int c = 0; c < NC; c++, gc++) {
-                const uint32_t stage = gc & 1u, cp = gc & 1u;
-                const uint8_t *tile = tiles + stage * L::tile_bytes;
-                const ChunkGeo g = make_geo<MODE>(W, H, WW, (int)strip, c, SR);
-                const uint32_t tag = (uint32_t)(c % kTagPeriod) + 1u;
-                if (MODE != NMS_OFF && c == 0) {  // strip start: restart the tag sequence on a cleared plane
-                    uint4 *pz = reinterpret_cast<uint4 *>(plane) + tid;
-#pragma unroll
-                    for (int i = 0; i < L::plane_bytes / 16 / kComputeThreads; i++)
-                        pz[i * kComputeThreads] = make_uint4(0u, 0u, 0u, 0u);
-                }
-                if (MODE != NMS_OFF && nms_pending) {  // overlaps with this chunk's phase A (other warps)
-                    const ChunkGeo gp = make_geo<MODE>(W, H, WW, (int)strip, c - 1, SR);
-                    nms_list<MODE, SR>(tid, pend_kn, klists + (cp ^ 1u) * kKlistCap, plane, sbits, gp,
-                                       (uint32_t)((c - 1) % kTagPeriod) + 1u);
-                    nms_pending = false;
-                }
-                mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags);
-                phase_a<MODE, SR>(tid, tile, queue, &qcount[cp], g, kbias, 0, SR);
-                bar_compute();  // B1: queue complete; previous chunk fully suppressed
-
-                const uint32_t qn = qcount[cp];
-                if (tid == 0) {
-                    qcount[cp ^ 1u] = 0u;
-                    kcount[cp ^ 1u] = 0u;
-                }
-                if (MODE != NMS_OFF && c != 0 && tag == 1u) {  // every 15 chunks: restart the tags
-                    uint4 *pz = reinterpret_cast<uint4 *>(plane) + tid;
-#pragma unroll
-                    for (int i = 0; i < L::plane_bytes / 16 / kComputeThreads; i++)
-                        pz[i * kComputeThreads] = make_uint4(0u, 0u, 0u, 0u);
-                    bar_compute();
-                }
-                bool dense = false;
-                if (qn <= (uint32_t)kQueueCap) {
-                    phase_b<MODE, SR>(tid, qn, tile, queue, plane, klists + cp * kKlistCap, &kcount[cp], sbits, g, t, n,
-                                      tag);
-                } else {  // very dense content: redo the chunk kGroupRows rows at a time
-                    dense = true;
-                    for (int lo = 0; lo < SR; lo += kGroupRows) {
-                        bar_compute();
-                        if (tid == 0) qcount[cp] = 0u;
-                        bar_compute();
-                        phase_a<MODE, SR>(tid, tile, queue, &qcount[cp], g, kbias, lo, lo + kGroupRows);
-                        bar_compute();
-                        phase_b<MODE, SR>(tid, qcount[cp], tile, queue, plane, klists + cp * kKlistCap, &kcount[cp],
-                                          sbits, g, t, n, tag);
-                    }
-                }
-                bar_compute();  // B2: tile[stage] is free again; every score of this chunk is in the plane
-
-                if (tid == 0) request_tile(c + ahead, gc + (uint32_t)ahead);
-                if (MODE != NMS_OFF) {
-                    const uint32_t kn = kcount[cp];
-                    if (dense || kn > (uint32_t)kKlistCap) {
-                        nms_dense<MODE, SR>(tid, plane, sbits, g, tag);
-                        bar_compute();  // the plane may be re-tagged / the counters reused
-                    } else {
-                        nms_pending = true;
-                        pend_kn = kn;
-                    }
-                }
-            }
-            if (MODE != NMS_OFF && nms_pending) {
-                const ChunkGeo gp = make_geo<MODE>(W, H, WW, (int)strip, NC - 1, SR);
-                nms_list<MODE, SR>(tid, pend_kn, klists + ((gc - 1u) & 1u) * kKlistCap, plane, sbits, gp,
-                                   (uint32_t)((NC - 1) % kTagPeriod) + 1u);
-            }
-            if (tid == 0) {
-                if (!have_nxt) nxt = atomicAdd(p.ticket, 1u);  // (only when the look-ahead never reached the next strip)
-                s_ticket[2 + buf] = nxt;
-                have_nxt = false;
-            }
-            bar_compute();  // strip end: all bits of the strip are set; plane and lists are free
-            if (tid == 0) mbar_arrive(&bits_full[buf]);
-            cur = s_ticket[2 + buf];  // the slot alternates per strip, so it is not rewritten before everyone read it
+            item = nxt;
+            c -= NC;
         }
-    } else {
-        // ======================= emit warp =======================
-        for (uint32_t it = 0;; it++) {
-            const int buf = (int)(it & 1u);
-            mbar_wait(&bits_full[buf], (it >> 1) & 1u, p.flags);
-            const uint32_t item = s_item[buf];
-            if (item >= total_items) break;
-            const uint32_t strip = item % p.strips_per_frame;
-            const int y0 = first_out_row(MODE) + (int)strip * OUT_R;  // first row this strip emits
-            uint32_t *sbits = bits + buf * nwords;
+        if (item >= total_items) return;
+        const uint32_t frame = item / p.strips_per_frame;
+        const uint32_t strip = item - frame * p.strips_per_frame;
+        const int ty0 = first_out_row(MODE) + (int)strip * OUT_R - HS - 3;  // image row of tile row 0
+        const uint32_t stage = stream_index & 1u;
+        mbar_expect_tx(&full_bar[stage], (uint32_t)L::tile_bytes);
+        tma_load_3d(tiles + stage * L::tile_bytes, &tmap, c * kChunkW - kTileLead, ty0, (int)frame, &full_bar[stage]);
+    };
+    if (tid == 0)
+        for (int c = 0; c < ahead; c++) request_tile(c, (uint32_t)c);
 
-            uint32_t cnt = 0;
-            for (int i = lane; i < nwords; i += 32) cnt += (uint32_t)__popc(sbits[i]);
+    for (uint32_t it = 0; cur < total_items; it++) {
+        const uint32_t frame = cur / p.strips_per_frame;
+        const uint32_t strip = cur - frame * p.strips_per_frame;
+        bool nms_pending = false;  // the NMS pass of the previous chunk still has to run
+        uint32_t pend_kn = 0;
+
+        for (int c = 0; c < NC; c++, gc++) {
+            const uint32_t stage = gc & 1u, cp = gc & 1u;
+            const uint8_t *tile = tiles + stage * L::tile_bytes;
+            const ChunkGeo g = make_geo<MODE>(W, H, WW, (int)strip, c, SR);
+            const uint32_t tag = (uint32_t)(c % kTagPeriod) + 1u;
+            if (MODE != NMS_OFF && c == 0) {  // strip start: restart the tag sequence on a cleared plane
+                uint4 *pz = reinterpret_cast<uint4 *>(plane) + tid;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);  // strip total
-            unsigned long long o = 0ull;
-            if (lane == 0) {
-                if (cnt != 0u) o = atomicAdd(p.cursor, (unsigned long long)cnt);  // this strip's run in staging
-                p.item_count[item] = cnt;
-                p.item_src[item] = o;
+                for (int i = 0; i < L::plane_bytes / 16 / kThreads; i++) pz[i * kThreads] = make_uint4(0u, 0u, 0u, 0u);
             }
-            o = __shfl_sync(0xffffffffu, o, 0);
-            if (cnt != 0u) {
-                int i = lane;
-                int row = i / WW, col = i - row * WW;
-                for (int base = 0; base < nwords; base += 32, i += 32) {
-                    const uint32_t m = i < nwords ? sbits[i] : 0u;
-                    const uint32_t c = (uint32_t)__popc(m);
-                    uint32_t incl = c;
+            if (MODE != NMS_OFF && nms_pending) {  // overlaps with this chunk's phase A (other warps)
+                const ChunkGeo gp = make_geo<MODE>(W, H, WW, (int)strip, c - 1, SR);
+                nms_list<MODE, SR>(tid, pend_kn, klists + (cp ^ 1u) * kKlistCap, plane, bits, gp,
+                                   (uint32_t)((c - 1) % kTagPeriod) + 1u);
+                nms_pending = false;
+            }
+            mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags);
+            phase_a<MODE, SR>(tid, tile, queue, &qcount[cp], g, kbias, 0, SR);
+            __syncthreads();  // B1: queue complete; previous chunk fully suppressed
+
+            const uint32_t qn = qcount[cp];
+            if (tid == 0) {
+                qcount[cp ^ 1u] = 0u;
+                kcount[cp ^ 1u] = 0u;
+            }
+            if (MODE != NMS_OFF && c != 0 && tag == 1u) {  // every 15 chunks: restart the tags
+                uint4 *pz = reinterpret_cast<uint4 *>(plane) + tid;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += v;
-                    }
-                    if (m != 0u) {
-                        emit_word(m, (uint32_t)col * 32u, (uint32_t)(y0 + row), o + (incl - c), p.cap, p.staging);
-                        sbits[i] = 0u;  // leave the plane zeroed for the strip after next
-                    }
-                    o += __shfl_sync(0xffffffffu, incl, 31);
-                    col += 32;
-                    while (col >= WW) {
-                        col -= WW;
-                        row++;
-                    }
+                for (int i = 0; i < L::plane_bytes / 16 / kThreads; i++) pz[i * kThreads] = make_uint4(0u, 0u, 0u, 0u);
+                __syncthreads();
+            }
+            bool dense = false;
+            if (qn <= (uint32_t)kQueueCap) {
+                phase_b<MODE, SR>(tid, qn, tile, queue, plane, klists + cp * kKlistCap, &kcount[cp], bits, g, t, n, tag);
+            } else {  // very dense content: redo the chunk kGroupRows rows at a time
+                dense = true;
+                for (int lo = 0; lo < SR; lo += kGroupRows) {
+                    __syncthreads();
+                    if (tid == 0) qcount[cp] = 0u;
+                    __syncthreads();
+                    phase_a<MODE, SR>(tid, tile, queue, &qcount[cp], g, kbias, lo, lo + kGroupRows);
+                    __syncthreads();
+                    phase_b<MODE, SR>(tid, qcount[cp], tile, queue, plane, klists + cp * kKlistCap, &kcount[cp], bits, g,
+                                      t, n, tag);
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bits_empty[buf]);
+            __syncthreads();  // B2: tile[stage] is free again; every score of this chunk is in the plane
+
+            if (tid == 0) request_tile(c + ahead, gc + (uint32_t)ahead);
+            if (MODE != NMS_OFF) {
+                const uint32_t kn = kcount[cp];
+                if (dense || kn > (uint32_t)kKlistCap) {
+                    nms_dense<MODE, SR>(tid, plane, bits, g, tag);
+                    __syncthreads();  // the plane may be re-tagged / the counters reused
+                } else {
+                    nms_pending = true;
+                    pend_kn = kn;
+                }
+            }
         }
+        if (MODE != NMS_OFF && nms_pending) {
+            const ChunkGeo gp = make_geo<MODE>(W, H, WW, (int)strip, NC - 1, SR);
+            nms_list<MODE, SR>(tid, pend_kn, klists + ((gc - 1u) & 1u) * kKlistCap, plane, bits, gp,
+                               (uint32_t)((NC - 1) % kTagPeriod) + 1u);
+        }
+        if (tid == 0) {
+            if (!have_nxt) nxt = atomicAdd(p.ticket, 1u);  // (only when the look-ahead never reached the next strip)
+            s_ticket[(it + 1u) & 1u] = nxt;
+            have_nxt = false;
+        }
+        __syncthreads();  // strip end: all bits of the strip are set; plane and lists are free
+
+        // ---- strip -> ordered run of points in the staging buffer --------------------------------------
+        const int y0 = first_out_row(MODE) + (int)strip * OUT_R;  // first row this strip emits
+        const EmitRange er = emit_range(warp, nwords);
+        uint32_t cnt = 0;
+        for (int i = er.begin + lane; i < er.end; i += 32) cnt += (uint32_t)__popc(bits[i]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);  // warp total
+        if (lane == 0) warp_sums[warp] = cnt;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t ws = lane < kThreads / 32 ? warp_sums[lane] : 0u;
+            uint32_t wincl = ws;
+#pragma unroll
+            for (int d = 1; d < kThreads / 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, wincl, d);
+                if (lane >= d) wincl += v;
+            }
+            if (lane < kThreads / 32) warp_sums[lane] = wincl - ws;  // exclusive offset of each warp
+            if (lane == kThreads / 32 - 1) {
+                unsigned long long o = 0ull;
+                if (wincl != 0u) o = atomicAdd(p.cursor, (unsigned long long)wincl);  // the strip's run in staging
+                *s_base = o;
+                p.item_count[cur] = wincl;
+                p.item_src[cur] = o;
+            }
+        }
+        __syncthreads();
+        if (cnt != 0u) {  // warp-uniform: this warp's range holds keypoints
+            unsigned long long o = *s_base + warp_sums[warp];
+            int i = er.begin + lane;
+            int row = i / WW, col = i - row * WW;
+            for (int base = er.begin; base < er.end; base += 32, i += 32) {
+                const uint32_t m = i < er.end ? bits[i] : 0u;
+                const uint32_t c = (uint32_t)__popc(m);
+                uint32_t incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                if (m != 0u) {
+                    emit_word(m, (uint32_t)col * 32u, (uint32_t)(y0 + row), o + (incl - c), p.cap, p.staging);
+                    bits[i] = 0u;  // leave the plane zeroed for the next strip
+                }
+                o += __shfl_sync(0xffffffffu, incl, 31);
+                col += 32;
+                while (col >= WW) {
+                    col -= WW;
+                    row++;
+                }
+            }
+        }
+        cur = s_ticket[(it + 1u) & 1u];
+        // (the next strip's first bit is set after its first barrier, i.e. after every warp left this loop)
     }
 }
 
@@ -506,7 +489,7 @@ size_t detect_smem_bytes(int mode, int sr, uint32_t words_per_row) {
     const size_t plane = mode == NMS_OFF ? 0 : (size_t)sr * kTileW * 2;
     const size_t queue = (size_t)kQueueCap * 2;
     const size_t klist = mode == NMS_OFF ? 0 : (size_t)2 * kKlistCap * 2;
-    return 2 * tile + plane + queue + klist + 128 + 2 * (size_t)out_rows(mode, sr) * words_per_row * 4;
+    return 2 * tile + plane + queue + klist + 128 + (size_t)out_rows(mode, sr) * words_per_row * 4;
 }
 
 cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream) {

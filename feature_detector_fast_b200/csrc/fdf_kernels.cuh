@@ -9,9 +9,9 @@ namespace fdf {
 // Geometry shared by host and device.  A frame is cut into STRIPS of full-width rows; a CTA
 // takes one strip at a time (atomic ticket) and walks it left to right in CHUNKS.  For every chunk a 256-byte-wide tile
 // (chunk + halo) is staged into shared memory by one TMA 3-D tiled load.
-constexpr int kComputeWarps = 8;                       // warps that filter / test / score / suppress
+constexpr int kComputeWarps = 8;
 constexpr int kComputeThreads = kComputeWarps * 32;
-constexpr int kThreads = kComputeThreads + 32;         // + one warp that scans and emits finished strips
+constexpr int kThreads = kComputeThreads;              // threads per CTA
 constexpr int kTileW = 256;     // tile width in bytes = TMA box inner extent (the maximum)
 constexpr int kChunkW = 240;    // output columns per chunk (the last chunk of a row may take one more)
 constexpr int kTileLead = 16;   // chunk c's tile starts at image column c*kChunkW - kTileLead: TMA needs the
@@ -23,7 +23,7 @@ constexpr int kTagPeriod = 15;  // score plane entries carry a 4-bit chunk tag (
                                 // plane is cleared at every strip start and every 15 chunks, so entries of
                                 // earlier chunks simply read as "no keypoint" and no per-chunk clear is needed
 constexpr int kQueueCap = 2048; // candidate queue entries per chunk (typical fill: ~200); more -> fallback below
-constexpr int kKlistCap = 1024; // confirmed keypoints per chunk the list NMS handles; more -> dense NMS
+constexpr int kKlistCap = 512;  // confirmed keypoints per chunk the list NMS handles (typical: ~90); more -> dense NMS
 constexpr int kGroupRows = 8;   // fallback for dense content: filter kGroupRows x 256 <= kQueueCap centres at a time
 
 __host__ __device__ constexpr int chunks_per_row(int w) { return (w + kChunkW - 1) / kChunkW; }

@@ -189,8 +189,20 @@ FDF_HD void nms_dense(int tid, const uint16_t *plane, uint32_t *bits, const Chun
 }
 
 // ---- emission: bit plane -> points, row-major -----------------------------------------------------
-// One warp walks the strip's bit plane (out_rows x ww words) 32 words at a time: one word per lane,
-// a warp prefix sum gives every lane its output offset.
+// The strip's bit plane (out_rows x ww words) is cut into one contiguous range per warp; a warp walks
+// its range 32 words at a time: one word per lane, a warp prefix sum gives every lane its offset.
+struct EmitRange {
+    int begin, end;  // word indices into bits[out_rows * ww]
+};
+
+FDF_HD EmitRange emit_range(int warp, int nwords) {
+    const int wpw = (nwords + kThreads / 32 - 1) / (kThreads / 32);
+    EmitRange r;
+    r.begin = min(warp * wpw, nwords);
+    r.end = min(r.begin + wpw, nwords);
+    return r;
+}
+
 // writes the points of one bit-plane word (row `y`, columns xw .. xw+31) starting at index o
 FDF_HD void emit_word(uint32_t m, uint32_t xw, uint32_t y, unsigned long long o, unsigned long long cap, uint2 *out) {
     while (m) {
