@@ -14,8 +14,9 @@ step: one NCCL all-gather of per-frame keypoint counts -> global CSR offsets.
   e2e          same metric through the C-ABI call `fdf_detect_batch` on HOST (pinned) buffers: host->device
                copy of the frames and device->host copy of offsets + keypoints inside the timed region
   roofline     dominant kernel (fdf_detect_kernel): algorithmic bytes (W*H per frame read once + 8 B per
-               keypoint + 8 B per frame offset) / CUDA-event duration of the launch, against the measured
-               HBM copy bandwidth in MEASURED_PEAKS.json
+               keypoint + 8 B per frame offset) / CUDA-event duration of that launch (events recorded by the
+               library on the launching stream during the timed steps), against the measured HBM copy
+               bandwidth in MEASURED_PEAKS.json
   cpu_baseline AVX2 port of the reference's fast_simd.rs (oracle/fdf_avx2_port.cpp) on the host cores,
                bounded sample of the same frames (rank 0, N = 1 only); reported, not the target
 
@@ -240,17 +241,15 @@ def main():
 
     # ---- device-resident timing: exactly K steps, CUDA events, max over ranks --------------------
     sampler = ClockSampler(local_rank)
+    det.set_timing(args.steps)  # CUDA events around each launch, recorded by the library on the launching stream
     launches0 = det.kernel_launches
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if rank == 0:
         sampler.start()
     ev0.record()
     for i in range(args.steps):
-        k_ev[i][0].record()
         det.detect_device(frames, cfg, points=points, offsets=offsets)
-        k_ev[i][1].record()
         if world > 1:
             counts = sharding.counts_from_offsets(offsets)
             sharding.global_offsets(sharding.gather_frame_counts(counts, n_total))
@@ -259,7 +258,11 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches = det.kernel_launches - launches0
     total_ms = ev0.elapsed_time(ev1)
-    kern_ms = sum(a.elapsed_time(b) for a, b in k_ev) / args.steps
+    per_launch = [det.get_timing(i) for i in range(args.steps)]
+    det.set_timing(0)
+    kern_ms = sum(t[0] for t in per_launch) / args.steps        # the dominant kernel: fdf_detect_kernel
+    scan_ms = sum(t[1] for t in per_launch) / args.steps
+    gather_ms = sum(t[2] for t in per_launch) / args.steps
     if world > 1:
         tt = torch.tensor([total_ms, kern_ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -273,6 +276,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": committed_traffic(), "peak_source": peak_src,
                 "kernel": "fdf_detect_kernel<MaxThreshold,32>", "kernel_ms": round(kern_ms, 4),
+                "other_kernels_ms": {"fdf_scan_kernel": round(scan_ms, 4), "fdf_gather_kernel": round(gather_ms, 4)},
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "read_only_frac": round(F * W * H / (kern_ms * 1e-3) / 1e9 / peak, 4)}
 

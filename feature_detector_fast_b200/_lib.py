@@ -60,6 +60,10 @@ def load_library() -> C.CDLL:
     lib.fdf_synth_frames_device.argtypes = [vp, vp, u32, u32, u32, u32, u64, u64, u32, u32, u32, vp]
     lib.fdf_kernel_launches.restype = u64
     lib.fdf_kernel_launches.argtypes = [vp]
+    lib.fdf_set_timing.restype = C.c_int
+    lib.fdf_set_timing.argtypes = [vp, u32]
+    lib.fdf_get_timing.restype = C.c_int
+    lib.fdf_get_timing.argtypes = [vp, u32, C.POINTER(C.c_float)]
     lib.fdf_check_device_flags.restype = C.c_int
     lib.fdf_check_device_flags.argtypes = [vp, C.POINTER(u32)]
     lib.fdf_last_error.restype = C.c_char_p

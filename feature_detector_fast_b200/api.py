@@ -187,6 +187,20 @@ class Detector:
             _raise(self._lib, self._ctx, st)
         return out
 
+    def set_timing(self, slots: int) -> None:
+        """Record CUDA events around the three launches of every following detect_device call (0 = off)."""
+        st = self._lib.fdf_set_timing(self._ctx, int(slots))
+        if st != 0:
+            _raise(self._lib, self._ctx, st)
+
+    def get_timing(self, slot: int):
+        """(detection, scan, gather) kernel milliseconds of timing slot `slot`."""
+        ms = (C.c_float * 3)()
+        st = self._lib.fdf_get_timing(self._ctx, int(slot), ms)
+        if st != 0:
+            _raise(self._lib, self._ctx, st)
+        return float(ms[0]), float(ms[1]), float(ms[2])
+
     def device_flags(self) -> int:
         flags = C.c_uint32(0)
         st = self._lib.fdf_check_device_flags(self._ctx, C.byref(flags))

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "../../include/fdf.h"
 #include "fdf_kernels.cuh"
@@ -52,6 +53,8 @@ struct fdf_ctx {
     unsigned long long *pinned_offsets = nullptr;
     size_t pinned_offsets_count = 0;
     uint64_t launches = 0;
+    std::vector<cudaEvent_t> timing_events;  // 4 per slot: before detection, after it, after scan, after gather
+    uint64_t timing_calls = 0;
     char error[512] = {0};
 };
 
@@ -148,6 +151,7 @@ void fdf_destroy(fdf_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
     ctx->workspace.release();
     ctx->staging.release();
     ctx->staged_frames.release();
@@ -234,9 +238,42 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(ctx, FDF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
 
+    cudaEvent_t *ev = nullptr;
+    if (!ctx->timing_events.empty()) {
+        const size_t slots = ctx->timing_events.size() / 4;
+        ev = &ctx->timing_events[4 * (size_t)(ctx->timing_calls++ % slots)];
+        FDF_CUDA(ctx, cudaEventRecord(ev[0], stream));
+    }
     FDF_CUDA(ctx, fdf::launch_detect(mode, sr, tmap, p, stream));
-    FDF_CUDA(ctx, fdf::launch_compact(p, stream));
+    if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[1], stream));
+    FDF_CUDA(ctx, fdf::launch_scan(p, stream));
+    if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[2], stream));
+    FDF_CUDA(ctx, fdf::launch_gather(p, stream));
+    if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[3], stream));
     ctx->launches += 3;  // detection, scan, gather
+    return FDF_OK;
+}
+
+fdf_status fdf_set_timing(fdf_ctx *ctx, uint32_t slots) {
+    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
+    ctx->timing_events.clear();
+    ctx->timing_calls = 0;
+    for (uint32_t i = 0; i < 4 * slots; i++) {
+        cudaEvent_t e;
+        FDF_CUDA(ctx, cudaEventCreate(&e));
+        ctx->timing_events.push_back(e);
+    }
+    return FDF_OK;
+}
+
+fdf_status fdf_get_timing(fdf_ctx *ctx, uint32_t slot, float ms[3]) {
+    if (!ctx || !ms) return FDF_ERR_INVALID_ARGUMENT;
+    if ((size_t)slot * 4 + 3 >= ctx->timing_events.size()) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "no such timing slot");
+    cudaEvent_t *ev = &ctx->timing_events[4 * (size_t)slot];
+    FDF_CUDA(ctx, cudaEventSynchronize(ev[3]));
+    for (int k = 0; k < 3; k++) FDF_CUDA(ctx, cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
     return FDF_OK;
 }
 

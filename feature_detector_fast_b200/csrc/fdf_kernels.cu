@@ -505,13 +505,17 @@ cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const Detec
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_compact(const DetectParams &p, cudaStream_t stream) {
+cudaError_t launch_scan(const DetectParams &p, cudaStream_t stream) {
     const unsigned long long items = (unsigned long long)p.n_frames * p.strips_per_frame;
     if (items == 0 || items > 0x7fffffffull) return cudaErrorInvalidValue;
     const unsigned tiles = (unsigned)((items + kScanTile - 1) / kScanTile);
     fdf_scan_kernel<<<tiles, kScanThreads, 0, stream>>>(p, (uint32_t)items);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream) {
+    const unsigned long long items = (unsigned long long)p.n_frames * p.strips_per_frame;
+    if (items == 0 || items > 0x7fffffffull) return cudaErrorInvalidValue;
     fdf_gather_kernel<<<(unsigned)((items + 7) / 8), 256, 0, stream>>>(p, (uint32_t)items);
     return cudaGetLastError();
 }

@@ -65,8 +65,9 @@ cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const Detec
 
 // Ordered compaction, off the detection kernel's critical path: an exclusive scan of the per-strip counts
 // (single pass, decoupled look-back between scan tiles) and a gather of every strip's run to its final,
-// row-major position.  Two launches.
-cudaError_t launch_compact(const DetectParams &p, cudaStream_t stream);
+// row-major position.
+cudaError_t launch_scan(const DetectParams &p, cudaStream_t stream);
+cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream);
 
 cudaError_t launch_synth(uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t pitch,
                          unsigned long long frame_stride, unsigned long long seed, uint32_t first_frame,

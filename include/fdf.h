@@ -107,6 +107,13 @@ fdf_status fdf_synth_frames_device(fdf_ctx *ctx, uint8_t *d_frames, uint32_t n_f
  * (detection, offset scan, gather) and one per synthetic-frame call. */
 uint64_t fdf_kernel_launches(const fdf_ctx *ctx);
 
+/* Per-kernel device timing for benchmarks.  fdf_set_timing(ctx, n) makes every following
+ * fdf_detect_device-family call record CUDA events around its three launches into slot
+ * (call index mod n); n = 0 switches it off.  fdf_get_timing synchronises on the slot's last event and
+ * returns the milliseconds of {detection kernel, offset-scan kernel, gather kernel}. */
+fdf_status fdf_set_timing(fdf_ctx *ctx, uint32_t slots);
+fdf_status fdf_get_timing(fdf_ctx *ctx, uint32_t slot, float ms[3]);
+
 /* Device-side flags of the last fdf_detect_device-family call on this context, read back with a
  * synchronising copy: 0 = clean, bit 0 = look-back wait timed out (result invalid). */
 fdf_status fdf_check_device_flags(fdf_ctx *ctx, uint32_t *flags);

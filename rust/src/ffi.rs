@@ -1,0 +1,66 @@
+//! Raw bindings of include/fdf.h (the C ABI of libfdf_cuda.so).  Hand-written, one item per declaration.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct fdf_ctx {
+    _private: [u8; 0],
+}
+
+/// `fdf_point` == `crate::Point` (`#[repr(C)] { x: u32, y: u32 }`).
+pub type fdf_point = crate::Point;
+
+pub const FDF_OK: c_int = 0;
+pub const FDF_ERR_INVALID_COUNT: c_int = 1;
+pub const FDF_ERR_CAPACITY: c_int = 4;
+
+extern "C" {
+    pub fn fdf_create(device: c_int, out_ctx: *mut *mut fdf_ctx) -> c_int;
+    pub fn fdf_destroy(ctx: *mut fdf_ctx);
+    pub fn fdf_detect(
+        ctx: *mut fdf_ctx,
+        img: *const u8,
+        w: u32,
+        h: u32,
+        pitch: u32,
+        threshold: u8,
+        count: u8,
+        nms: u8,
+        out: *mut fdf_point,
+        cap: usize,
+        n_out: *mut usize,
+    ) -> c_int;
+    pub fn fdf_detect_batch(
+        ctx: *mut fdf_ctx,
+        frames: *const u8,
+        n_frames: u32,
+        w: u32,
+        h: u32,
+        pitch: u32,
+        frame_stride: u64,
+        threshold: u8,
+        count: u8,
+        nms: u8,
+        out: *mut fdf_point,
+        cap: usize,
+        offsets: *mut u64,
+    ) -> c_int;
+    pub fn fdf_detect_device(
+        ctx: *mut fdf_ctx,
+        d_frames: *const u8,
+        n_frames: u32,
+        w: u32,
+        h: u32,
+        pitch: u32,
+        frame_stride: u64,
+        threshold: u8,
+        count: u8,
+        nms: u8,
+        d_out: *mut fdf_point,
+        cap: usize,
+        d_offsets: *mut u64,
+        stream: *mut c_void,
+    ) -> c_int;
+    pub fn fdf_last_error(ctx: *const fdf_ctx) -> *const c_char;
+    pub fn fdf_status_string(status: c_int) -> *const c_char;
+}

@@ -206,3 +206,36 @@ def test_idempotent_and_order_independent_of_batching(detector, oracle_mod):
         alone = detector.detect_array(frames[f], _cfg(16, 9, 2))
         assert same_points(pts[int(offs[f]):int(offs[f + 1])], alone)
         assert same_points(alone, detector.detect_array(frames[f], _cfg(16, 9, 2)))
+
+
+def test_cpp_binding_and_cli_regenerate_the_shipped_renders(golden, tmp_path):
+    """include/fdf.hpp (the C++ mirror of lib.rs) through tools/fdf_cli.cpp (the counterpart of main.rs):
+    the output image must be the shipped golden render (grey input + one pure-red pixel per keypoint,
+    main.rs:74-77) and the text file "x y" per keypoint in order (main.rs:4-15)."""
+    import subprocess
+
+    import __graft_entry__ as entry
+
+    cli = entry.build_cli()
+    grey = golden["grey"]
+    h, w = grey.shape
+    pgm = tmp_path / "in.pgm"
+    pgm.write_bytes(b"P5\n%d %d\n255\n" % (w, h) + grey.tobytes())
+    for mode, want in (("off", golden["rust_off"]), ("max_threshold", golden["rust_nonmax"])):
+        out = tmp_path / f"out_{mode}.ppm"
+        res = subprocess.run([cli, str(pgm), str(out), "16", "9", mode], capture_output=True, text=True, timeout=120)
+        assert res.returncode == 0, res.stderr
+        assert f"found {len(want)} keypoints" in res.stdout
+        raw = out.read_bytes()
+        header = b"P6\n%d %d\n255\n" % (w, h)
+        assert raw.startswith(header)
+        rgb = np.frombuffer(raw[len(header):], np.uint8).reshape(h, w, 3)
+        render = np.repeat(grey[:, :, None], 3, axis=2).copy()
+        render[want[:, 1], want[:, 0]] = (255, 0, 0)
+        assert np.array_equal(rgb, render)
+        lines = (tmp_path / f"out_{mode}.txt").read_text().split("\n")[:-1]
+        assert lines == [f"{x} {y}" for x, y in want.tolist()]
+    # the reference panics for count < 9 (exit status 101 is what a Rust panic gives)
+    res = subprocess.run([cli, str(pgm), str(tmp_path / "x.ppm"), "16", "8", "off"], capture_output=True, text=True,
+                         timeout=120)
+    assert res.returncode == 101 and "needs to exceed 9" in res.stderr
