@@ -61,9 +61,12 @@ def committed_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).
 
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    nvidia-smi takes a few hundred ms to start, so it is launched early (`start`, then `wait_ready`) and only
+    the samples whose timestamps fall inside [mark_begin, mark_end] are used."""
+
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -71,6 +74,7 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -82,11 +86,32 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_ready(self, timeout=5.0):
+        if self.proc is None:
+            return
+        end = time.time() + timeout
+        while time.time() < end:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                pass
+            time.sleep(0.02)
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
         try:
+            time.sleep(0.05)
             self.proc.terminate()
             self.proc.wait(timeout=5)
         except Exception:
@@ -96,22 +121,27 @@ class ClockSampler:
             os.unlink(self.path)
         except Exception:
             return out
-        sm, reasons, smax = [], set(), None
+        sm, reasons, smax, power = [], set(), None, []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
-            if len(r) < 9:
+            if len(r) < 10:
                 continue
             try:
-                sm.append(float(r[1]))
-                smax = float(r[2])
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if self.t0 is not None and not (self.t0 - 0.02 <= ts <= self.t1 + 0.02):
+                    continue
+                sm.append(float(r[2]))
+                smax = float(r[3])
+                power.append(float(r[4]))
             except ValueError:
                 continue
-            for name, v in zip(names, r[5:9]):
+            for name, v in zip(names, r[6:10]):
                 if v.strip().lower() == "active":
                     reasons.add(name)
         if sm:
             sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power) if power else None)
         return out
 
 
@@ -180,7 +210,7 @@ def run_reference_arm(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU (default: the named config)")
@@ -244,9 +274,11 @@ def main():
     det.set_timing(args.steps)  # CUDA events around each launch, recorded by the library on the launching stream
     launches0 = det.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
+    barrier()
+    sampler.mark_begin()
     ev0.record()
     for i in range(args.steps):
         det.detect_device(frames, cfg, points=points, offsets=offsets)
@@ -255,6 +287,7 @@ def main():
             sharding.global_offsets(sharding.gather_frame_counts(counts, n_total))
     ev1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches = det.kernel_launches - launches0
     total_ms = ev0.elapsed_time(ev1)
