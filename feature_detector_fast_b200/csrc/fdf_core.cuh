@@ -79,8 +79,27 @@ FDF_HD int popc32(uint32_t v) {
 #endif
 }
 
-FDF_HD int min3i(int a, int b, int c) { return min(a, min(b, c)); }  // VIMNMX3
-FDF_HD int max3i(int a, int b, int c) { return max(a, max(b, c)); }
+// Three-input min / max: ptxas fuses two dependent 2-input ops into one VIMNMX3 when the inner result has a
+// single use; the inner op goes through inline PTX so the front end cannot re-associate it for reuse
+// elsewhere (which would turn 16 VIMNMX3 of a sliding window into 32 two-input ops).
+FDF_HD int min3i(int a, int b, int c) {
+#if defined(__CUDA_ARCH__)
+    int m;
+    asm("min.s32 %0, %1, %2;" : "=r"(m) : "r"(b), "r"(c));
+    return min(a, m);
+#else
+    return min(a, min(b, c));
+#endif
+}
+FDF_HD int max3i(int a, int b, int c) {
+#if defined(__CUDA_ARCH__)
+    int m;
+    asm("max.s32 %0, %1, %2;" : "=r"(m) : "r"(b), "r"(c));
+    return max(a, m);
+#else
+    return max(a, max(b, c));
+#endif
+}
 
 // ---- dense SWAR filter (4 horizontally adjacent centres per 32-bit word) ---------------------
 //
@@ -119,12 +138,18 @@ struct RingMasks {
 
 FDF_HD RingMasks ring_masks(int c, const int ring[16], int t) {
     const int hi = c + t, lo = c - t;
-    RingMasks m{0u, 0u};
+    // four independent 8-step shift chains (two per mask) instead of two 16-step ones: shorter critical path
+    uint32_t bl = 0u, bh = 0u, dl = 0u, dh = 0u;
 #pragma unroll
-    for (int i = 15; i >= 0; i--) {
-        m.bright = shift_in_sign(m.bright, hi - ring[i]);  // hi - p < 0  <=>  p > c + t
-        m.dark = shift_in_sign(m.dark, ring[i] - lo);      // p - lo < 0  <=>  p < c - t
+    for (int i = 7; i >= 0; i--) {
+        bl = shift_in_sign(bl, hi - ring[i]);      // hi - p < 0  <=>  p > c + t
+        bh = shift_in_sign(bh, hi - ring[i + 8]);
+        dl = shift_in_sign(dl, ring[i] - lo);      // p - lo < 0  <=>  p < c - t
+        dh = shift_in_sign(dh, ring[i + 8] - lo);
     }
+    RingMasks m;
+    m.bright = bl | (bh << 8);
+    m.dark = dl | (dh << 8);
     return m;
 }
 

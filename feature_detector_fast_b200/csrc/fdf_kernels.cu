@@ -126,7 +126,8 @@ struct Layout {
     static constexpr int klist_bytes = (MODE == NMS_OFF) ? 0 : 2 * kKlistCap * 2;  // two lists (chunk parity)
     static constexpr int misc_off = klist_off + klist_bytes;
     static constexpr int misc_bytes = 128;
-    static constexpr int bits_off = misc_off + misc_bytes;  // bit plane of out_rows x words_per_row words
+    static constexpr int bits_off = misc_off + misc_bytes;  // bit plane: out_rows x words_per_row words (+ pad to 4)
+    static_assert(bits_off % 16 == 0, "the bit plane is walked with 128-bit loads");
     static_assert(tile_bytes % 128 == 0, "TMA destination must stay 128-byte aligned");
     static_assert(SR % 16 == 0 && SR <= 64, "phase A walks rows in steps of 16; queue entries hold 6 row bits");
     static_assert(kGroupRows * kTileW <= kQueueCap, "a row group must always fit the candidate queue");
@@ -197,6 +198,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     const int NC = (int)p.chunks_per_strip;
     const int WW = (int)p.words_per_row;
     const int nwords = OUT_R * WW;
+    const int nunits = (nwords + 3) / 4;  // the bit plane in 128-bit units (padding words stay zero)
     const uint32_t total_items = p.n_frames * p.strips_per_frame;
 
     if (tid == 0) {
@@ -208,7 +210,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         kcount[0] = kcount[1] = 0u;
         s_ticket[0] = atomicAdd(p.ticket, 1u);
     }
-    for (int i = tid; i < nwords; i += kThreads) bits[i] = 0u;
+    for (int i = tid; i < 4 * nunits; i += kThreads) bits[i] = 0u;
     __syncthreads();
 
     const int t = (int)p.threshold, n = (int)p.count;
@@ -322,10 +324,15 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         __syncthreads();  // strip end: all bits of the strip are set; plane and lists are free
 
         // ---- strip -> ordered run of points in the staging buffer --------------------------------------
+        // the bit plane is walked in 128-bit units: one unit (4 words = 128 columns) per lane and step
         const int y0 = first_out_row(MODE) + (int)strip * OUT_R;  // first row this strip emits
-        const EmitRange er = emit_range(warp, nwords);
+        const EmitRange er = emit_range(warp, nunits);
+        uint4 *bits4 = reinterpret_cast<uint4 *>(bits);
         uint32_t cnt = 0;
-        for (int i = er.begin + lane; i < er.end; i += 32) cnt += (uint32_t)__popc(bits[i]);
+        for (int u = er.begin + lane; u < er.end; u += 32) {
+            const uint4 v = bits4[u];
+            cnt += (uint32_t)(__popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w));
+        }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);  // warp total
         if (lane == 0) warp_sums[warp] = cnt;
@@ -350,27 +357,36 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         __syncthreads();
         if (cnt != 0u) {  // warp-uniform: this warp's range holds keypoints
             unsigned long long o = *s_base + warp_sums[warp];
-            int i = er.begin + lane;
-            int row = i / WW, col = i - row * WW;
-            for (int base = er.begin; base < er.end; base += 32, i += 32) {
-                const uint32_t m = i < er.end ? bits[i] : 0u;
-                const uint32_t c = (uint32_t)__popc(m);
+            for (int base = er.begin; base < er.end; base += 32) {
+                const int u = base + lane;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (u < er.end) v = bits4[u];
+                const uint32_t c = (uint32_t)(__popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w));
                 uint32_t incl = c;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += v;
+                    const uint32_t w = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += w;
                 }
-                if (m != 0u) {
-                    emit_word(m, (uint32_t)col * 32u, (uint32_t)(y0 + row), o + (incl - c), p.cap, p.staging);
-                    bits[i] = 0u;  // leave the plane zeroed for the next strip
+                if (c != 0u) {
+                    unsigned long long oo = o + (incl - c);
+                    const int wi = 4 * u;
+                    int row = wi / WW, col = wi - row * WW;
+                    const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (words[k] != 0u) {
+                            emit_word(words[k], (uint32_t)col * 32u, (uint32_t)(y0 + row), oo, p.cap, p.staging);
+                            oo += (unsigned long long)__popc(words[k]);
+                        }
+                        if (++col == WW) {
+                            col = 0;
+                            row++;
+                        }
+                    }
+                    bits4[u] = make_uint4(0u, 0u, 0u, 0u);  // leave the plane zeroed for the next strip
                 }
                 o += __shfl_sync(0xffffffffu, incl, 31);
-                col += 32;
-                while (col >= WW) {
-                    col -= WW;
-                    row++;
-                }
             }
         }
         cur = s_ticket[(it + 1u) & 1u];
@@ -489,7 +505,8 @@ size_t detect_smem_bytes(int mode, int sr, uint32_t words_per_row) {
     const size_t plane = mode == NMS_OFF ? 0 : (size_t)sr * kTileW * 2;
     const size_t queue = (size_t)kQueueCap * 2;
     const size_t klist = mode == NMS_OFF ? 0 : (size_t)2 * kKlistCap * 2;
-    return 2 * tile + plane + queue + klist + 128 + (size_t)out_rows(mode, sr) * words_per_row * 4;
+    const size_t bit_words = (((size_t)out_rows(mode, sr) * words_per_row + 3) / 4) * 4;
+    return 2 * tile + plane + queue + klist + 128 + bit_words * 4;
 }
 
 cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream) {

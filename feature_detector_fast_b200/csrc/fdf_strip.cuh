@@ -75,11 +75,17 @@ FDF_HD ChunkGeo make_geo(int w, int h, int ww, int strip, int chunk, int sr) {
 template <int MODE, int SR>
 FDF_HD void phase_a(int tid, const uint8_t *tile, uint16_t *queue, uint32_t *qcount, const ChunkGeo &g,
                     uint32_t kbias, int row_lo, int row_hi) {
-    const int q = tid & 15;   // which 16-pixel group of the 256-wide tile row
-    const int r0 = tid >> 4;  // first scored row of this thread
-    for (int rr = r0; rr < SR; rr += kComputeThreads / 16) {
+    constexpr int IT = SR / (kComputeThreads / 16);  // rows per thread
+    const int q = tid & 15;                          // which 16-pixel group of the 256-wide tile row
+    const int r0 = tid >> 4;                         // first scored row of this thread
+    // step 1, straight-line for all of the thread's rows (independent work the scheduler can overlap):
+    // bit (8*b + k) of gm[it] <=> byte b of word k of the group passed the filter
+    uint32_t gm[IT];
+#pragma unroll
+    for (int it = 0; it < IT; it++) {
+        const int rr = r0 + it * (kComputeThreads / 16);
         const int y = g.ys0 + rr;
-        if (y < 3 || y >= g.h - 3 || rr < row_lo || rr >= row_hi) continue;  // fast_simd.rs:342
+        const bool live = y >= 3 && y < g.h - 3 && rr >= row_lo && rr < row_hi;  // fast_simd.rs:342
         const uint8_t *rowp = tile + (rr + 3) * kTileW + q * 16;
         const uint4 C = *reinterpret_cast<const uint4 *>(rowp);
         const uint4 N = *reinterpret_cast<const uint4 *>(rowp - 3 * kTileW);
@@ -95,16 +101,22 @@ FDF_HD void phase_a(int tid, const uint8_t *tile, uint16_t *queue, uint32_t *qco
         const uint32_t f1 = filter4(C.y, N.y, S.y, e1, w1, kbias, 0x80808080u);
         const uint32_t f2 = filter4(C.z, N.z, S.z, e2, w2, kbias, 0x80808080u);
         const uint32_t f3 = filter4(C.w, N.w, S.w, e3, w3, kbias, 0x80808080u);
-        if ((f0 | f1 | f2 | f3) != 0u) {
-            // each f has only bit 7 of its bytes set: bit (8*b + k) of gm <=> byte b of word k
-            uint32_t gm = (f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4);
-            const uint32_t cnt = (uint32_t)popc32(gm);
+        // each f has only bit 7 of its bytes set
+        gm[it] = live ? ((f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4)) : 0u;
+    }
+    // step 2: push the survivors
+#pragma unroll
+    for (int it = 0; it < IT; it++) {
+        uint32_t m = gm[it];
+        if (m != 0u) {
+            const int rr = r0 + it * (kComputeThreads / 16);
+            const uint32_t cnt = (uint32_t)popc32(m);
             uint32_t slot = atomic_add_u32(qcount, cnt);
             if (slot + cnt <= (uint32_t)kQueueCap) {
                 const uint32_t ent0 = (uint32_t)((rr << 8) | (q * 16));
-                while (gm) {
-                    const uint32_t p = (uint32_t)lowest_set_bit(gm);
-                    gm &= gm - 1u;
+                while (m) {
+                    const uint32_t p = (uint32_t)lowest_set_bit(m);
+                    m &= m - 1u;
                     queue[slot++] = (uint16_t)(ent0 + ((p & 7u) << 2) + (p >> 3));
                 }
             }
@@ -189,17 +201,17 @@ FDF_HD void nms_dense(int tid, const uint16_t *plane, uint32_t *bits, const Chun
 }
 
 // ---- emission: bit plane -> points, row-major -----------------------------------------------------
-// The strip's bit plane (out_rows x ww words) is cut into one contiguous range per warp; a warp walks
-// its range 32 words at a time: one word per lane, a warp prefix sum gives every lane its offset.
+// The strip's bit plane (out_rows x ww words, in 128-bit units) is cut into one contiguous range per warp;
+// a warp walks its range 32 units at a time: one unit per lane, a warp prefix sum gives every lane its offset.
 struct EmitRange {
-    int begin, end;  // word indices into bits[out_rows * ww]
+    int begin, end;  // unit indices
 };
 
-FDF_HD EmitRange emit_range(int warp, int nwords) {
-    const int wpw = (nwords + kThreads / 32 - 1) / (kThreads / 32);
+FDF_HD EmitRange emit_range(int warp, int nunits) {
+    const int upw = (nunits + kThreads / 32 - 1) / (kThreads / 32);
     EmitRange r;
-    r.begin = min(warp * wpw, nwords);
-    r.end = min(r.begin + wpw, nwords);
+    r.begin = min(warp * upw, nunits);
+    r.end = min(r.begin + upw, nunits);
     return r;
 }
 
