@@ -90,8 +90,8 @@ fdf_status check_config(fdf_ctx *ctx, uint8_t count, uint8_t nms) {
 // strip height: tall strips (less halo) when there is enough work to fill the GPU, short otherwise
 int choose_scored_rows(uint32_t n_frames, uint32_t h, int mode) {
     const long long rows = (long long)h - 2 * fdf::first_out_row(mode);
-    const long long strips32 = (rows + fdf::out_rows(mode, 32) - 1) / fdf::out_rows(mode, 32);
-    return (long long)n_frames * strips32 >= 2 * 148 ? 32 : 16;
+    const long long strips64 = (rows + fdf::out_rows(mode, 64) - 1) / fdf::out_rows(mode, 64);
+    return (long long)n_frames * strips64 >= 2 * 148 ? 64 : 32;
 }
 
 }  // namespace

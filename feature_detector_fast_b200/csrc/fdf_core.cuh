@@ -1,9 +1,14 @@
-// fdf_core.cuh -- pixel-level primitives of the FAST-n path (segment test, scores, SWAR filter).
+// fdf_core.cuh -- pixel-level primitives of the FAST-n path (SWAR filter, segment test, scores).
 //
 // Everything here is `__host__ __device__` so the exact device arithmetic can also be compiled
-// with g++ and checked against the CPU oracle without a GPU (tests/host/core_check.cpp).  On the
-// device each helper maps to one native sm_100a instruction where one exists
-// (VABSDIFF4.U8[.ACC], PRMT, SHF.L.W, VIMNMX3, POPC).
+// with g++ and checked against the CPU oracle without a GPU (tests/host/strip_emulator.cpp).
+//
+// What the hardware dictates (measured with tools/pipe_probe.cu on a B200): LOP3, VABSDIFF4, PRMT, SHF,
+// VIMNMX* and ISETP all issue on ONE pipe at 0.5 warp-instructions / clock / scheduler; IMAD (and adds /
+// left shifts expressed as IMAD) issue on a second pipe at the same rate; POPC / FLO run at 1/8.  The path is
+// bound by the first pipe, so the code below (a) works on 4 pixels per instruction in the dense filter,
+// (b) works on 2 ring pixels per instruction (16-bit lanes) in the per-candidate test and scores, and
+// (c) phrases adds, doublings and packing as multiply-adds wherever that is free.
 //
 // Reference semantics (citations into the reference checkout):
 //   ring order / offsets     src/fast_simd.rs:79-98
@@ -63,14 +68,6 @@ FDF_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {  // PRMT
 #endif
 }
 
-FDF_HD uint32_t shift_in_sign(uint32_t acc, int v) {  // (acc << 1) | (v < 0)    SHF.L.W.U32.HI
-#if defined(__CUDA_ARCH__)
-    return __funnelshift_l((uint32_t)v, acc, 1);
-#else
-    return (acc << 1) | ((uint32_t)v >> 31);
-#endif
-}
-
 FDF_HD int popc32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
     return __popc(v);
@@ -79,25 +76,62 @@ FDF_HD int popc32(uint32_t v) {
 #endif
 }
 
-// Three-input min / max: ptxas fuses two dependent 2-input ops into one VIMNMX3 when the inner result has a
-// single use; the inner op goes through inline PTX so the front end cannot re-associate it for reuse
-// elsewhere (which would turn 16 VIMNMX3 of a sliding window into 32 two-input ops).
-FDF_HD int min3i(int a, int b, int c) {
+FDF_HD int highest_set_bit(uint32_t m) {  // m != 0                              FLO.U32
 #if defined(__CUDA_ARCH__)
-    int m;
-    asm("min.s32 %0, %1, %2;" : "=r"(m) : "r"(b), "r"(c));
-    return min(a, m);
+    int r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(m));
+    return r;
 #else
-    return min(a, min(b, c));
+    return 31 - __builtin_clz(m);
 #endif
 }
-FDF_HD int max3i(int a, int b, int c) {
+
+// a * b + c on the multiply-add pipe.  ptxas is free to turn small cases into adds / shifts; the point of
+// spelling it this way is that it never needs the logic pipe.
+FDF_HD uint32_t mad32(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+
+// ---- 2 x 16-bit lane helpers (DPX: VIMNMX3.U16x2, VIMNMX.U16x2, VIADDMNMX.S16x2.RELU) ----------
+FDF_HD uint32_t swap16(uint32_t v) { return byte_perm(v, 0u, 0x1032u); }
+
+FDF_HD uint32_t min_u16x2(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
-    int m;
-    asm("max.s32 %0, %1, %2;" : "=r"(m) : "r"(b), "r"(c));
-    return max(a, m);
+    return __vminu2(a, b);
 #else
-    return max(a, max(b, c));
+    return min(a & 0xffffu, b & 0xffffu) | (min(a >> 16, b >> 16) << 16);
+#endif
+}
+FDF_HD uint32_t max_u16x2(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __vmaxu2(a, b);
+#else
+    return max(a & 0xffffu, b & 0xffffu) | (max(a >> 16, b >> 16) << 16);
+#endif
+}
+FDF_HD uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    return __vimin3_u16x2(a, b, c);
+#else
+    return min_u16x2(a, min_u16x2(b, c));
+#endif
+}
+FDF_HD uint32_t max3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    return __vimax3_u16x2(a, b, c);
+#else
+    return max_u16x2(a, max_u16x2(b, c));
+#endif
+}
+// per 16-bit lane: max(a + b, 0) with signed wrap-around lanes
+FDF_HD uint32_t addrelu_s16x2(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __viaddmax_s16x2_relu(a, b, 0u);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 2; i++) {
+        const int16_t s = (int16_t)(uint16_t)(((a >> (16 * i)) + (b >> (16 * i))) & 0xffffu);
+        r |= (uint32_t)(uint16_t)(s > 0 ? s : 0) << (16 * i);
+    }
+    return r;
 #endif
 }
 
@@ -112,50 +146,101 @@ FDF_HD int max3i(int a, int b, int c) {
 // pre-check (fast_simd.rs:441-509): it never changes the result, only which centres get the full
 // test.  It is direction-less and slightly looser; it holds for every n in 9..=16.
 //
-// kbias = (0x7f - t) * 0x01010101 for t < 128, and 0 for t >= 128 (then only bit 7 of the
-// difference is tested: |d| > t >= 128 implies |d| >= 128).  Per byte: bit 7 of
-// ((m & 0x7f) + kbias) | m is set  <=>  m > t (t < 128)  or  m >= 128 (t >= 128).
+// Threshold test of a word m of four byte values:  f = (m + kbias) | m, flag = bit 7 of each byte, with
+// kbias = (0x7f - t) * 0x01010101 for t < 128 and 0 for t >= 128.  Per byte (t < 128): if m <= 0x7f the
+// sum cannot carry out and has bit 7 set iff m + 0x7f - t >= 0x80 iff m > t; if m >= 0x80 (> t) the OR
+// with m sets bit 7.  A carry out of a byte >= 0x80 adds 1 to the next byte, which can only turn a flag
+// ON: the test stays a necessary condition and no byte mask is needed.  For t >= 128 the flag is
+// m >= 128, implied by m > t.  All other bits of f are garbage.
 FDF_HD uint32_t filter_kbias(uint32_t t) { return t < 128u ? (0x7fu - t) * 0x01010101u : 0u; }
 
-FDF_HD uint32_t pair_exceeds(uint32_t a, uint32_t b, uint32_t c, uint32_t kbias) {
-    const uint32_t da = absdiff4(a, c), db = absdiff4(b, c);
-    const uint32_t x = ((da | db) & 0x7f7f7f7fu) + kbias;  // LOP3, IADD
-    return x | da | db;                                    // LOP3; bit 7 of each byte is the flag
+FDF_HD uint32_t exceeds4(uint32_t m, uint32_t kbias) { return mad32(m, 1u, kbias) | m; }
+
+// the 16 pixels x .. x+15 of a tile row, as four little-endian words
+struct Px16 {
+    uint32_t w[4];
+};
+
+FDF_HD Px16 load16(const uint8_t *p) {  // p 16-byte aligned                      LDS.128
+    const uint4 v = *reinterpret_cast<const uint4 *>(p);
+    Px16 r;
+    r.w[0] = v.x;
+    r.w[1] = v.y;
+    r.w[2] = v.z;
+    r.w[3] = v.w;
+    return r;
 }
 
-// Returns candidate flags in bit 7 of each byte, already ANDed with `valid` (0x80 per byte that
-// is allowed to be a centre at all).
-FDF_HD uint32_t filter4(uint32_t c, uint32_t n, uint32_t s, uint32_t e, uint32_t w, uint32_t kbias,
-                        uint32_t valid) {
-    return pair_exceeds(n, s, c, kbias) & pair_exceeds(e, w, c, kbias) & valid;
+// Stage 1 (every scored pixel): north/south pair only.  Returns non-zero iff at least one of the 16 centres
+// has a north or south ring pixel that differs from it by more than t.
+FDF_HD uint32_t vertical_any(const Px16 &c, const Px16 &n, const Px16 &s, uint32_t kbias) {
+    uint32_t o = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) o |= exceeds4(absdiff4(n.w[k], c.w[k]) | absdiff4(s.w[k], c.w[k]), kbias);
+    return o & 0x80808080u;
 }
 
-// ---- exact segment test ------------------------------------------------------------------------
+// Stage 2 (16-pixel groups that passed stage 1): both pairs.  cl / cr are the words left / right of the
+// centre row's 16 pixels; valid[k] has 0x80 in every byte that may be a centre at all (image border, chunk
+// halo).  Returns the candidate mask of the group: centre 4k + b  <->  bit 8b + 7 - k.
+// The east/west differences are computed once per pixel: H(x) = |p(x+3) - p(x)| is the east difference
+// of centre x and the west difference of centre x + 3.
+FDF_HD uint32_t candidate_mask16(const Px16 &c, const Px16 &n, const Px16 &s, uint32_t cl, uint32_t cr,
+                                 const uint32_t valid[4], uint32_t kbias) {
+    uint32_t h[5];  // h[k + 1] = H of word k, h[0] = H of the word left of the group
+    h[0] = absdiff4(byte_perm(cl, c.w[0], 0x6543u), cl);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t east = byte_perm(c.w[k], k < 3 ? c.w[k + 1] : cr, 0x6543u);  // pixels x+3 .. x+6
+        h[k + 1] = absdiff4(east, c.w[k]);
+    }
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t a = absdiff4(n.w[k], c.w[k]) | absdiff4(s.w[k], c.w[k]);
+        const uint32_t b = h[k + 1] | byte_perm(h[k], h[k + 1], 0x4321u);  // H(x) | H(x-3)
+        const uint32_t fb = (exceeds4(b, kbias)) & valid[k];
+        r[k] = exceeds4(a, kbias) & fb;  // only bit 7 of valid bytes survives
+    }
+    return mad32(r[0], 1u, r[1] >> 1) + mad32(r[2] >> 2, 1u, r[3] >> 3);
+}
+
+// candidate-mask bit -> pixel index inside the group
+FDF_HD int mask_bit_to_px(int p) { return 4 * (7 - (p & 7)) + (p >> 3); }
+
+// ---- exact segment test on 2 x 16-bit lanes ----------------------------------------------------------
+// The 16 ring pixels are held as 8 words  P[i] = ring[i] | ring[i + 8] << 16  (opposite pixels share a word).
+struct Ring2 {
+    uint32_t p[8];
+};
+
 struct RingMasks {
     uint32_t bright;  // bit i set <=> ring[i] > c + t   (fast_simd.rs:224 is_above)
     uint32_t dark;    // bit i set <=> ring[i] < c - t   (fast_simd.rs:225 is_below)
 };
 
-FDF_HD RingMasks ring_masks(int c, const int ring[16], int t) {
-    const int hi = c + t, lo = c - t;
-    // four independent 8-step shift chains (two per mask) instead of two 16-step ones: shorter critical path
-    uint32_t bl = 0u, bh = 0u, dl = 0u, dh = 0u;
+// bright: lane value p + 255 - hi with hi = min(c + t, 255) lies in [0, 510] and has bit 8 set iff p > hi;
+// dark:   lane value 255 + lo - p with lo = max(c - t, 0)  lies in [0, 510] and has bit 8 set iff p < lo.
+// Neither can borrow across lanes.  The flags are collected Horner style (acc = 2 * acc + flag), so ring i
+// ends up in bit 8 + i of its lane; one PRMT then gathers the two lane bytes into a 16-bit mask.
+FDF_HD RingMasks ring_masks(int c, const Ring2 &r, int t) {
+    const uint32_t kb = (uint32_t)(255 - min(c + t, 255)) * 0x00010001u;
+    const uint32_t kd = (uint32_t)(255 + max(c - t, 0)) * 0x00010001u;
+    uint32_t ab = 0u, ad = 0u;
 #pragma unroll
     for (int i = 7; i >= 0; i--) {
-        bl = shift_in_sign(bl, hi - ring[i]);      // hi - p < 0  <=>  p > c + t
-        bh = shift_in_sign(bh, hi - ring[i + 8]);
-        dl = shift_in_sign(dl, ring[i] - lo);      // p - lo < 0  <=>  p < c - t
-        dh = shift_in_sign(dh, ring[i + 8] - lo);
+        ab = mad32(ab, 2u, (r.p[i] + kb) & 0x01000100u);
+        ad = mad32(ad, 2u, (kd - r.p[i]) & 0x01000100u);
     }
     RingMasks m;
-    m.bright = bl | (bh << 8);
-    m.dark = dl | (dh << 8);
+    m.bright = byte_perm(ab, 0u, 0x4431u);
+    m.dark = byte_perm(ad, 0u, 0x4431u);
     return m;
 }
 
 // exists a cyclic run of >= n set bits in the 16-bit ring mask (9 <= n <= 16)
 FDF_HD bool has_arc(uint32_t m16, int n) {
-    uint32_t r = m16 | (m16 << 16);
+    uint32_t r = mad32(m16, 0x00010001u, 0u);
     r &= r >> 1;
     r &= r >> 2;
     r &= r >> 4;         // bit i: positions i..i+7 all set
@@ -172,52 +257,69 @@ FDF_HD bool has_arc(uint32_t m16, int n) {
 // -el = max_k min_{W_k} (p - c); for an arc darker than the centre (p < c-t) eh >= t+1 > 0, so
 // el >= eh > 0 and the score is eh = max_k min_{W_k} (c - p).  So for keypoints
 // (the only pixels that are ever scored, fast_simd.rs:276-279) one sliding-window max-of-min over
-// e_i = +-(c - p_i) is exact.  Window minima: 3-window, then 9-window = min3 of three 3-windows,
-// then n-window = min(9-window at k, 9-window at k+n-9).
+// e_i = +-(c - p_i) is exact.  Here e is biased by 256 (lanes in [1, 511], unsigned), two ring positions
+// 8 apart per word:  E[i] = (e_i, e_{i+8}),  E[i + 8] = swap16(E[i]).  Window minima: 3-window, then
+// 9-window = min3 of three 3-windows, then n-window = min(9-window at k, 9-window at k + n - 9).
 template <int K>
-FDF_HD int max_of_extended(const int u9[16]) {
-    int v[16];
+FDF_HD uint32_t max_of_extended(const uint32_t u[16]) {  // u[i + 8] = swap16(u[i]); only u[0 .. 7 + K] are read
+    uint32_t v[8];
 #pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = (K == 0) ? u9[i] : min(u9[i], u9[(i + K) & 15]);
-    int a = max3i(v[0], v[1], v[2]), b = max3i(v[3], v[4], v[5]), c = max3i(v[6], v[7], v[8]);
-    int d = max3i(v[9], v[10], v[11]), e = max3i(v[12], v[13], v[14]);
-    return max(max3i(a, b, c), max3i(d, e, v[15]));
+    for (int i = 0; i < 8; i++) v[i] = (K == 0) ? u[i] : min_u16x2(u[i], u[i + K]);
+    const uint32_t a = max3_u16x2(v[0], v[1], v[2]), b = max3_u16x2(v[3], v[4], v[5]);
+    const uint32_t m = max3_u16x2(a, b, max_u16x2(v[6], v[7]));
+    return max(m & 0xffffu, m >> 16);
 }
 
 // pixel_is_brighter: the arc found by the segment test is a "bright" arc (ring pixels > c + t)
-FDF_HD uint32_t score_max_threshold(int c, const int ring[16], int n, bool pixel_is_brighter) {
-    int e[16], t3[16], u9[16];
+FDF_HD uint32_t score_max_threshold(int c, const Ring2 &r, int n, bool pixel_is_brighter) {
+    const uint32_t sgn = pixel_is_brighter ? 1u : 0xffffffffu;
+    const uint32_t k = pixel_is_brighter ? (uint32_t)(256 - c) * 0x00010001u : (uint32_t)(256 + c) * 0x00010001u;
+    uint32_t e[10], t3[14], u[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) e[i] = pixel_is_brighter ? ring[i] - c : c - ring[i];
+    for (int i = 0; i < 8; i++) e[i] = mad32(r.p[i], sgn, k);  // 256 +- (p - c) per lane, no cross-lane borrow
+    e[8] = swap16(e[0]);
+    e[9] = swap16(e[1]);
 #pragma unroll
-    for (int i = 0; i < 16; i++) t3[i] = min3i(e[i], e[(i + 1) & 15], e[(i + 2) & 15]);
+    for (int i = 0; i < 8; i++) t3[i] = min3_u16x2(e[i], e[i + 1], e[i + 2]);
 #pragma unroll
-    for (int i = 0; i < 16; i++) u9[i] = min3i(t3[i], t3[(i + 3) & 15], t3[(i + 6) & 15]);
-    int r;
-    switch (n) {
-        case 9: r = max_of_extended<0>(u9); break;
-        case 10: r = max_of_extended<1>(u9); break;
-        case 11: r = max_of_extended<2>(u9); break;
-        case 12: r = max_of_extended<3>(u9); break;
-        case 13: r = max_of_extended<4>(u9); break;
-        case 14: r = max_of_extended<5>(u9); break;
-        case 15: r = max_of_extended<6>(u9); break;
-        default: r = max_of_extended<7>(u9); break;
+    for (int i = 0; i < 6; i++) t3[i + 8] = swap16(t3[i]);
+#pragma unroll
+    for (int i = 0; i < 8; i++) u[i] = min3_u16x2(t3[i], t3[i + 3], t3[i + 6]);
+    uint32_t m;
+    if (n == 9) {
+        m = max_of_extended<0>(u);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 7; i++) u[i + 8] = swap16(u[i]);
+        u[15] = 0u;
+        switch (n) {
+            case 10: m = max_of_extended<1>(u); break;
+            case 11: m = max_of_extended<2>(u); break;
+            case 12: m = max_of_extended<3>(u); break;
+            case 13: m = max_of_extended<4>(u); break;
+            case 14: m = max_of_extended<5>(u); break;
+            case 15: m = max_of_extended<6>(u); break;
+            default: m = max_of_extended<7>(u); break;
+        }
     }
-    return (uint32_t)r;
+    return m - 256u;
 }
 
 // SumAbsolute (opencv_compat.rs:278-299): max( sum_{p > c+t} (p-c-t), sum_{p < c-t} (c-p-t) ) over
-// ALL 16 ring pixels.  p - c - t > 0 <=> p > c + t, so each term is a relu.
-FDF_HD uint32_t score_sum_abs(int c, const int ring[16], int t) {
-    const int hi = c + t, lo = c - t;
-    int sum_bright = 0, sum_dark = 0;
+// ALL 16 ring pixels.  p - c - t > 0 <=> p > c + t, so each term is a relu; clamping c + t to 255 and
+// c - t to 0 changes nothing (every term is then <= 0).  Lane sums stay below 8 * 255.
+FDF_HD uint32_t score_sum_abs(int c, const Ring2 &r, int t) {
+    const uint32_t nhi = (uint32_t)((0x10000 - min(c + t, 255)) & 0xffff) * 0x00010001u;  // -hi per lane
+    const uint32_t lo1 = (uint32_t)(max(c - t, 0) + 1) * 0x00010001u;                      // lo + 1 per lane
+    uint32_t sb = 0u, sd = 0u;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        sum_bright += max(ring[i] - hi, 0);
-        sum_dark += max(lo - ring[i], 0);
+    for (int i = 0; i < 8; i++) {
+        sb += addrelu_s16x2(r.p[i], nhi);   // max(p - hi, 0)
+        sd += addrelu_s16x2(~r.p[i], lo1);  // (-p - 1) + (lo + 1) = lo - p
     }
-    return (uint32_t)max(sum_bright, sum_dark);
+    sb = (sb & 0xffffu) + (sb >> 16);
+    sd = (sd & 0xffffu) + (sd >> 16);
+    return max(sb, sd);
 }
 
 }  // namespace fdf

@@ -124,12 +124,18 @@ struct Layout {
     static constexpr int queue_bytes = kQueueCap * 2;
     static constexpr int klist_off = queue_off + queue_bytes;
     static constexpr int klist_bytes = (MODE == NMS_OFF) ? 0 : 2 * kKlistCap * 2;  // two lists (chunk parity)
-    static constexpr int misc_off = klist_off + klist_bytes;
+    static constexpr int wq_off = klist_off + klist_bytes;             // per-warp stage-1 -> stage-2 queues
+    static constexpr int wq_bytes = kComputeWarps * kWarpQueueCap * 2;
+    static constexpr int vtab_off = wq_off + wq_bytes;                  // validity tables: first / middle / last chunk
+    static constexpr int vtab_bytes = 3 * kVtabWords * 4;
+    static constexpr int misc_off = vtab_off + vtab_bytes;
     static constexpr int misc_bytes = 128;
     static constexpr int bits_off = misc_off + misc_bytes;  // bit plane: out_rows x words_per_row words (+ pad to 4)
     static_assert(bits_off % 16 == 0, "the bit plane is walked with 128-bit loads");
     static_assert(tile_bytes % 128 == 0, "TMA destination must stay 128-byte aligned");
     static_assert(SR % 16 == 0 && SR <= 64, "phase A walks rows in steps of 16; queue entries hold 6 row bits");
+    static_assert((SR / 16) * 32 <= kWarpQueueCap, "a warp queue must hold every group stage 1 looks at");
+    static_assert(vtab_off % 16 == 0, "the validity tables are read with 128-bit loads");
     static_assert(kGroupRows * kTileW <= kQueueCap, "a row group must always fit the candidate queue");
 };
 
@@ -174,7 +180,7 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long *statu
 
 // ---- the detection kernel ----------------------------------------------------------------------
 template <int MODE, int SR>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, SR >= 64 ? 2 : 4)
 fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p) {
     using L = Layout<MODE, SR>;
     constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;  // score halo (rows and columns) needed by the 3x3 NMS
@@ -185,6 +191,8 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     uint16_t *plane = reinterpret_cast<uint16_t *>(smem + L::plane_off);
     uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L::queue_off);
     uint16_t *klists = reinterpret_cast<uint16_t *>(smem + L::klist_off);               // [2][kKlistCap]
+    uint16_t *wq = reinterpret_cast<uint16_t *>(smem + L::wq_off) + (threadIdx.x >> 5) * kWarpQueueCap;
+    uint32_t *vtabs = reinterpret_cast<uint32_t *>(smem + L::vtab_off);                 // [3][kVtabWords]
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::misc_off);             // [2] tile landed
     uint32_t *qcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 16);          // [2] queue fill (chunk parity)
     uint32_t *kcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 24);          // [2] keypoints of the chunk
@@ -211,6 +219,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         s_ticket[0] = atomicAdd(p.ticket, 1u);
     }
     for (int i = tid; i < 4 * nunits; i += kThreads) bits[i] = 0u;
+    if (tid < 3 * kVtabWords) vtabs[tid] = valid_word<MODE>(W, vtab_chunk(tid / kVtabWords, NC), tid % kVtabWords);
     __syncthreads();
 
     const int t = (int)p.threshold, n = (int)p.count;
@@ -268,7 +277,8 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                 nms_pending = false;
             }
             mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags);
-            phase_a<MODE, SR>(tid, tile, queue, &qcount[cp], g, kbias, 0, SR);
+            const uint32_t *vtab = vtabs + vtab_variant(c, NC) * kVtabWords;
+            phase_a_warp<MODE, SR>(warp, lane, tile, wq, vtab, queue, &qcount[cp], g, kbias, 0, SR);
             __syncthreads();  // B1: queue complete; previous chunk fully suppressed
 
             const uint32_t qn = qcount[cp];
@@ -291,7 +301,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                     __syncthreads();
                     if (tid == 0) qcount[cp] = 0u;
                     __syncthreads();
-                    phase_a<MODE, SR>(tid, tile, queue, &qcount[cp], g, kbias, lo, lo + kGroupRows);
+                    phase_a_warp<MODE, SR>(warp, lane, tile, wq, vtab, queue, &qcount[cp], g, kbias, lo, lo + kGroupRows);
                     __syncthreads();
                     phase_b<MODE, SR>(tid, qcount[cp], tile, queue, plane, klists + cp * kKlistCap, &kcount[cp], bits, g,
                                       t, n, tag);
@@ -506,18 +516,19 @@ size_t detect_smem_bytes(int mode, int sr, uint32_t words_per_row) {
     const size_t queue = (size_t)kQueueCap * 2;
     const size_t klist = mode == NMS_OFF ? 0 : (size_t)2 * kKlistCap * 2;
     const size_t bit_words = (((size_t)out_rows(mode, sr) * words_per_row + 3) / 4) * 4;
-    return 2 * tile + plane + queue + klist + 128 + bit_words * 4;
+    const size_t wq = (size_t)kComputeWarps * kWarpQueueCap * 2, vtab = (size_t)3 * (kTileW / 4) * 4;
+    return 2 * tile + plane + queue + klist + wq + vtab + 128 + bit_words * 4;
 }
 
 cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream) {
 #define FDF_CASE(M, S) \
     if (mode == M && sr == S) return launch_t<M, S>(tmap, p, stream);
-    FDF_CASE(0, 16)
     FDF_CASE(0, 32)
-    FDF_CASE(1, 16)
+    FDF_CASE(0, 64)
     FDF_CASE(1, 32)
-    FDF_CASE(2, 16)
+    FDF_CASE(1, 64)
     FDF_CASE(2, 32)
+    FDF_CASE(2, 64)
 #undef FDF_CASE
     return cudaErrorInvalidValue;
 }

@@ -22,9 +22,11 @@ constexpr int kLeftHalo = 12;   // the chunk's first output column is tile colum
 constexpr int kTagPeriod = 15;  // score plane entries carry a 4-bit chunk tag (1..15) above the 12-bit score; the
                                 // plane is cleared at every strip start and every 15 chunks, so entries of
                                 // earlier chunks simply read as "no keypoint" and no per-chunk clear is needed
-constexpr int kQueueCap = 2048; // candidate queue entries per chunk (typical fill: ~200); more -> fallback below
-constexpr int kKlistCap = 512;  // confirmed keypoints per chunk the list NMS handles (typical: ~90); more -> dense NMS
+constexpr int kQueueCap = 2048; // candidate queue entries per chunk (typical fill: ~320 at 64 rows); more -> fallback below
+constexpr int kKlistCap = 1024; // confirmed keypoints per chunk the list NMS handles (typical: ~170); more -> dense NMS
 constexpr int kGroupRows = 8;   // fallback for dense content: filter kGroupRows x 256 <= kQueueCap centres at a time
+constexpr int kWarpQueueCap = 128;  // 16-pixel groups one warp can pass from filter stage 1 to stage 2 per chunk
+                                    // (= 32 lanes x 4 rows, the most stage 1 looks at)
 
 __host__ __device__ constexpr int chunks_per_row(int w) { return (w + kChunkW - 1) / kChunkW; }
 

@@ -1,9 +1,10 @@
-// fdf_strip.cuh -- the per-thread bodies of the detection kernel's phases.
+// fdf_strip.cuh -- the per-thread / per-warp bodies of the detection kernel's phases.
 //
-// They are `__host__ __device__` and take the thread index as an argument: fdf_kernels.cu calls
-// them with threadIdx.x between its barriers, and tests/host/strip_emulator.cpp runs the very same
-// code thread by thread on the CPU (TMA replaced by a zero-filled copy) so that the tiling,
-// halo, validity and NMS-row rules are checked against the oracle without a GPU.
+// They are `__host__ __device__` and take the thread (or warp and lane) index as an argument:
+// fdf_kernels.cu calls them with threadIdx.x between its barriers, and tests/host/strip_emulator.cpp
+// runs the very same code thread by thread on the CPU (TMA replaced by a zero-filled copy, the warp
+// ballot replaced by a loop over the 32 lanes) so that the tiling, halo, validity and NMS-row rules
+// are checked against the oracle without a GPU.
 //
 // Geometry (see fdf_kernels.cuh): a strip has SR scored rows; tile row 0 is image row
 // ys0 - 3 where ys0 is the image row of scored row 0; tile column 0 is image column xt0,
@@ -66,97 +67,147 @@ FDF_HD ChunkGeo make_geo(int w, int h, int ww, int strip, int chunk, int sr) {
     return g;
 }
 
-// ---- phase A: dense filter, 16 centres per thread and row (replaces fast_simd.rs:368-520) -------
-// Thread t handles the 16-pixel group t & 15 of scored rows (t >> 4) + 16k inside [row_lo, row_hi) and
-// pushes (scored row << 8 | tile column) of each centre that passes the necessary-condition filter to the
-// CTA's candidate queue.  Column validity (image border, chunk halo) is checked in phase B.  When the queue
-// is full the entries are dropped but still counted: *qcount > kQueueCap tells the caller to redo the chunk
-// in row groups.
-template <int MODE, int SR>
-FDF_HD void phase_a(int tid, const uint8_t *tile, uint16_t *queue, uint32_t *qcount, const ChunkGeo &g,
-                    uint32_t kbias, int row_lo, int row_hi) {
-    constexpr int IT = SR / (kComputeThreads / 16);  // rows per thread
-    const int q = tid & 15;                          // which 16-pixel group of the 256-wide tile row
-    const int r0 = tid >> 4;                         // first scored row of this thread
-    // step 1, straight-line for all of the thread's rows (independent work the scheduler can overlap):
-    // bit (8*b + k) of gm[it] <=> byte b of word k of the group passed the filter
-    uint32_t gm[IT];
-#pragma unroll
-    for (int it = 0; it < IT; it++) {
-        const int rr = r0 + it * (kComputeThreads / 16);
-        const int y = g.ys0 + rr;
-        const bool live = y >= 3 && y < g.h - 3 && rr >= row_lo && rr < row_hi;  // fast_simd.rs:342
-        const uint8_t *rowp = tile + (rr + 3) * kTileW + q * 16;
-        const uint4 C = *reinterpret_cast<const uint4 *>(rowp);
-        const uint4 N = *reinterpret_cast<const uint4 *>(rowp - 3 * kTileW);
-        const uint4 S = *reinterpret_cast<const uint4 *>(rowp + 3 * kTileW);
-        const uint32_t cl = q > 0 ? *reinterpret_cast<const uint32_t *>(rowp - 4) : 0u;
-        const uint32_t cr = q < 15 ? *reinterpret_cast<const uint32_t *>(rowp + 16) : 0u;
-        // east = pixel x+3, west = pixel x-3 of the same row: byte-shifted views of the row words
-        const uint32_t e0 = byte_perm(C.x, C.y, 0x6543), e1 = byte_perm(C.y, C.z, 0x6543);
-        const uint32_t e2 = byte_perm(C.z, C.w, 0x6543), e3 = byte_perm(C.w, cr, 0x6543);
-        const uint32_t w0 = byte_perm(cl, C.x, 0x4321), w1 = byte_perm(C.x, C.y, 0x4321);
-        const uint32_t w2 = byte_perm(C.y, C.z, 0x4321), w3 = byte_perm(C.z, C.w, 0x4321);
-        const uint32_t f0 = filter4(C.x, N.x, S.x, e0, w0, kbias, 0x80808080u);
-        const uint32_t f1 = filter4(C.y, N.y, S.y, e1, w1, kbias, 0x80808080u);
-        const uint32_t f2 = filter4(C.z, N.z, S.z, e2, w2, kbias, 0x80808080u);
-        const uint32_t f3 = filter4(C.w, N.w, S.w, e3, w3, kbias, 0x80808080u);
-        // each f has only bit 7 of its bytes set
-        gm[it] = live ? ((f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4)) : 0u;
+// ---- which tile columns may hold a centre (fast_simd.rs:369-371, 559-562) ------------------------------
+// Scored columns of a chunk: its own columns plus the one-column score halo the 3x3 NMS needs, inside the
+// image's centre range [3, w-3).  The table has one word per 4 tile columns with 0x80 in every valid byte; it
+// depends on the chunk only through "first / middle / last chunk of the row", so the kernel builds the
+// three variants once (kVtabWords words each).
+constexpr int kVtabWords = kTileW / 4;
+
+template <int MODE>
+FDF_HD uint32_t valid_word(int w, int chunk, int word) {
+    constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;
+    const int xt0 = chunk * kChunkW - kTileLead, x0 = xt0 + kLeftHalo;
+    const int x1 = (chunk == chunks_per_row(w) - 1) ? w - 3 : x0 + kChunkW;
+    const int xlo = max(3, x0 - HS), xhi = min(w - 3, x1 + HS);
+    uint32_t v = 0u;
+    for (int b = 0; b < 4; b++) {
+        const int x = xt0 + 4 * word + b;
+        if (x >= xlo && x < xhi) v |= 0x80u << (8 * b);
     }
-    // step 2: push the survivors
-#pragma unroll
-    for (int it = 0; it < IT; it++) {
-        uint32_t m = gm[it];
-        if (m != 0u) {
-            const int rr = r0 + it * (kComputeThreads / 16);
-            const uint32_t cnt = (uint32_t)popc32(m);
-            uint32_t slot = atomic_add_u32(qcount, cnt);
-            if (slot + cnt <= (uint32_t)kQueueCap) {
-                const uint32_t ent0 = (uint32_t)((rr << 8) | (q * 16));
-                while (m) {
-                    const uint32_t p = (uint32_t)lowest_set_bit(m);
-                    m &= m - 1u;
-                    queue[slot++] = (uint16_t)(ent0 + ((p & 7u) << 2) + (p >> 3));
-                }
-            }
+    return v;
+}
+
+// variant of chunk c: 2 = last chunk of the row (also when it is the only one), 0 = first, 1 = any other
+FDF_HD int vtab_variant(int c, int nc) { return c == nc - 1 ? 2 : (c == 0 ? 0 : 1); }
+FDF_HD int vtab_chunk(int variant, int nc) { return variant == 2 ? nc - 1 : variant; }
+
+// ---- phase A: two-stage dense filter (replaces fast_simd.rs:368-520) -------------------------------------
+// Stage 1 looks at every scored pixel, 16 per lane and row, north/south pair only (~12 % of the pixels of
+// natural content pass, ~19 % of the 16-pixel groups).  Groups with a survivor are compacted into the warp's
+// own queue (ballot + rank, no atomics, no block barrier); stage 2 then runs the full two-pair filter with one
+// lane per queued group and pushes every surviving centre (~2 % of the pixels) to the CTA's candidate queue.
+//
+// Lane l of warp v handles 16-pixel group q = l & 15 of scored rows 16 * it + 2 * v + (l >> 4), it = 0 .. SR/16 - 1.
+// Warp queue entry: scored row << 4 | group.  Candidate entry: scored row << 9 | group << 5 | mask bit.
+
+// stage 1 for one lane and row: non-zero iff the group needs stage 2
+template <int MODE, int SR>
+FDF_HD uint32_t stage1_lane(const uint8_t *tile, int rr, int q, const ChunkGeo &g, uint32_t kbias, int row_lo,
+                            int row_hi) {
+    const int y = g.ys0 + rr;
+    const bool live = y >= 3 && y < g.h - 3 && rr >= row_lo && rr < row_hi;  // fast_simd.rs:342
+    const uint8_t *rowp = tile + (rr + 3) * kTileW + q * 16;
+    const uint32_t any = vertical_any(load16(rowp), load16(rowp - 3 * kTileW), load16(rowp + 3 * kTileW), kbias);
+    return live ? any : 0u;
+}
+
+// stage 2 for one queued group: candidate mask, then one queue entry per surviving centre.  When the queue is
+// full the entries are dropped but still counted: *qcount > kQueueCap tells the caller to redo the chunk in
+// row groups.
+FDF_HD void stage2_entry(uint32_t e, const uint8_t *tile, const uint32_t *vtab, uint32_t kbias, uint16_t *queue,
+                         uint32_t *qcount) {
+    const int rr = (int)(e >> 4), q = (int)(e & 15u);
+    const uint8_t *rowp = tile + (rr + 3) * kTileW + q * 16;
+    // the words left / right of the group: for q = 0 / q = 15 they belong to the neighbouring tile row, which
+    // only reaches centres the validity table excludes (tile columns 0..2 and 253..255)
+    const uint32_t cl = *reinterpret_cast<const uint32_t *>(rowp - 4);
+    const uint32_t cr = *reinterpret_cast<const uint32_t *>(rowp + 16);
+    const uint4 vv = *reinterpret_cast<const uint4 *>(vtab + 4 * q);
+    const uint32_t valid[4] = {vv.x, vv.y, vv.z, vv.w};
+    uint32_t m = candidate_mask16(load16(rowp), load16(rowp - 3 * kTileW), load16(rowp + 3 * kTileW), cl, cr, valid,
+                                  kbias);
+    if (m != 0u) {
+        const uint32_t cnt = (uint32_t)popc32(m);
+        uint32_t slot = atomic_add_u32(qcount, cnt);
+        if (slot + cnt <= (uint32_t)kQueueCap) {
+            const uint32_t base = (uint32_t)((rr << 9) | (q << 5));
+            do {
+                const uint32_t p = (uint32_t)highest_set_bit(m);
+                m ^= 1u << p;
+                queue[slot++] = (uint16_t)(base + p);
+            } while (m != 0u);
         }
     }
 }
 
+// One warp's phase A.  On the device the 32 lanes run it together (lane = threadIdx.x & 31); on the host the
+// emulator calls it once per warp and the lane loops below run sequentially, in the same order as the ballot
+// ranks.  wq is the warp's private queue (kWarpQueueCap entries).
+template <int MODE, int SR>
+FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint16_t *wq, const uint32_t *vtab,
+                         uint16_t *queue, uint32_t *qcount, const ChunkGeo &g, uint32_t kbias, int row_lo,
+                         int row_hi) {
+    constexpr int IT = SR / 16;
+    uint32_t n = 0u;  // entries in wq (warp-uniform)
+#if defined(__CUDA_ARCH__)
+    const int lane = lane_or_minus1;
+    const int q = lane & 15, r0 = 2 * warp + (lane >> 4);
+    uint32_t any[IT];
+#pragma unroll
+    for (int it = 0; it < IT; it++) any[it] = stage1_lane<MODE, SR>(tile, 16 * it + r0, q, g, kbias, row_lo, row_hi);
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int it = 0; it < IT; it++) {
+        const uint32_t b = __ballot_sync(0xffffffffu, any[it] != 0u);
+        if (any[it] != 0u) wq[n + (uint32_t)__popc(b & lt)] = (uint16_t)(((16 * it + r0) << 4) | q);
+        n += (uint32_t)__popc(b);
+    }
+    __syncwarp();
+    for (uint32_t i = (uint32_t)lane; i < n; i += 32u) stage2_entry(wq[i], tile, vtab, kbias, queue, qcount);
+#else
+    (void)lane_or_minus1;
+    for (int it = 0; it < IT; it++)
+        for (int lane = 0; lane < 32; lane++) {
+            const int q = lane & 15, rr = 16 * it + 2 * warp + (lane >> 4);
+            if (stage1_lane<MODE, SR>(tile, rr, q, g, kbias, row_lo, row_hi) != 0u) wq[n++] = (uint16_t)((rr << 4) | q);
+        }
+    for (uint32_t i = 0; i < n; i++) stage2_entry(wq[i], tile, vtab, kbias, queue, qcount);
+#endif
+}
+
 // ---- phase B: exact segment test (+ score) per candidate (replaces fast_simd.rs:115-297, 623-749)
 // One thread per queue entry.  Off mode: sets the keypoint's bit in the strip bit plane.  NMS modes: writes
-// (tag << 12 | score) into the score plane at (scored row, tile column) and appends the entry to the
+// (tag << 12 | score) into the score plane at (scored row, tile column) and appends (row << 8 | column) to the
 // chunk's keypoint list (entries beyond kKlistCap are only counted: the caller then runs the dense NMS).
 template <int MODE, int SR>
 FDF_HD void phase_b(int tid, uint32_t qn, const uint8_t *tile, const uint16_t *queue, uint16_t *plane,
                     uint16_t *klist, uint32_t *kcount, uint32_t *bits, const ChunkGeo &g, int t, int n,
                     uint32_t tag) {
-    constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;
-    // scored columns: the chunk's own columns plus the NMS score halo, inside the image's centre range
-    const int xlo = max(3, g.x0 - HS), xhi = min(g.w - 3, g.x1 + HS);
     for (uint32_t i = (uint32_t)tid; i < qn; i += (uint32_t)kComputeThreads) {
         const uint32_t ent = queue[i];
-        const int rr = (int)(ent >> 8), j = (int)(ent & 0xffu);
-        const int x = g.xt0 + j;
-        if (x < xlo || x >= xhi) continue;  // fast_simd.rs:369-371, 559-562
+        const int rr = (int)(ent >> 9);
+        const int j = (int)((ent >> 5) & 15u) * 16 + mask_bit_to_px((int)(ent & 31u));
         const uint8_t *pc = tile + (rr + 3) * kTileW + j;
         const int cv = pc[0];
-        int ring[16];
+        Ring2 ring;
 #pragma unroll
-        for (int k = 0; k < 16; k++) ring[k] = pc[FDF_RING_DY(k) * kTileW + FDF_RING_DX(k)];
+        for (int k = 0; k < 8; k++)
+            ring.p[k] = mad32((uint32_t)pc[FDF_RING_DY(k + 8) * kTileW + FDF_RING_DX(k + 8)], 0x10000u,
+                              (uint32_t)pc[FDF_RING_DY(k) * kTileW + FDF_RING_DX(k)]);
         const RingMasks rm = ring_masks(cv, ring, t);
         const bool arc_bright = has_arc(rm.bright, n);
         const bool arc_dark = has_arc(rm.dark, n);
         if (arc_bright || arc_dark) {
             if (MODE == NMS_OFF) {
+                const int x = g.xt0 + j;
                 atomic_or_u32(&bits[rr * g.ww + (x >> 5)], 1u << (x & 31));
             } else {
                 const uint32_t sc = (MODE == NMS_MAX_THRESHOLD) ? score_max_threshold(cv, ring, n, arc_bright)
                                                                 : score_sum_abs(cv, ring, t);  // <= 4080 < 2^12
                 plane[rr * kTileW + j] = (uint16_t)((tag << 12) | sc);
                 const uint32_t k = atomic_add_u32(kcount, 1u);
-                if (k < (uint32_t)kKlistCap) klist[k] = (uint16_t)ent;
+                if (k < (uint32_t)kKlistCap) klist[k] = (uint16_t)((rr << 8) | j);
             }
         }
     }

@@ -17,7 +17,7 @@ namespace {
 
 using namespace fdf;
 
-// Mirrors the kernel's per-chunk schedule: phase A (with the previous chunk's list NMS in the same barrier
+// Mirrors the kernel's per-chunk schedule: phase A, warp by warp (with the previous chunk's list NMS in the same barrier
 // interval), barrier, phase B (or the row-group fallback when the queue overflowed), barrier, then either
 // the dense NMS (list overflow) or a deferred list NMS.  `small_caps` has no effect on the code paths (the
 // capacities are compile-time); dense inputs reach the fallbacks by themselves.
@@ -31,7 +31,10 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
     const int NC = chunks_per_row(w);
     const int WW = (w + 31) / 32;
     alignas(16) static uint8_t tile[tile_rows(64) * kTileW];
-    std::vector<uint16_t> plane((size_t)SR * kTileW), queue(kQueueCap), klists(2 * kKlistCap);
+    std::vector<uint16_t> plane((size_t)SR * kTileW), queue(kQueueCap), klists(2 * kKlistCap), wq(kWarpQueueCap);
+    alignas(16) uint32_t vtab[3][kVtabWords];  // validity tables: first / middle / last chunk of a row
+    for (int v = 0; v < 3; v++)
+        for (int i = 0; i < kVtabWords; i++) vtab[v][i] = valid_word<MODE>(w, vtab_chunk(v, NC), i);
     uint32_t qcount[2] = {0, 0}, kcount[2] = {0, 0};
     std::vector<uint32_t> bits((size_t)OUT_R * WW);
     const uint32_t kbias = filter_kbias((uint32_t)t);
@@ -61,8 +64,9 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
                     const int y = ty0 + r, x = g.xt0 + j;
                     tile[r * kTileW + j] = (y >= 0 && y < h && x >= 0 && x < w) ? img[(size_t)y * pitch + x] : 0;
                 }
-            for (int tid = 0; tid < kComputeThreads; tid++)
-                phase_a<MODE, SR>(tid, tile, queue.data(), &qcount[cp], g, kbias, 0, SR);
+            const uint32_t *vt = vtab[vtab_variant(c, NC)];
+            for (int warp = 0; warp < kComputeWarps; warp++)
+                phase_a_warp<MODE, SR>(warp, -1, tile, wq.data(), vt, queue.data(), &qcount[cp], g, kbias, 0, SR);
             const uint32_t qn = qcount[cp];
             qcount[cp ^ 1u] = 0;
             kcount[cp ^ 1u] = 0;
@@ -77,8 +81,9 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
                 if (fallbacks) fallbacks[0]++;
                 for (int lo = 0; lo < SR; lo += kGroupRows) {
                     qcount[cp] = 0;
-                    for (int tid = 0; tid < kComputeThreads; tid++)
-                        phase_a<MODE, SR>(tid, tile, queue.data(), &qcount[cp], g, kbias, lo, lo + kGroupRows);
+                    for (int warp = 0; warp < kComputeWarps; warp++)
+                        phase_a_warp<MODE, SR>(warp, -1, tile, wq.data(), vt, queue.data(), &qcount[cp], g, kbias, lo,
+                                               lo + kGroupRows);
                     if (qcount[cp] > (uint32_t)kQueueCap) return -18;
                     for (int tid = 0; tid < kComputeThreads; tid++)
                         phase_b<MODE, SR>(tid, qcount[cp], tile, queue.data(), plane.data(), klists.data() + cp * kKlistCap,
@@ -131,7 +136,7 @@ int64_t fdf_emulate_detect(const uint8_t *img, uint32_t w, uint32_t h, uint32_t 
     if (fallbacks) fallbacks[0] = fallbacks[1] = 0;  // [0] queue overflow -> row groups, [1] dense NMS
 #define CASE(M, S) \
     if (nms == M && sr == S) return emulate<M, S>(img, (int)w, (int)h, (int)pitch, t, n, o, cap, fallbacks);
-    CASE(0, 16) CASE(0, 32) CASE(1, 16) CASE(1, 32) CASE(2, 16) CASE(2, 32)
+    CASE(0, 32) CASE(0, 64) CASE(1, 32) CASE(1, 64) CASE(2, 32) CASE(2, 64)
 #undef CASE
     return -1;
 }
@@ -176,8 +181,10 @@ int64_t fdf_core_check(uint64_t iterations, uint64_t seed) {
             pos[i] = d > 0 && d > t;
         }
         const bool kp_bright = fdf_oracle_consecutive(neg, 16, n), kp_dark = fdf_oracle_consecutive(pos, 16, n);
-        // device arithmetic
-        const RingMasks rm = ring_masks(c, ring, t);
+        // device arithmetic (two ring pixels per word: ring[i] | ring[i + 8] << 16)
+        Ring2 rp;
+        for (int i = 0; i < 8; i++) rp.p[i] = (uint32_t)ring[i] | ((uint32_t)ring[i + 8] << 16);
+        const RingMasks rm = ring_masks(c, rp, t);
         uint32_t mb = 0, md = 0;
         for (int i = 0; i < 16; i++) {
             mb |= (uint32_t)neg[i] << i;
@@ -186,17 +193,39 @@ int64_t fdf_core_check(uint64_t iterations, uint64_t seed) {
         if ((rm.bright & 0xffffu) != mb || (rm.dark & 0xffffu) != md) bad++;
         const bool ab = has_arc(rm.bright & 0xffffu, n), ad = has_arc(rm.dark & 0xffffu, n);
         if (ab != kp_bright || ad != kp_dark) bad++;
-        if (score_sum_abs(c, ring, t) != fdf_oracle_score_sum_abs_px((uint8_t)c, ring8, (uint8_t)t)) bad++;
+        if (score_sum_abs(c, rp, t) != fdf_oracle_score_sum_abs_px((uint8_t)c, ring8, (uint8_t)t)) bad++;
         if (ab || ad) {
-            if (score_max_threshold(c, ring, n, ab) != fdf_oracle_score_max_threshold_px((uint8_t)c, ring8, (uint8_t)n))
+            if (score_max_threshold(c, rp, n, ab) != fdf_oracle_score_max_threshold_px((uint8_t)c, ring8, (uint8_t)n))
                 bad++;
             // the filter must pass every keypoint: put the centre in each byte lane in turn
-            for (int lane = 0; lane < 4; lane++) {
-                const uint32_t other = (uint32_t)splitmix(s);
-                auto put = [&](int v) { return (other & ~(0xffu << (8 * lane))) | ((uint32_t)v << (8 * lane)); };
-                const uint32_t f = filter4(put(c), put(ring[0]), put(ring[8]), put(ring[4]), put(ring[12]),
-                                           filter_kbias((uint32_t)t), 0x80808080u);
-                if (!((f >> (8 * lane + 7)) & 1u)) bad++;
+            // (a 16-pixel row group of random bytes with the keypoint's N / S / E / W planted around column px)
+            for (int px = 0; px < 16; px += 5) {
+                uint8_t rows[3][24];  // north, centre, south; columns -4 .. 19 of the group
+                for (int rr = 0; rr < 3; rr++)
+                    for (int i = 0; i < 24; i += 8) {
+                        const uint64_t v = splitmix(s);
+                        memcpy(&rows[rr][i], &v, 8);
+                    }
+                rows[1][4 + px] = (uint8_t)c;
+                rows[0][4 + px] = ring8[0];
+                rows[2][4 + px] = ring8[8];
+                rows[1][4 + px + 3] = ring8[4];
+                rows[1][4 + px - 3] = ring8[12];
+                Px16 pc, pn, ps;
+                memcpy(pn.w, &rows[0][4], 16);
+                memcpy(pc.w, &rows[1][4], 16);
+                memcpy(ps.w, &rows[2][4], 16);
+                uint32_t cl, cr;
+                memcpy(&cl, &rows[1][0], 4);
+                memcpy(&cr, &rows[1][20], 4);
+                const uint32_t all[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
+                const uint32_t kb = filter_kbias((uint32_t)t);
+                if (vertical_any(pc, pn, ps, kb) == 0u) bad++;
+                const uint32_t m = candidate_mask16(pc, pn, ps, cl, cr, all, kb);
+                bool found = false;
+                for (int p = 0; p < 32; p++)
+                    if (((m >> p) & 1u) && mask_bit_to_px(p) == px) found = true;
+                if (!found) bad++;
             }
         }
     }

@@ -12,7 +12,7 @@ def test_device_arithmetic_against_oracle(emulator):
     assert emulator.core_check(2_000_000, 42) == 0
 
 
-@pytest.mark.parametrize("sr", [16, 32])
+@pytest.mark.parametrize("sr", [32, 64])
 def test_shipped_image_all_reference_configs(emulator, oracle_mod, golden, sr):
     grey = golden["grey"]
     assert same_points(emulator(grey, 16, 9, 0, sr), golden["rust_off"])
@@ -34,15 +34,15 @@ def test_widths_around_chunk_and_word_boundaries(emulator, oracle_mod):
     for w in (7, 8, 9, 31, 32, 33, 239, 240, 241, 243, 244, 246, 247, 248, 255, 256, 257, 479, 480, 481, 487):
         img = oracle_mod.synth_frame(w, 41, seed=w, frame=0, kind=1)
         for nms in (0, 1):
-            assert same_points(emulator(img, 30, 9, nms, 16), oracle_mod.detect(img, 30, 9, nms)), w
+            assert same_points(emulator(img, 30, 9, nms, 32), oracle_mod.detect(img, 30, 9, nms)), w
 
 
 def test_heights_around_strip_boundaries(emulator, oracle_mod):
-    # strips emit 16/32 rows (Off) or 14/30 rows (NMS) starting at row 3/4
-    for h in (7, 8, 9, 10, 17, 18, 19, 20, 21, 22, 23, 33, 34, 35, 36, 37, 38, 39, 40, 64, 65, 66, 67, 68, 69, 70):
+    # strips emit 32/64 rows (Off) or 30/62 rows (NMS) starting at row 3/4
+    for h in (7, 8, 9, 10, 17, 23, 33, 34, 35, 36, 37, 38, 39, 40, 64, 65, 66, 67, 68, 69, 70, 71, 72, 73, 74, 130, 131, 132):
         img = oracle_mod.synth_frame(70, h, seed=h, frame=1, kind=1)
         for nms in (0, 2):
-            for sr in (16, 32):
+            for sr in (32, 64):
                 assert same_points(emulator(img, 25, 9, nms, sr), oracle_mod.detect(img, 25, 9, nms)), (h, nms, sr)
 
 
@@ -58,7 +58,7 @@ def test_random_images(emulator, oracle_mod):
         else:  # binary blobs: many exact ties for the NMS
             img = (rng.integers(0, 2, (h, w)) * rng.integers(20, 255)).astype(np.uint8)
         t = int(rng.choice([0, 1, 7, 16, 20, 60, 127, 128, 200]))
-        n, nms, sr = int(rng.integers(9, 17)), trial % 3, (16 if trial % 2 else 32)
+        n, nms, sr = int(rng.integers(9, 17)), trial % 3, (64 if trial % 2 else 32)
         assert same_points(emulator(img, t, n, nms, sr), oracle_mod.detect(img, t, n, nms)), (w, h, t, n, nms, sr)
 
 
@@ -68,7 +68,7 @@ def test_wide_image_many_chunks_tag_wrap(emulator, oracle_mod):
     for nms in (1, 2):
         assert same_points(emulator(img, 16, 9, nms, 32), oracle_mod.detect(img, 16, 9, nms))
     img = oracle_mod.synth_frame(4100, 24, seed=78, frame=0, kind=1)
-    assert same_points(emulator(img, 40, 9, 1, 16), oracle_mod.detect(img, 40, 9, 1))
+    assert same_points(emulator(img, 40, 9, 1, 64), oracle_mod.detect(img, 40, 9, 1))
 
 
 def test_dense_content_takes_the_fallback_paths(emulator, oracle_mod):
