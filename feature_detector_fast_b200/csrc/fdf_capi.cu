@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -45,8 +46,8 @@ struct fdf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     EncodeTiledFn encode = nullptr;
-    DeviceBuffer<uint8_t> workspace;            // tickets | flags | cursor | scan status | per-strip count/src/dst
-    DeviceBuffer<fdf_point> staging;            // per-strip ordered runs before the gather
+    DeviceBuffer<uint8_t> workspace;            // tickets | flags | cursor | scan status | per-strip count/dst | run records
+    DeviceBuffer<uint32_t> staging;             // per-chunk unordered runs of (row << 16 | x) before the gather
     DeviceBuffer<uint8_t> staged_frames;        // host-path input staging (pitched to 16 bytes)
     DeviceBuffer<fdf_point> staged_points;      // host-path output staging
     DeviceBuffer<unsigned long long> staged_offsets;
@@ -90,6 +91,10 @@ fdf_status check_config(fdf_ctx *ctx, uint8_t count, uint8_t nms) {
 // strip height: tall strips (less halo) when there is enough work to fill the GPU, short otherwise
 int choose_scored_rows(uint32_t n_frames, uint32_t h, int mode) {
     const long long rows = (long long)h - 2 * fdf::first_out_row(mode);
+    if (const char *force = getenv("FDF_FORCE_SR")) {  // tuning knob for experiments: 32 or 64
+        const int v = atoi(force);
+        if (v == 32 || v == 64) return v;
+    }
     const long long strips64 = (rows + fdf::out_rows(mode, 64) - 1) / fdf::out_rows(mode, 64);
     return (long long)n_frames * strips64 >= 2 * 148 ? 64 : 32;
 }
@@ -197,23 +202,28 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     p.words_per_row = (w + 31) / 32;
     p.threshold = threshold;
     p.count = count;
+    p.mode = (uint32_t)mode;
+    p.sr = (uint32_t)sr;
     p.cap = cap;
     p.out = reinterpret_cast<uint2 *>(d_out);
     p.offsets = reinterpret_cast<unsigned long long *>(d_offsets);
 
-    const size_t smem = fdf::detect_smem_bytes(mode, sr, p.words_per_row);
-    if (smem > 227 * 1024) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "image too wide (%u) for the strip bit plane", w);
+    if (fdf::gather_smem_bytes(mode, sr, p.words_per_row) > 200 * 1024 || w > 65535u)
+        return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "image too wide (%u) for the strip bit plane", w);
     const unsigned long long items = (unsigned long long)n_frames * p.strips_per_frame;
     if (items > 0x7fffffffull) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "batch too large");
 
     // workspace: [header 64 B: ticket, flags, scan ticket, cursor][scan status][zeroed up to here per launch]
-    //            [item_src][item_dst][item_count]
+    //            [item_dst][run_base][item_count][run_count][run_n]
     const size_t scan_tiles = ((size_t)items + fdf::kScanTile - 1) / fdf::kScanTile;
     const size_t zeroed_bytes = kWorkspaceHeader + scan_tiles * sizeof(unsigned long long);
-    const size_t src_off = (zeroed_bytes + 15) & ~(size_t)15;
-    const size_t dst_off = src_off + (size_t)items * sizeof(unsigned long long);
-    const size_t cnt_off = dst_off + (size_t)items * sizeof(unsigned long long);
-    const size_t ws_bytes = cnt_off + (size_t)items * sizeof(uint32_t);
+    const size_t chunks = (size_t)items * p.chunks_per_strip, runs = chunks * (size_t)fdf::run_stride(mode);
+    const size_t dst_off = (zeroed_bytes + 15) & ~(size_t)15;
+    const size_t rbase_off = dst_off + (size_t)items * sizeof(unsigned long long);
+    const size_t cnt_off = rbase_off + runs * sizeof(unsigned long long);
+    const size_t rcnt_off = cnt_off + (size_t)items * sizeof(uint32_t);
+    const size_t rn_off = rcnt_off + runs * sizeof(uint32_t);
+    const size_t ws_bytes = rn_off + chunks * sizeof(uint32_t);
     FDF_CUDA(ctx, ctx->workspace.reserve(ws_bytes));
     FDF_CUDA(ctx, ctx->staging.reserve(cap ? cap : 1));
     FDF_CUDA(ctx, cudaMemsetAsync(ctx->workspace.ptr, 0, zeroed_bytes, stream));
@@ -222,10 +232,12 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     p.scan_ticket = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + 8);
     p.cursor = reinterpret_cast<unsigned long long *>(ctx->workspace.ptr + 16);
     p.scan_status = reinterpret_cast<unsigned long long *>(ctx->workspace.ptr + kWorkspaceHeader);
-    p.item_src = reinterpret_cast<unsigned long long *>(ctx->workspace.ptr + src_off);
     p.item_dst = reinterpret_cast<unsigned long long *>(ctx->workspace.ptr + dst_off);
+    p.run_base = reinterpret_cast<unsigned long long *>(ctx->workspace.ptr + rbase_off);
     p.item_count = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + cnt_off);
-    p.staging = reinterpret_cast<uint2 *>(ctx->staging.ptr);
+    p.run_count = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + rcnt_off);
+    p.run_n = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + rn_off);
+    p.staging = ctx->staging.ptr;
 
     // frames as a 3-D u8 tensor (x, y, frame); box = one tile; out-of-bounds elements read as 0
     CUtensorMap tmap;

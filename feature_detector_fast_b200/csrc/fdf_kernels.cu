@@ -1,31 +1,33 @@
 // fdf_kernels.cu -- sm_100a kernels of the FAST-n detection path.
 //
-// One persistent kernel does the whole path for a batch of frames (replaces fast_simd.rs:301-620):
+// One persistent kernel does the detection for a batch of frames (replaces fast_simd.rs:301-620):
 //
-//   work item  = (frame, strip of full-width rows), handed out through an atomic ticket in row-major
-//                order, which is what makes the decoupled look-back deadlock-free.
+//   work item  = (frame, strip of full-width rows), handed out through an atomic ticket.
 //   8 warps, per chunk of a strip (two block barriers per chunk):
 //     TMA 3-D tiled load (u8 tile 256 x (SR+6), zero-filled outside the image, double buffered,
 //     issued two chunks ahead -- across strip boundaries --, completion on an mbarrier)  -> shared memory
-//     phase A  : dense SWAR filter, 16 centres per thread (LDS.128 + PRMT + VABSDIFF4 + LOP3),
-//                survivors pushed to the CTA's candidate queue                 (fast_simd.rs:368-520)
+//     phase A  : two-stage dense SWAR filter.  Stage 1 (every pixel, 16 per lane: LDS.128 + VABSDIFF4 + LOP3)
+//                tests the north/south pair; groups with a survivor go to the warp's own queue (ballot, no
+//                barrier); stage 2 (one lane per queued group) adds the east/west pair (PRMT byte shifts) and
+//                pushes the surviving centres to the CTA's candidate queue           (fast_simd.rs:368-520)
 //                (the NMS pass of the previous chunk runs in the same barrier interval)
-//     phase B  : one thread per candidate: 16 ring bytes -> brighter/darker 16-bit masks ->
-//                rotate-AND arc test -> score in registers -> tagged score plane + keypoint list
+//     phase B  : one thread per candidate: 16 ring bytes, two per 32-bit word -> brighter/darker 16-bit masks
+//                -> rotate-AND arc test -> score in 16-bit lanes -> tagged score plane + keypoint list
 //                                                                     (fast_simd.rs:115-297, 623-749)
+//                (one warp meanwhile copies the previous chunk's surviving keypoints to the staging buffer)
 //     NMS pass : strict 3x3 maximum on the shared-memory score plane          (fast_simd.rs:588-616)
-//                survivors set one bit in the strip's shared-memory bit plane
-//   per finished strip: popcount of the bit plane (warp + block prefix sums), then the bits are expanded
-//     to (x, y) points, in row-major order, into a bump-allocated run of the staging buffer;
-//     (count, position) is recorded.  The next strip's first tiles are already in flight.
+//                survivors are marked in the chunk's keypoint list
+//   Every chunk leaves one unordered run of (row, x) entries in the staging buffer plus a run record.
 //
 // Two small kernels finish the ordered compaction (fast_simd.rs:550, 596-613: output is row-major):
 //   fdf_scan_kernel   : exclusive prefix sum of the per-strip counts in (frame, strip) order -- block scan
 //                       + decoupled look-back between scan tiles -- giving every strip's final offset and
 //                       the CSR frame offsets;
-//   fdf_gather_kernel : one warp per strip copies its run from staging to that offset.
+//   fdf_gather_kernel : one CTA per strip scatters the strip's runs into a bit plane in shared memory and
+//                       expands it, row-major, to (x, y) points at the strip's final offset.
 // (Doing the look-back inside the detection kernel was measured at +45 % kernel time: with ~450 strips
-// in flight every strip ends up waiting for all in-flight predecessors.)
+// in flight every strip ends up waiting for all in-flight predecessors.  Keeping the strip bit plane inside
+// the detection kernel cost 30 KB of shared memory per CTA, i.e. one resident CTA per SM.)
 #include "fdf_kernels.cuh"
 
 #include "fdf_core.cuh"
@@ -60,11 +62,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// barrier among the compute warps only (the emit warp never joins it)
-__device__ __forceinline__ void bar_compute() {
-    asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory");
 }
 
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
@@ -119,24 +116,25 @@ struct Layout {
     static constexpr int TR = tile_rows(SR);
     static constexpr int tile_bytes = TR * kTileW;  // one TMA box
     static constexpr int plane_off = 2 * tile_bytes;
-    static constexpr int plane_bytes = (MODE == NMS_OFF) ? 0 : SR * kTileW * 2;  // u16: tag << 12 | score
+    static constexpr int plane_bytes = (MODE == NMS_OFF) ? 0 : SR * kPlaneW * 2;  // u16: tag << 12 | score
     static constexpr int queue_off = plane_off + plane_bytes;
     static constexpr int queue_bytes = kQueueCap * 2;
     static constexpr int klist_off = queue_off + queue_bytes;
-    static constexpr int klist_bytes = (MODE == NMS_OFF) ? 0 : 2 * kKlistCap * 2;  // two lists (chunk parity)
+    static constexpr int klist_bytes = 2 * kQueueCap * 2;              // two keypoint lists (chunk parity)
     static constexpr int wq_off = klist_off + klist_bytes;             // per-warp stage-1 -> stage-2 queues
     static constexpr int wq_bytes = kComputeWarps * kWarpQueueCap * 2;
     static constexpr int vtab_off = wq_off + wq_bytes;                  // validity tables: first / middle / last chunk
     static constexpr int vtab_bytes = 3 * kVtabWords * 4;
     static constexpr int misc_off = vtab_off + vtab_bytes;
     static constexpr int misc_bytes = 128;
-    static constexpr int bits_off = misc_off + misc_bytes;  // bit plane: out_rows x words_per_row words (+ pad to 4)
-    static_assert(bits_off % 16 == 0, "the bit plane is walked with 128-bit loads");
+    static constexpr int total = misc_off + misc_bytes;
     static_assert(tile_bytes % 128 == 0, "TMA destination must stay 128-byte aligned");
+    static_assert(plane_bytes % 16 == 0 && plane_off % 16 == 0, "the plane is cleared with 128-bit stores");
     static_assert(SR % 16 == 0 && SR <= 64, "phase A walks rows in steps of 16; queue entries hold 6 row bits");
     static_assert((SR / 16) * 32 <= kWarpQueueCap, "a warp queue must hold every group stage 1 looks at");
     static_assert(vtab_off % 16 == 0, "the validity tables are read with 128-bit loads");
     static_assert(kGroupRows * kTileW <= kQueueCap, "a row group must always fit the candidate queue");
+    static_assert(SR % kGroupRows == 0, "the dense fallback walks whole row groups");
 };
 
 // ---- decoupled look-back (one warp) -------------------------------------------------------------
@@ -179,34 +177,80 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long *statu
 }
 
 // ---- the detection kernel ----------------------------------------------------------------------
+// What is still owed for the chunk processed one step earlier: its NMS pass (runs next to the following
+// chunk's phase A) and the copy of its surviving keypoints to the staging buffer (one warp, next to the
+// following chunk's phase B).
+struct Pending {
+    ChunkGeo g;
+    uint32_t kn;       // keypoints in the chunk's list
+    uint32_t tag;
+    uint32_t slot;     // item * chunks + chunk: index of the chunk's run record
+    uint32_t item;
+    bool last;         // last chunk of its strip: the strip's total is final once it is staged
+    bool nms, out;     // which of the two are still owed
+};
+
+// One warp: copies the (surviving) keypoints of a chunk's list to a freshly reserved run of the staging buffer.
+template <int MODE>
+__device__ __forceinline__ void stage_list(int lane, const uint16_t *klist, const Pending &pd, uint32_t *scount,
+                                           uint32_t *s_total, const DetectParams &p) {
+    const uint32_t count = (MODE == NMS_OFF) ? pd.kn : *scount;
+    __syncwarp();
+    unsigned long long base = 0ull;
+    if (lane == 0) {
+        if (MODE != NMS_OFF) *scount = 0u;
+        if (count != 0u) {
+            base = atomicAdd(p.cursor, (unsigned long long)count);
+            p.run_base[(size_t)pd.slot * run_stride(MODE)] = base;   // (host and gather use the same stride)
+            p.run_count[(size_t)pd.slot * run_stride(MODE)] = count;
+        }
+        p.run_n[pd.slot] = count != 0u ? 1u : 0u;
+        const uint32_t tot = *s_total + count;
+        if (pd.last) p.item_count[pd.item] = tot;
+        *s_total = pd.last ? 0u : tot;
+    }
+    if (count == 0u) return;
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t i0 = 0; i0 < pd.kn; i0 += 32u) {
+        const uint32_t i = i0 + (uint32_t)lane;
+        const uint32_t ent = i < pd.kn ? klist[i] : 0u;
+        const bool take = (MODE == NMS_OFF) ? (i < pd.kn) : ((ent & kSurvivor) != 0u);
+        const uint32_t b = __ballot_sync(0xffffffffu, take);
+        if (take) {
+            const unsigned long long o = base + (unsigned long long)__popc(b & lt);
+            if (o < p.cap) p.staging[o] = staged_entry<MODE>((int)((ent >> 8) & 0x3fu), (int)(ent & 0xffu), pd.g);
+        }
+        base += (unsigned long long)__popc(b);
+    }
+}
+
 template <int MODE, int SR>
-__global__ void __launch_bounds__(kThreads, SR >= 64 ? 2 : 4)
+__global__ void __launch_bounds__(kThreads, SR >= 64 ? 3 : 4)
 fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p) {
     using L = Layout<MODE, SR>;
     constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;  // score halo (rows and columns) needed by the 3x3 NMS
     constexpr int OUT_R = out_rows(MODE, SR);
+    constexpr int RPC = run_stride(MODE);
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *tiles = smem;
     uint16_t *plane = reinterpret_cast<uint16_t *>(smem + L::plane_off);
     uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L::queue_off);
-    uint16_t *klists = reinterpret_cast<uint16_t *>(smem + L::klist_off);               // [2][kKlistCap]
+    uint16_t *klists = reinterpret_cast<uint16_t *>(smem + L::klist_off);               // [2][kQueueCap]
     uint16_t *wq = reinterpret_cast<uint16_t *>(smem + L::wq_off) + (threadIdx.x >> 5) * kWarpQueueCap;
     uint32_t *vtabs = reinterpret_cast<uint32_t *>(smem + L::vtab_off);                 // [3][kVtabWords]
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::misc_off);             // [2] tile landed
     uint32_t *qcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 16);          // [2] queue fill (chunk parity)
     uint32_t *kcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 24);          // [2] keypoints of the chunk
     uint32_t *s_ticket = reinterpret_cast<uint32_t *>(smem + L::misc_off + 32);        // [2] next strip's ticket
-    uint32_t *warp_sums = reinterpret_cast<uint32_t *>(smem + L::misc_off + 48);       // [8]
-    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 80);
-    uint32_t *bits = reinterpret_cast<uint32_t *>(smem + L::bits_off);                  // [OUT_R][words_per_row]
+    uint32_t *scount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 40);          // [2] NMS survivors of the chunk
+    uint32_t *s_total = reinterpret_cast<uint32_t *>(smem + L::misc_off + 48);         // keypoints of the strip so far
+    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 56);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = (int)p.w, H = (int)p.h;
     const int NC = (int)p.chunks_per_strip;
-    const int WW = (int)p.words_per_row;
-    const int nwords = OUT_R * WW;
-    const int nunits = (nwords + 3) / 4;  // the bit plane in 128-bit units (padding words stay zero)
     const uint32_t total_items = p.n_frames * p.strips_per_frame;
 
     if (tid == 0) {
@@ -216,10 +260,18 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         fence_mbar_init();
         qcount[0] = qcount[1] = 0u;
         kcount[0] = kcount[1] = 0u;
+        scount[0] = scount[1] = 0u;
+        *s_total = 0u;
         s_ticket[0] = atomicAdd(p.ticket, 1u);
     }
-    for (int i = tid; i < 4 * nunits; i += kThreads) bits[i] = 0u;
     if (tid < 3 * kVtabWords) vtabs[tid] = valid_word<MODE>(W, vtab_chunk(tid / kVtabWords, NC), tid % kVtabWords);
+    auto clear_plane = [&]() {
+        uint4 *pz = reinterpret_cast<uint4 *>(plane);
+#pragma unroll
+        for (int i = 0; i < (L::plane_bytes / 16 + kThreads - 1) / kThreads; i++)
+            if (i * kThreads + tid < L::plane_bytes / 16) pz[i * kThreads + tid] = make_uint4(0u, 0u, 0u, 0u);
+    };
+    if (MODE != NMS_OFF) clear_plane();
     __syncthreads();
 
     const int t = (int)p.threshold, n = (int)p.count;
@@ -230,6 +282,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     uint32_t cur = s_ticket[0], nxt = 0xffffffffu;
     bool have_nxt = false;
     uint32_t gc = 0;  // chunks processed by this CTA so far: tile stage = gc & 1, mbarrier parity = (gc >> 1) & 1
+    uint32_t tag = 1u;  // (gc % kTagPeriod) + 1
 
     // request the tile of chunk c of the current strip (c < NC) or of chunk c - NC of the next strip
     auto request_tile = [&](int c, uint32_t stream_index) {
@@ -254,30 +307,26 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     if (tid == 0)
         for (int c = 0; c < ahead; c++) request_tile(c, (uint32_t)c);
 
+    Pending pd;
+    pd.nms = pd.out = false;
+    pd.kn = 0u;
+
     for (uint32_t it = 0; cur < total_items; it++) {
         const uint32_t frame = cur / p.strips_per_frame;
         const uint32_t strip = cur - frame * p.strips_per_frame;
-        bool nms_pending = false;  // the NMS pass of the previous chunk still has to run
-        uint32_t pend_kn = 0;
 
         for (int c = 0; c < NC; c++, gc++) {
             const uint32_t stage = gc & 1u, cp = gc & 1u;
             const uint8_t *tile = tiles + stage * L::tile_bytes;
-            const ChunkGeo g = make_geo<MODE>(W, H, WW, (int)strip, c, SR);
-            const uint32_t tag = (uint32_t)(c % kTagPeriod) + 1u;
-            if (MODE != NMS_OFF && c == 0) {  // strip start: restart the tag sequence on a cleared plane
-                uint4 *pz = reinterpret_cast<uint4 *>(plane) + tid;
-#pragma unroll
-                for (int i = 0; i < L::plane_bytes / 16 / kThreads; i++) pz[i * kThreads] = make_uint4(0u, 0u, 0u, 0u);
-            }
-            if (MODE != NMS_OFF && nms_pending) {  // overlaps with this chunk's phase A (other warps)
-                const ChunkGeo gp = make_geo<MODE>(W, H, WW, (int)strip, c - 1, SR);
-                nms_list<MODE, SR>(tid, pend_kn, klists + (cp ^ 1u) * kKlistCap, plane, bits, gp,
-                                   (uint32_t)((c - 1) % kTagPeriod) + 1u);
-                nms_pending = false;
+            const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
+            const uint32_t *vtab = vtabs + vtab_variant(c, NC) * kVtabWords;
+
+            // -- interval 1: NMS of the previous chunk, dense filter of this one ----------------------------
+            if (MODE != NMS_OFF && pd.nms) {
+                nms_list<MODE, SR>(tid, pd.kn, klists + (cp ^ 1u) * kQueueCap, plane, &scount[cp ^ 1u], pd.g, pd.tag);
+                pd.nms = false;
             }
             mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags);
-            const uint32_t *vtab = vtabs + vtab_variant(c, NC) * kVtabWords;
             phase_a_warp<MODE, SR>(warp, lane, tile, wq, vtab, queue, &qcount[cp], g, kbias, 0, SR);
             __syncthreads();  // B1: queue complete; previous chunk fully suppressed
 
@@ -286,122 +335,105 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                 qcount[cp ^ 1u] = 0u;
                 kcount[cp ^ 1u] = 0u;
             }
-            if (MODE != NMS_OFF && c != 0 && tag == 1u) {  // every 15 chunks: restart the tags
-                uint4 *pz = reinterpret_cast<uint4 *>(plane) + tid;
-#pragma unroll
-                for (int i = 0; i < L::plane_bytes / 16 / kThreads; i++) pz[i * kThreads] = make_uint4(0u, 0u, 0u, 0u);
+            if (MODE != NMS_OFF && tag == 1u && gc != 0u) {  // every 15 chunks: restart the tags on a cleared plane
+                clear_plane();
                 __syncthreads();
             }
-            bool dense = false;
+            // -- interval 2: the last warp stages the previous chunk's keypoints, everybody tests candidates ---
+            if (pd.out && warp == kComputeWarps - 1) stage_list<MODE>(lane, klists + (cp ^ 1u) * kQueueCap, pd, &scount[cp ^ 1u], s_total, p);
+            pd.out = false;
+
+            const uint32_t slot = cur * (uint32_t)NC + (uint32_t)c;
             if (qn <= (uint32_t)kQueueCap) {
-                phase_b<MODE, SR>(tid, qn, tile, queue, plane, klists + cp * kKlistCap, &kcount[cp], bits, g, t, n, tag);
-            } else {  // very dense content: redo the chunk kGroupRows rows at a time
-                dense = true;
+                phase_b<MODE, SR>(tid, qn, tile, queue, plane, klists + cp * kQueueCap, &kcount[cp], t, n, tag);
+                __syncthreads();  // B2: tile[stage] is free again; every score of this chunk is in the plane
+                if (tid == 0) request_tile(c + ahead, gc + (uint32_t)ahead);
+                pd.g = g;
+                pd.kn = kcount[cp];
+                pd.tag = tag;
+                pd.slot = slot;
+                pd.item = cur;
+                pd.last = c == NC - 1;
+                pd.nms = MODE != NMS_OFF;
+                pd.out = true;
+            } else {
+                // very dense content: redo the chunk kGroupRows rows at a time and stage it right away
+                uint32_t runs = 0u, chunk_total = 0u;
                 for (int lo = 0; lo < SR; lo += kGroupRows) {
                     __syncthreads();
-                    if (tid == 0) qcount[cp] = 0u;
+                    if (tid == 0) {
+                        qcount[cp] = 0u;
+                        if (MODE == NMS_OFF) kcount[cp] = 0u;
+                    }
                     __syncthreads();
                     phase_a_warp<MODE, SR>(warp, lane, tile, wq, vtab, queue, &qcount[cp], g, kbias, lo, lo + kGroupRows);
                     __syncthreads();
-                    phase_b<MODE, SR>(tid, qcount[cp], tile, queue, plane, klists + cp * kKlistCap, &kcount[cp], bits, g,
-                                      t, n, tag);
+                    phase_b<MODE, SR>(tid, qcount[cp], tile, queue, plane, klists + cp * kQueueCap, &kcount[cp], t, n, tag);
+                    if (MODE == NMS_OFF) {  // Off mode: the group's keypoints are final -> one run per group
+                        __syncthreads();
+                        const uint32_t kn = kcount[cp];
+                        if (kn != 0u) {
+                            if (tid == 0) {
+                                *s_base = atomicAdd(p.cursor, (unsigned long long)kn);
+                                p.run_base[(size_t)slot * RPC + runs] = *s_base;
+                                p.run_count[(size_t)slot * RPC + runs] = kn;
+                            }
+                            __syncthreads();
+                            const unsigned long long base = *s_base;
+                            const uint16_t *kl = klists + cp * kQueueCap;
+                            for (uint32_t i = (uint32_t)tid; i < kn; i += (uint32_t)kThreads)
+                                if (base + i < p.cap)
+                                    p.staging[base + i] = staged_entry<MODE>((int)(kl[i] >> 8), (int)(kl[i] & 0xffu), g);
+                            runs++;
+                            chunk_total += kn;
+                        }
+                    }
                 }
-            }
-            __syncthreads();  // B2: tile[stage] is free again; every score of this chunk is in the plane
-
-            if (tid == 0) request_tile(c + ahead, gc + (uint32_t)ahead);
-            if (MODE != NMS_OFF) {
-                const uint32_t kn = kcount[cp];
-                if (dense || kn > (uint32_t)kKlistCap) {
-                    nms_dense<MODE, SR>(tid, plane, bits, g, tag);
-                    __syncthreads();  // the plane may be re-tagged / the counters reused
-                } else {
-                    nms_pending = true;
-                    pend_kn = kn;
+                __syncthreads();  // every score of this chunk is in the plane; tile[stage] is free again
+                if (tid == 0) request_tile(c + ahead, gc + (uint32_t)ahead);
+                if (MODE != NMS_OFF) {  // NMS modes: scan the whole plane (count, reserve, write)
+                    if (tid == 0) kcount[cp] = 0u;
+                    __syncthreads();
+                    nms_dense<MODE, SR>(tid, 0, plane, &kcount[cp], 0ull, p.cap, p.staging, g, tag);
+                    __syncthreads();
+                    const uint32_t kn = kcount[cp];
+                    if (tid == 0) {
+                        kcount[cp] = 0u;
+                        if (kn != 0u) {
+                            *s_base = atomicAdd(p.cursor, (unsigned long long)kn);
+                            p.run_base[(size_t)slot * RPC] = *s_base;
+                            p.run_count[(size_t)slot * RPC] = kn;
+                        }
+                    }
+                    __syncthreads();
+                    if (kn != 0u) nms_dense<MODE, SR>(tid, 1, plane, &kcount[cp], *s_base, p.cap, p.staging, g, tag);
+                    runs = kn != 0u ? 1u : 0u;
+                    chunk_total = kn;
+                    __syncthreads();
                 }
+                if (tid == 0) {
+                    p.run_n[slot] = runs;
+                    const uint32_t tot = *s_total + chunk_total;
+                    if (c == NC - 1) p.item_count[cur] = tot;
+                    *s_total = c == NC - 1 ? 0u : tot;
+                    kcount[cp] = 0u;
+                }
+                __syncthreads();
             }
-        }
-        if (MODE != NMS_OFF && nms_pending) {
-            const ChunkGeo gp = make_geo<MODE>(W, H, WW, (int)strip, NC - 1, SR);
-            nms_list<MODE, SR>(tid, pend_kn, klists + ((gc - 1u) & 1u) * kKlistCap, plane, bits, gp,
-                               (uint32_t)((NC - 1) % kTagPeriod) + 1u);
+            tag = tag == (uint32_t)kTagPeriod ? 1u : tag + 1u;
         }
         if (tid == 0) {
             if (!have_nxt) nxt = atomicAdd(p.ticket, 1u);  // (only when the look-ahead never reached the next strip)
             s_ticket[(it + 1u) & 1u] = nxt;
             have_nxt = false;
         }
-        __syncthreads();  // strip end: all bits of the strip are set; plane and lists are free
-
-        // ---- strip -> ordered run of points in the staging buffer --------------------------------------
-        // the bit plane is walked in 128-bit units: one unit (4 words = 128 columns) per lane and step
-        const int y0 = first_out_row(MODE) + (int)strip * OUT_R;  // first row this strip emits
-        const EmitRange er = emit_range(warp, nunits);
-        uint4 *bits4 = reinterpret_cast<uint4 *>(bits);
-        uint32_t cnt = 0;
-        for (int u = er.begin + lane; u < er.end; u += 32) {
-            const uint4 v = bits4[u];
-            cnt += (uint32_t)(__popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w));
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);  // warp total
-        if (lane == 0) warp_sums[warp] = cnt;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t ws = lane < kThreads / 32 ? warp_sums[lane] : 0u;
-            uint32_t wincl = ws;
-#pragma unroll
-            for (int d = 1; d < kThreads / 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, wincl, d);
-                if (lane >= d) wincl += v;
-            }
-            if (lane < kThreads / 32) warp_sums[lane] = wincl - ws;  // exclusive offset of each warp
-            if (lane == kThreads / 32 - 1) {
-                unsigned long long o = 0ull;
-                if (wincl != 0u) o = atomicAdd(p.cursor, (unsigned long long)wincl);  // the strip's run in staging
-                *s_base = o;
-                p.item_count[cur] = wincl;
-                p.item_src[cur] = o;
-            }
-        }
-        __syncthreads();
-        if (cnt != 0u) {  // warp-uniform: this warp's range holds keypoints
-            unsigned long long o = *s_base + warp_sums[warp];
-            for (int base = er.begin; base < er.end; base += 32) {
-                const int u = base + lane;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (u < er.end) v = bits4[u];
-                const uint32_t c = (uint32_t)(__popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w));
-                uint32_t incl = c;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t w = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += w;
-                }
-                if (c != 0u) {
-                    unsigned long long oo = o + (incl - c);
-                    const int wi = 4 * u;
-                    int row = wi / WW, col = wi - row * WW;
-                    const uint32_t words[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        if (words[k] != 0u) {
-                            emit_word(words[k], (uint32_t)col * 32u, (uint32_t)(y0 + row), oo, p.cap, p.staging);
-                            oo += (unsigned long long)__popc(words[k]);
-                        }
-                        if (++col == WW) {
-                            col = 0;
-                            row++;
-                        }
-                    }
-                    bits4[u] = make_uint4(0u, 0u, 0u, 0u);  // leave the plane zeroed for the next strip
-                }
-                o += __shfl_sync(0xffffffffu, incl, 31);
-            }
-        }
+        __syncthreads();  // the next ticket is visible
         cur = s_ticket[(it + 1u) & 1u];
-        // (the next strip's first bit is set after its first barrier, i.e. after every warp left this loop)
     }
+    // what the last chunk still owes
+    if (MODE != NMS_OFF && pd.nms) nms_list<MODE, SR>(tid, pd.kn, klists + ((gc - 1u) & 1u) * kQueueCap, plane, &scount[(gc - 1u) & 1u], pd.g, pd.tag);
+    __syncthreads();
+    if (pd.out && warp == kComputeWarps - 1) stage_list<MODE>(lane, klists + ((gc - 1u) & 1u) * kQueueCap, pd, &scount[(gc - 1u) & 1u], s_total, p);
 }
 
 // ---- ordered compaction, step 2: exclusive scan of the per-strip counts -------------------------------
@@ -458,15 +490,84 @@ __global__ void __launch_bounds__(kScanThreads) fdf_scan_kernel(const DetectPara
     }
 }
 
-// ---- ordered compaction, step 3: one warp per strip moves its run to its final position ------------------
-__global__ void __launch_bounds__(256) fdf_gather_kernel(const DetectParams p, uint32_t n_items) {
-    const uint32_t item = blockIdx.x * 8u + (threadIdx.x >> 5);
-    const uint32_t lane = threadIdx.x & 31u;
-    if (item >= n_items) return;
-    const uint32_t cnt = p.item_count[item];
-    const unsigned long long src = p.item_src[item], dst = p.item_dst[item];
-    for (uint32_t k = lane; k < cnt; k += 32u)
-        if (src + k < p.cap && dst + k < p.cap) p.out[dst + k] = p.staging[src + k];
+// ---- ordered compaction, step 3: strip by strip, unordered runs -> row-major points ----------------------
+// Persistent CTAs; a CTA takes strips blockIdx.x, blockIdx.x + gridDim.x, ...  For each strip its keypoints are
+// scattered into a two-level bitmap in shared memory: level 1 = one bit per pixel of the strip's emitted rows
+// (out_rows x words_per_row words), level 2 = one bit per level-1 word.  Thread t then owns level-1 words
+// 32t .. 32t+31 (in row-major order): it counts their bits by walking the set bits of its level-2 word, a block
+// prefix sum turns the counts into offsets, and the same walk expands the bits to (x, y) points at the strip's
+// final position (fast_simd.rs:550, 596-613: the output is row-major).  Every word that is read is cleared, so
+// the bitmap is zeroed only once per CTA and the work per strip is proportional to its keypoints.
+__global__ void __launch_bounds__(kThreads) fdf_gather_kernel(const DetectParams p, uint32_t n_items) {
+    extern __shared__ __align__(16) uint32_t gsm[];
+    __shared__ uint32_t warp_sums[kThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mode = (int)p.mode, sr = (int)p.sr;
+    const int WW = (int)p.words_per_row, NC = (int)p.chunks_per_strip;
+    const int nwords = out_rows(mode, sr) * WW;
+    const int nsum = (nwords + 31) / 32;  // level-2 words
+    const int rpc = run_stride(mode);
+    uint32_t *bits = gsm, *summary = gsm + nsum * 32;
+    for (int i = tid; i < nsum * 33; i += kThreads) gsm[i] = 0u;
+    __syncthreads();
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t total = p.item_count[item];
+        if (total == 0u) continue;  // (block-uniform)
+        const uint32_t strip = item % p.strips_per_frame;
+        const uint32_t y0 = (uint32_t)(first_out_row(mode) + (int)strip * out_rows(mode, sr));
+        // one warp per chunk: its runs -> bits
+        for (int c = warp; c < NC; c += kThreads / 32) {
+            const size_t slot = (size_t)item * NC + c;
+            const uint32_t nr = p.run_n[slot];
+            for (uint32_t r = 0; r < nr; r++) {
+                const unsigned long long base = p.run_base[slot * rpc + r];
+                const uint32_t cnt = p.run_count[slot * rpc + r];
+                for (uint32_t i = (uint32_t)lane; i < cnt; i += 32u) {
+                    if (base + i >= p.cap) break;
+                    const uint32_t e = p.staging[base + i];
+                    const uint32_t x = e & 0xffffu, w1 = (e >> 16) * (uint32_t)WW + (x >> 5);
+                    atomicOr(&bits[w1], 1u << (x & 31u));
+                    atomicOr(&summary[w1 >> 5], 1u << (w1 & 31u));
+                }
+            }
+        }
+        __syncthreads();
+        unsigned long long o = p.item_dst[item];
+        uint32_t block_off = 0u;
+        for (int t0 = 0; t0 < nsum; t0 += kThreads) {  // (one round unless the image is wider than ~8000 pixels)
+            const int ts = t0 + tid;
+            const uint32_t sm = ts < nsum ? summary[ts] : 0u;
+            uint32_t cnt = 0u;
+            for (uint32_t m = sm; m != 0u; m &= m - 1u) cnt += (uint32_t)__popc(bits[32 * ts + lowest_set_bit(m)]);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (lane == 31) warp_sums[warp] = incl;
+            __syncthreads();
+            uint32_t before = block_off, all = 0u;
+#pragma unroll
+            for (int w2 = 0; w2 < kThreads / 32; w2++) {
+                const uint32_t ws = warp_sums[w2];
+                if (w2 < warp) before += ws;
+                all += ws;
+            }
+            block_off += all;
+            unsigned long long oo = o + before + (incl - cnt);
+            for (uint32_t m = sm; m != 0u; m &= m - 1u) {
+                const int w1 = 32 * ts + lowest_set_bit(m);
+                const uint32_t word = bits[w1];
+                bits[w1] = 0u;
+                const int row = w1 / WW, col = w1 - row * WW;
+                emit_word(word, (uint32_t)col * 32u, y0 + (uint32_t)row, oo, p.cap, p.out);
+                oo += (unsigned long long)__popc(word);
+            }
+            if (sm != 0u) summary[ts] = 0u;
+            __syncthreads();  // warp_sums and the bitmap are free again
+        }
+    }
 }
 
 __global__ void fdf_synth_kernel(uint8_t *frames, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t pitch,
@@ -491,7 +592,7 @@ __global__ void fdf_synth_kernel(uint8_t *frames, uint32_t n_frames, uint32_t w,
 template <int MODE, int SR>
 cudaError_t launch_t(const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream) {
     auto kern = fdf_detect_kernel<MODE, SR>;
-    const size_t smem = detect_smem_bytes(MODE, SR, p.words_per_row);
+    const size_t smem = detect_smem_bytes(MODE, SR);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned long long items = (unsigned long long)p.n_frames * p.strips_per_frame;
@@ -510,16 +611,18 @@ cudaError_t launch_t(const CUtensorMap &tmap, const DetectParams &p, cudaStream_
 
 }  // namespace
 
-size_t detect_smem_bytes(int mode, int sr, uint32_t words_per_row) {
+size_t detect_smem_bytes(int mode, int sr) {
     const size_t tile = (size_t)tile_rows(sr) * kTileW;
-    const size_t plane = mode == NMS_OFF ? 0 : (size_t)sr * kTileW * 2;
-    const size_t queue = (size_t)kQueueCap * 2;
-    const size_t klist = mode == NMS_OFF ? 0 : (size_t)2 * kKlistCap * 2;
-    const size_t bit_words = (((size_t)out_rows(mode, sr) * words_per_row + 3) / 4) * 4;
+    const size_t plane = mode == NMS_OFF ? 0 : (size_t)sr * kPlaneW * 2;
+    const size_t queue = (size_t)kQueueCap * 2, klist = (size_t)2 * kQueueCap * 2;
     const size_t wq = (size_t)kComputeWarps * kWarpQueueCap * 2, vtab = (size_t)3 * (kTileW / 4) * 4;
-    return 2 * tile + plane + queue + klist + wq + vtab + 128 + bit_words * 4;
+    return 2 * tile + plane + queue + klist + wq + vtab + 128;
 }
 
+size_t gather_smem_bytes(int mode, int sr, uint32_t words_per_row) {
+    const size_t nsum = ((size_t)out_rows(mode, sr) * words_per_row + 31) / 32;  // level-2 words
+    return nsum * 33 * 4;
+}
 cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream) {
 #define FDF_CASE(M, S) \
     if (mode == M && sr == S) return launch_t<M, S>(tmap, p, stream);
@@ -544,7 +647,17 @@ cudaError_t launch_scan(const DetectParams &p, cudaStream_t stream) {
 cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream) {
     const unsigned long long items = (unsigned long long)p.n_frames * p.strips_per_frame;
     if (items == 0 || items > 0x7fffffffull) return cudaErrorInvalidValue;
-    fdf_gather_kernel<<<(unsigned)((items + 7) / 8), 256, 0, stream>>>(p, (uint32_t)items);
+    const size_t smem = gather_smem_bytes((int)p.mode, (int)p.sr, p.words_per_row);
+    cudaError_t e = cudaFuncSetAttribute(fdf_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fdf_gather_kernel, kThreads, smem)) != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    unsigned long long grid = (unsigned long long)sms * (unsigned)per_sm;
+    if (grid > items) grid = items;
+    fdf_gather_kernel<<<(unsigned)grid, kThreads, smem, stream>>>(p, (uint32_t)items);
     return cudaGetLastError();
 }
 

@@ -18,13 +18,15 @@ constexpr int kTileLead = 16;   // chunk c's tile starts at image column c*kChun
                                 // innermost start coordinate 16-byte aligned (an unaligned one faults)
 constexpr int kLeftHalo = 12;   // the chunk's first output column is tile column 12: left halo 12, right halo 4
                                 // (4 = 3 ring pixels + 1 NMS neighbour)
+constexpr int kPlaneW = 248;    // score plane row pitch in cells: plane column = tile column - kPlaneLead
+constexpr int kPlaneLead = 8;   // (scored tile columns are 11 .. 252 = plane columns 3 .. 244; the NMS reads 3 .. 245)
 
 constexpr int kTagPeriod = 15;  // score plane entries carry a 4-bit chunk tag (1..15) above the 12-bit score; the
-                                // plane is cleared at every strip start and every 15 chunks, so entries of
+                                // plane is cleared every 15 chunks a CTA processes, so entries of
                                 // earlier chunks simply read as "no keypoint" and no per-chunk clear is needed
-constexpr int kQueueCap = 2048; // candidate queue entries per chunk (typical fill: ~320 at 64 rows); more -> fallback below
-constexpr int kKlistCap = 1024; // confirmed keypoints per chunk the list NMS handles (typical: ~170); more -> dense NMS
-constexpr int kGroupRows = 8;   // fallback for dense content: filter kGroupRows x 256 <= kQueueCap centres at a time
+constexpr int kQueueCap = 1024; // candidate queue entries per chunk (typical fill: ~320 at 64 rows); more -> fallback below.
+                                // The keypoint lists have the same capacity, so they cannot overflow when the queue did not.
+constexpr int kGroupRows = 4;   // fallback for dense content: filter kGroupRows x 256 <= kQueueCap centres at a time
 constexpr int kWarpQueueCap = 128;  // 16-pixel groups one warp can pass from filter stage 1 to stage 2 per chunk
                                     // (= 32 lanes x 4 rows, the most stage 1 looks at)
 
@@ -34,21 +36,27 @@ __host__ __device__ constexpr int chunks_per_row(int w) { return (w + kChunkW - 
 __host__ __device__ constexpr int tile_rows(int sr) { return sr + 6; }                             // +-3 ring rows
 __host__ __device__ constexpr int out_rows(int mode, int sr) { return mode == 0 ? sr : sr - 2; }  // NMS needs a 1-row score halo
 __host__ __device__ constexpr int first_out_row(int mode) { return mode == 0 ? 3 : 4; }          // fast_simd.rs:342 / :589-596
+// runs of staged keypoints one chunk can produce: 1, except that the Off-mode dense fallback flushes once per row group
+__host__ __device__ constexpr int runs_per_chunk(int mode, int sr) { return mode == 0 ? sr / kGroupRows : 1; }
+__host__ __device__ constexpr int run_stride(int mode) { return runs_per_chunk(mode, 64); }  // run-record slots per chunk
 
 struct DetectParams {
     uint32_t w, h, n_frames;
     uint32_t strips_per_frame;
     uint32_t chunks_per_strip;
-    uint32_t words_per_row;  // ceil(w / 32): bit-plane words per row
+    uint32_t words_per_row;  // ceil(w / 32): bit-plane words per row (gather kernel)
     uint32_t threshold, count;
+    uint32_t mode, sr;       // (the gather kernel is not templated)
     unsigned long long cap;  // capacity of out (and of staging), in points
     uint2 *out;              // fdf_point[cap], packed over the whole batch, row-major per frame
-    uint2 *staging;          // fdf_point[cap]: each strip's ordered run at a bump-allocated position
+    uint32_t *staging;       // [cap] keypoints as (row in strip << 16 | x), one unordered run per chunk
     unsigned long long *offsets;      // n_frames + 1
     unsigned long long *cursor;       // staging bump allocator (zeroed per launch)
     uint32_t *item_count;             // [items] keypoints of each (frame, strip)
-    unsigned long long *item_src;     // [items] where the strip's run sits in staging
-    unsigned long long *item_dst;     // [items] where it goes in out (exclusive scan of item_count)
+    unsigned long long *item_dst;     // [items] where the strip's points go in out (exclusive scan of item_count)
+    unsigned long long *run_base;     // [items * chunks * runs_per_chunk] where a run sits in staging
+    uint32_t *run_count;              // [items * chunks * runs_per_chunk]
+    uint32_t *run_n;                  // [items * chunks] runs the chunk produced
     unsigned long long *scan_status;  // look-back words of the scan kernel's tiles (zeroed per launch)
     uint32_t *ticket;                 // strip tickets of the detection kernel (zeroed per launch)
     uint32_t *scan_ticket;            // tile tickets of the scan kernel (zeroed per launch)
@@ -59,15 +67,16 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItemsPerThread = 8;
 constexpr int kScanTile = kScanThreads * kScanItemsPerThread;  // strips per scan tile
 
-size_t detect_smem_bytes(int mode, int sr, uint32_t words_per_row);
+size_t detect_smem_bytes(int mode, int sr);
+size_t gather_smem_bytes(int mode, int sr, uint32_t words_per_row);
 
 // Enqueues the detection kernel for (mode, sr) on `stream`.  tmap describes the frames as a 3-D
 // u8 tensor (x, y, frame) with box (kTileW, tile_rows(sr), 1).
 cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream);
 
 // Ordered compaction, off the detection kernel's critical path: an exclusive scan of the per-strip counts
-// (single pass, decoupled look-back between scan tiles) and a gather of every strip's run to its final,
-// row-major position.
+// (single pass, decoupled look-back between scan tiles), then one CTA per strip turns the strip's unordered
+// runs into row-major points at their final position (through a bit plane of the strip in shared memory).
 cudaError_t launch_scan(const DetectParams &p, cudaStream_t stream);
 cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream);
 

@@ -50,15 +50,13 @@ struct ChunkGeo {
     int x0;     // first image column this chunk emits
     int x1;     // one past the last image column this chunk emits
     int xt0;    // image column of tile column 0 (a multiple of 16)
-    int ww;     // bit-plane words per row
 };
 
 template <int MODE>
-FDF_HD ChunkGeo make_geo(int w, int h, int ww, int strip, int chunk, int sr) {
+FDF_HD ChunkGeo make_geo(int w, int h, int strip, int chunk, int sr) {
     ChunkGeo g;
     g.w = w;
     g.h = h;
-    g.ww = ww;
     g.y0 = first_out_row(MODE) + strip * out_rows(MODE, sr);
     g.ys0 = g.y0 - (MODE == NMS_OFF ? 0 : 1);
     g.xt0 = chunk * kChunkW - kTileLead;
@@ -177,13 +175,12 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
 }
 
 // ---- phase B: exact segment test (+ score) per candidate (replaces fast_simd.rs:115-297, 623-749)
-// One thread per queue entry.  Off mode: sets the keypoint's bit in the strip bit plane.  NMS modes: writes
-// (tag << 12 | score) into the score plane at (scored row, tile column) and appends (row << 8 | column) to the
-// chunk's keypoint list (entries beyond kKlistCap are only counted: the caller then runs the dense NMS).
+// One thread per queue entry.  Every confirmed keypoint is appended to the chunk's keypoint list as
+// (scored row << 8 | tile column); the list has the queue's capacity, so it cannot overflow.  NMS modes also
+// write (tag << 12 | score) into the score plane at (scored row, tile column - kPlaneLead).
 template <int MODE, int SR>
 FDF_HD void phase_b(int tid, uint32_t qn, const uint8_t *tile, const uint16_t *queue, uint16_t *plane,
-                    uint16_t *klist, uint32_t *kcount, uint32_t *bits, const ChunkGeo &g, int t, int n,
-                    uint32_t tag) {
+                    uint16_t *klist, uint32_t *kcount, int t, int n, uint32_t tag) {
     for (uint32_t i = (uint32_t)tid; i < qn; i += (uint32_t)kComputeThreads) {
         const uint32_t ent = queue[i];
         const int rr = (int)(ent >> 9);
@@ -199,16 +196,13 @@ FDF_HD void phase_b(int tid, uint32_t qn, const uint8_t *tile, const uint16_t *q
         const bool arc_bright = has_arc(rm.bright, n);
         const bool arc_dark = has_arc(rm.dark, n);
         if (arc_bright || arc_dark) {
-            if (MODE == NMS_OFF) {
-                const int x = g.xt0 + j;
-                atomic_or_u32(&bits[rr * g.ww + (x >> 5)], 1u << (x & 31));
-            } else {
+            if (MODE != NMS_OFF) {
                 const uint32_t sc = (MODE == NMS_MAX_THRESHOLD) ? score_max_threshold(cv, ring, n, arc_bright)
                                                                 : score_sum_abs(cv, ring, t);  // <= 4080 < 2^12
-                plane[rr * kTileW + j] = (uint16_t)((tag << 12) | sc);
-                const uint32_t k = atomic_add_u32(kcount, 1u);
-                if (k < (uint32_t)kKlistCap) klist[k] = (uint16_t)((rr << 8) | j);
+                plane[rr * kPlaneW + j - kPlaneLead] = (uint16_t)((tag << 12) | sc);
             }
+            const uint32_t k = atomic_add_u32(kcount, 1u);
+            if (k < (uint32_t)kQueueCap) klist[k] = (uint16_t)((rr << 8) | j);
         }
     }
 }
@@ -219,39 +213,57 @@ FDF_HD void phase_b(int tid, uint32_t qn, const uint8_t *tile, const uint16_t *q
 // A plane entry belongs to the current chunk iff its tag does; anything else is stale = "no keypoint".
 FDF_HD uint32_t live_score(uint32_t v, uint32_t tag_floor) { return v >= tag_floor ? (v & 0xfffu) : 0u; }
 
+// does the keypoint at (scored row rr, tile column j) survive?
 template <int MODE, int SR>
-FDF_HD void nms_one(int rr, int j, const uint16_t *plane, uint32_t *bits, const ChunkGeo &g, uint32_t floor) {
+FDF_HD bool nms_keep(int rr, int j, const uint16_t *plane, const ChunkGeo &g, uint32_t floor) {
     const int y = g.ys0 + rr, x = g.xt0 + j;
-    if (rr < 1 || rr > SR - 2 || x < g.x0 || x >= g.x1 || y >= g.h - 4) return;
-    const uint16_t *pp = plane + rr * kTileW + j;
+    if (rr < 1 || rr > SR - 2 || x < g.x0 || x >= g.x1 || y >= g.h - 4) return false;
+    const uint16_t *pp = plane + rr * kPlaneW + j - kPlaneLead;
     const uint32_t s = live_score(pp[0], floor);
-    if (s == 0u) return;
-    const bool keep = s > live_score(pp[-kTileW - 1], floor) && s > live_score(pp[-kTileW], floor) &&
-                      s > live_score(pp[-kTileW + 1], floor) && s > live_score(pp[-1], floor) &&
-                      s > live_score(pp[1], floor) && s > live_score(pp[kTileW - 1], floor) &&
-                      s > live_score(pp[kTileW], floor) && s > live_score(pp[kTileW + 1], floor);
-    if (keep) atomic_or_u32(&bits[(rr - 1) * g.ww + (x >> 5)], 1u << (x & 31));
+    if (s == 0u) return false;
+    return s > live_score(pp[-kPlaneW - 1], floor) && s > live_score(pp[-kPlaneW], floor) &&
+           s > live_score(pp[-kPlaneW + 1], floor) && s > live_score(pp[-1], floor) &&
+           s > live_score(pp[1], floor) && s > live_score(pp[kPlaneW - 1], floor) &&
+           s > live_score(pp[kPlaneW], floor) && s > live_score(pp[kPlaneW + 1], floor);
 }
 
-// the chunk's keypoint list (the common case)
+constexpr uint32_t kSurvivor = 0x8000u;  // keypoint-list entries use 14 bits; bit 15 marks "emit this one"
+
+// The chunk's keypoint list: survivors are marked in place and counted.  (Off mode never calls this: every
+// list entry is emitted.)
 template <int MODE, int SR>
-FDF_HD void nms_list(int tid, uint32_t kn, const uint16_t *klist, const uint16_t *plane, uint32_t *bits,
+FDF_HD void nms_list(int tid, uint32_t kn, uint16_t *klist, const uint16_t *plane, uint32_t *scount,
                      const ChunkGeo &g, uint32_t tag) {
     for (uint32_t i = (uint32_t)tid; i < kn; i += (uint32_t)kComputeThreads) {
         const uint32_t ent = klist[i];
-        nms_one<MODE, SR>((int)(ent >> 8), (int)(ent & 0xffu), plane, bits, g, tag << 12);
+        if (nms_keep<MODE, SR>((int)(ent >> 8), (int)(ent & 0xffu), plane, g, tag << 12)) {
+            klist[i] = (uint16_t)(ent | kSurvivor);
+            atomic_add_u32(scount, 1u);
+        }
     }
 }
 
-// every cell of the plane (only when the list overflowed: very dense content)
+// staged form of a keypoint: row inside the strip's emitted rows << 16 | image column
+template <int MODE>
+FDF_HD uint32_t staged_entry(int rr, int j, const ChunkGeo &g) {
+    return (uint32_t)((rr - (MODE == NMS_OFF ? 0 : 1)) << 16) | (uint32_t)(g.xt0 + j);
+}
+
+// Dense fallback (queue overflow: very dense content), NMS modes: every cell of the plane.  Pass 0 counts the
+// survivors, pass 1 writes them to staging[base + slot] with slots handed out through *slot_counter.
 template <int MODE, int SR>
-FDF_HD void nms_dense(int tid, const uint16_t *plane, uint32_t *bits, const ChunkGeo &g, uint32_t tag) {
-    for (int i = tid; i < SR * kTileW; i += kComputeThreads) {
-        if (plane[i] >= (tag << 12)) nms_one<MODE, SR>(i / kTileW, i % kTileW, plane, bits, g, tag << 12);
+FDF_HD void nms_dense(int tid, int pass, const uint16_t *plane, uint32_t *counter, unsigned long long base,
+                      unsigned long long cap, uint32_t *staging, const ChunkGeo &g, uint32_t tag) {
+    for (int i = tid; i < SR * kPlaneW; i += kComputeThreads) {
+        if (plane[i] < (tag << 12)) continue;
+        const int rr = i / kPlaneW, j = i % kPlaneW + kPlaneLead;
+        if (!nms_keep<MODE, SR>(rr, j, plane, g, tag << 12)) continue;
+        const uint32_t slot = atomic_add_u32(counter, 1u);
+        if (pass == 1 && base + slot < cap) staging[base + slot] = staged_entry<MODE>(rr, j, g);
     }
 }
 
-// ---- emission: bit plane -> points, row-major -----------------------------------------------------
+// ---- emission (gather kernel): bit plane -> points, row-major ------------------------------------------
 // The strip's bit plane (out_rows x ww words, in 128-bit units) is cut into one contiguous range per warp;
 // a warp walks its range 32 units at a time: one unit per lane, a warp prefix sum gives every lane its offset.
 struct EmitRange {

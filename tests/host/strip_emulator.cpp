@@ -17,10 +17,10 @@ namespace {
 
 using namespace fdf;
 
-// Mirrors the kernel's per-chunk schedule: phase A, warp by warp (with the previous chunk's list NMS in the same barrier
-// interval), barrier, phase B (or the row-group fallback when the queue overflowed), barrier, then either
-// the dense NMS (list overflow) or a deferred list NMS.  `small_caps` has no effect on the code paths (the
-// capacities are compile-time); dense inputs reach the fallbacks by themselves.
+// Mirrors the kernel's per-chunk schedule: phase A warp by warp, barrier, phase B (or the row-group fallback
+// when the candidate queue overflowed), barrier, NMS pass over the chunk's keypoint list (the kernel runs it next
+// to the following chunk's phase A), then the chunk's surviving keypoints go to the staging buffer as one
+// unordered run.  At the end of a strip the gather kernel's part follows: runs -> bit plane -> row-major points.
 template <int MODE, int SR>
 int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2 *out, size_t cap, int *fallbacks) {
     constexpr int OUT_R = out_rows(MODE, SR);
@@ -31,34 +31,22 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
     const int NC = chunks_per_row(w);
     const int WW = (w + 31) / 32;
     alignas(16) static uint8_t tile[tile_rows(64) * kTileW];
-    std::vector<uint16_t> plane((size_t)SR * kTileW), queue(kQueueCap), klists(2 * kKlistCap), wq(kWarpQueueCap);
+    std::vector<uint16_t> plane((size_t)SR * kPlaneW), queue(kQueueCap), klists(2 * kQueueCap), wq(kWarpQueueCap);
     alignas(16) uint32_t vtab[3][kVtabWords];  // validity tables: first / middle / last chunk of a row
     for (int v = 0; v < 3; v++)
         for (int i = 0; i < kVtabWords; i++) vtab[v][i] = valid_word<MODE>(w, vtab_chunk(v, NC), i);
-    uint32_t qcount[2] = {0, 0}, kcount[2] = {0, 0};
-    std::vector<uint32_t> bits((size_t)OUT_R * WW);
+    uint32_t qcount[2] = {0, 0}, kcount[2] = {0, 0}, scount = 0;
+    std::vector<uint32_t> bits((size_t)OUT_R * WW), staged;
     const uint32_t kbias = filter_kbias((uint32_t)t);
     unsigned long long total = 0;
-    uint32_t gc = 0;
+    uint32_t gc = 0, tag = 1;
     for (int strip = 0; strip < S; strip++) {
-        std::fill(bits.begin(), bits.end(), 0u);
-        bool nms_pending = false;
-        uint32_t pend_kn = 0;
+        staged.clear();
         for (int c = 0; c < NC; c++, gc++) {
             const uint32_t cp = gc & 1u;
-            const ChunkGeo g = make_geo<MODE>(w, h, WW, strip, c, SR);
-            const uint32_t tag = (uint32_t)(c % kTagPeriod) + 1u;
+            const ChunkGeo g = make_geo<MODE>(w, h, strip, c, SR);
             const int ty0 = g.ys0 - 3;
             if (g.xt0 % 16 != 0) return -16;  // TMA: innermost box start must be 16-byte aligned
-            if (MODE != NMS_OFF && c == 0) std::fill(plane.begin(), plane.end(), (uint16_t)0);
-            // the deferred NMS of chunk c-1 reads the plane before this chunk's tile is touched
-            if (MODE != NMS_OFF && nms_pending) {
-                const ChunkGeo gp = make_geo<MODE>(w, h, WW, strip, c - 1, SR);
-                for (int tid = 0; tid < kComputeThreads; tid++)
-                    nms_list<MODE, SR>(tid, pend_kn, klists.data() + (cp ^ 1u) * kKlistCap, plane.data(), bits.data(), gp,
-                                       (uint32_t)((c - 1) % kTagPeriod) + 1u);
-                nms_pending = false;
-            }
             for (int r = 0; r < TR; r++)      // what the TMA tiled load delivers: zero fill outside the image
                 for (int j = 0; j < kTileW; j++) {
                     const int y = ty0 + r, x = g.xt0 + j;
@@ -70,48 +58,69 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
             const uint32_t qn = qcount[cp];
             qcount[cp ^ 1u] = 0;
             kcount[cp ^ 1u] = 0;
-            if (MODE != NMS_OFF && c != 0 && tag == 1u) std::fill(plane.begin(), plane.end(), (uint16_t)0);
-            bool dense = false;
+            if (MODE != NMS_OFF && tag == 1u && gc != 0u) std::fill(plane.begin(), plane.end(), (uint16_t)0);
+            uint16_t *kl = klists.data() + cp * kQueueCap;
             if (qn <= (uint32_t)kQueueCap) {
                 for (int tid = 0; tid < kComputeThreads; tid++)
-                    phase_b<MODE, SR>(tid, qn, tile, queue.data(), plane.data(), klists.data() + cp * kKlistCap, &kcount[cp],
-                                      bits.data(), g, t, n, tag);
+                    phase_b<MODE, SR>(tid, qn, tile, queue.data(), plane.data(), kl, &kcount[cp], t, n, tag);
+                const uint32_t kn = kcount[cp];
+                if (kn > (uint32_t)kQueueCap) return -19;
+                if (MODE != NMS_OFF) {
+                    scount = 0;
+                    for (int tid = 0; tid < kComputeThreads; tid++)
+                        nms_list<MODE, SR>(tid, kn, kl, plane.data(), &scount, g, tag);
+                }
+                uint32_t taken = 0;
+                for (uint32_t i = 0; i < kn; i++)
+                    if (MODE == NMS_OFF || (kl[i] & kSurvivor)) {
+                        staged.push_back(staged_entry<MODE>((kl[i] >> 8) & 0x3f, kl[i] & 0xff, g));
+                        taken++;
+                    }
+                if (MODE != NMS_OFF && taken != scount) return -20;
             } else {
-                dense = true;
                 if (fallbacks) fallbacks[0]++;
                 for (int lo = 0; lo < SR; lo += kGroupRows) {
                     qcount[cp] = 0;
+                    if (MODE == NMS_OFF) kcount[cp] = 0;
                     for (int warp = 0; warp < kComputeWarps; warp++)
                         phase_a_warp<MODE, SR>(warp, -1, tile, wq.data(), vt, queue.data(), &qcount[cp], g, kbias, lo,
                                                lo + kGroupRows);
                     if (qcount[cp] > (uint32_t)kQueueCap) return -18;
                     for (int tid = 0; tid < kComputeThreads; tid++)
-                        phase_b<MODE, SR>(tid, qcount[cp], tile, queue.data(), plane.data(), klists.data() + cp * kKlistCap,
-                                          &kcount[cp], bits.data(), g, t, n, tag);
+                        phase_b<MODE, SR>(tid, qcount[cp], tile, queue.data(), plane.data(), kl, &kcount[cp], t, n, tag);
+                    if (MODE == NMS_OFF)
+                        for (uint32_t i = 0; i < kcount[cp]; i++) staged.push_back(staged_entry<MODE>(kl[i] >> 8, kl[i] & 0xff, g));
                 }
-            }
-            if (MODE != NMS_OFF) {
-                const uint32_t kn = kcount[cp];
-                if (dense || kn > (uint32_t)kKlistCap) {
+                if (MODE != NMS_OFF) {
                     if (fallbacks) fallbacks[1]++;
-                    for (int tid = 0; tid < kComputeThreads; tid++) nms_dense<MODE, SR>(tid, plane.data(), bits.data(), g, tag);
-                } else {
-                    nms_pending = true;
-                    pend_kn = kn;
+                    uint32_t counter = 0;
+                    for (int tid = 0; tid < kComputeThreads; tid++)
+                        nms_dense<MODE, SR>(tid, 0, plane.data(), &counter, 0ull, 0ull, nullptr, g, tag);
+                    std::vector<uint32_t> run(counter + 1);
+                    const uint32_t kn = counter;
+                    counter = 0;
+                    for (int tid = 0; tid < kComputeThreads; tid++)
+                        nms_dense<MODE, SR>(tid, 1, plane.data(), &counter, 0ull, kn, run.data(), g, tag);
+                    if (counter != kn) return -21;
+                    staged.insert(staged.end(), run.begin(), run.begin() + kn);
                 }
+                kcount[cp] = 0;
             }
+            tag = tag == (uint32_t)kTagPeriod ? 1u : tag + 1u;
         }
-        if (MODE != NMS_OFF && nms_pending) {
-            const ChunkGeo gp = make_geo<MODE>(w, h, WW, strip, NC - 1, SR);
-            for (int tid = 0; tid < kComputeThreads; tid++)
-                nms_list<MODE, SR>(tid, pend_kn, klists.data() + ((gc - 1u) & 1u) * kKlistCap, plane.data(), bits.data(), gp,
-                                   (uint32_t)((NC - 1) % kTagPeriod) + 1u);
+        // the gather kernel's part: the strip's runs -> bit plane -> row-major points
+        std::fill(bits.begin(), bits.end(), 0u);
+        for (uint32_t e : staged) {
+            const uint32_t x = e & 0xffffu, row = e >> 16;
+            if ((int)row >= OUT_R || (int)x >= w) return -22;
+            if (bits[row * WW + (x >> 5)] & (1u << (x & 31u))) return -23;  // a keypoint staged twice
+            bits[row * WW + (x >> 5)] |= 1u << (x & 31u);
         }
-        const ChunkGeo g0 = make_geo<MODE>(w, h, WW, strip, 0, SR);
-        for (int i = 0; i < OUT_R * WW; i++) {  // the emit warp's walk, in word order
+        const int y0 = first_out_row(MODE) + strip * OUT_R;
+        for (int i = 0; i < OUT_R * WW; i++) {
             const uint32_t m = bits[i];
             const int row = i / WW, col = i - row * WW;
-            emit_word(m, (uint32_t)col * 32u, (uint32_t)(g0.y0 + row), total, cap, out);
+            emit_word(m, (uint32_t)col * 32u, (uint32_t)(y0 + row), total, cap, out);
             total += (unsigned long long)__builtin_popcount(m);
         }
     }
