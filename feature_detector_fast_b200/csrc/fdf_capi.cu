@@ -42,6 +42,12 @@ struct DeviceBuffer {
 
 }  // namespace
 
+#ifdef FDF_PHASE_CLOCKS
+namespace fdf {
+cudaError_t read_phase_clocks(unsigned long long out[128]);
+}
+#endif
+
 struct fdf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -225,7 +231,8 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     const size_t rn_off = rcnt_off + runs * sizeof(uint32_t);
     const size_t ws_bytes = rn_off + chunks * sizeof(uint32_t);
     FDF_CUDA(ctx, ctx->workspace.reserve(ws_bytes));
-    FDF_CUDA(ctx, ctx->staging.reserve(cap ? cap : 1));
+    p.staging_cap = cap + cap / 2 + fdf::kStageSlack;
+    FDF_CUDA(ctx, ctx->staging.reserve((size_t)p.staging_cap));
     FDF_CUDA(ctx, cudaMemsetAsync(ctx->workspace.ptr, 0, zeroed_bytes, stream));
     p.ticket = reinterpret_cast<uint32_t *>(ctx->workspace.ptr);
     p.flags = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + 4);
@@ -380,6 +387,16 @@ fdf_status fdf_detect(fdf_ctx *ctx, const uint8_t *img, uint32_t w, uint32_t h, 
     if (st == FDF_OK || st == FDF_ERR_CAPACITY) *n_out = (size_t)offsets[1];
     return st;
 }
+
+#ifdef FDF_PHASE_CLOCKS
+// (debug builds only, not part of include/fdf.h) cycles per kernel phase since the last call
+fdf_status fdf_debug_phase_clocks(fdf_ctx *ctx, uint64_t out[128]) {
+    if (!ctx || !out) return FDF_ERR_INVALID_ARGUMENT;
+    FDF_CUDA(ctx, cudaDeviceSynchronize());
+    FDF_CUDA(ctx, fdf::read_phase_clocks(reinterpret_cast<unsigned long long *>(out)));
+    return FDF_OK;
+}
+#endif
 
 fdf_status fdf_synth_frames_device(fdf_ctx *ctx, uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h,
                                    uint32_t pitch, uint64_t frame_stride, uint64_t seed, uint32_t first_frame,

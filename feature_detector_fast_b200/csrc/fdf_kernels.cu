@@ -85,6 +85,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32
             atomicOr(flags, kFlagTmaTimeout);
             break;
         }
+        __nanosleep(64);  // the other warp group is busy: leave it the issue slots
     }
 }
 
@@ -111,18 +112,19 @@ __device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned l
 }
 
 // ---- shared-memory carve-up ------------------------------------------------------------------
+constexpr int kQueueBufs = 3;  // candidate queues in flight: being filled, being tested, being staged
+  // queue entries a test thread works on at once (interleaved dependency chains)
+
 template <int MODE, int SR>
 struct Layout {
     static constexpr int TR = tile_rows(SR);
     static constexpr int tile_bytes = TR * kTileW;  // one TMA box
     static constexpr int plane_off = 2 * tile_bytes;
-    static constexpr int plane_bytes = (MODE == NMS_OFF) ? 0 : SR * kPlaneW * 2;  // u16: tag << 12 | score
+    static constexpr int plane_bytes = SR * kPlaneW * 2;  // u16: tag << 12 | score (Off mode: score 1)
     static constexpr int queue_off = plane_off + plane_bytes;
-    static constexpr int queue_bytes = kQueueCap * 2;
-    static constexpr int klist_off = queue_off + queue_bytes;
-    static constexpr int klist_bytes = 2 * kQueueCap * 2;              // two keypoint lists (chunk parity)
-    static constexpr int wq_off = klist_off + klist_bytes;             // per-warp stage-1 -> stage-2 queues
-    static constexpr int wq_bytes = kComputeWarps * kWarpQueueCap * 2;
+    static constexpr int queue_bytes = kQueueBufs * kQueueCap * 2;      // candidate queue = keypoint list, per chunk
+    static constexpr int wq_off = queue_off + queue_bytes;              // filter warps' stage-1 -> stage-2 queues
+    static constexpr int wq_bytes = kFilterWarps * kWarpQueueCap * 2;
     static constexpr int vtab_off = wq_off + wq_bytes;                  // validity tables: first / middle / last chunk
     static constexpr int vtab_bytes = 3 * kVtabWords * 4;
     static constexpr int misc_off = vtab_off + vtab_bytes;
@@ -130,8 +132,8 @@ struct Layout {
     static constexpr int total = misc_off + misc_bytes;
     static_assert(tile_bytes % 128 == 0, "TMA destination must stay 128-byte aligned");
     static_assert(plane_bytes % 16 == 0 && plane_off % 16 == 0, "the plane is cleared with 128-bit stores");
-    static_assert(SR % 16 == 0 && SR <= 64, "phase A walks rows in steps of 16; queue entries hold 6 row bits");
-    static_assert((SR / 16) * 32 <= kWarpQueueCap, "a warp queue must hold every group stage 1 looks at");
+    static_assert(SR % (2 * kFilterWarps) == 0 && SR <= 64, "filter warps take row pairs; queue entries hold 6 row bits");
+    static_assert(kTestWarps * kWarpQueueCap * 2 <= kQueueCap * 2, "the dense fallback borrows a queue buffer for its warp queues");
     static_assert(vtab_off % 16 == 0, "the validity tables are read with 128-bit loads");
     static_assert(kGroupRows * kTileW <= kQueueCap, "a row group must always fit the candidate queue");
     static_assert(SR % kGroupRows == 0, "the dense fallback walks whole row groups");
@@ -176,53 +178,66 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long *statu
     return excl;
 }
 
-// ---- the detection kernel ----------------------------------------------------------------------
-// What is still owed for the chunk processed one step earlier: its NMS pass (runs next to the following
-// chunk's phase A) and the copy of its surviving keypoints to the staging buffer (one warp, next to the
-// following chunk's phase B).
-struct Pending {
-    ChunkGeo g;
-    uint32_t kn;       // keypoints in the chunk's list
-    uint32_t tag;
-    uint32_t slot;     // item * chunks + chunk: index of the chunk's run record
-    uint32_t item;
-    bool last;         // last chunk of its strip: the strip's total is final once it is staged
-    bool nms, out;     // which of the two are still owed
-};
+// Optional phase clocks (tools/phase_clocks.py builds the library with -DFDF_PHASE_CLOCKS): cycles per phase, summed over
+// the warps of a group (lane 0 of each) and over all CTAs.
+#ifdef FDF_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clocks[8 * 16];  // [warp][slot]
+#define FDF_CLK_BEGIN                 \
+    long long clk_prev = clock64();   \
+    long long clk_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define FDF_CLK(slot)                              \
+    {                                              \
+        const long long clk_now = clock64();       \
+        clk_acc[slot] += clk_now - clk_prev;       \
+        clk_prev = clk_now;                        \
+    }
+#define FDF_CLK_END                                                                               \
+    if (lane == 0)                                                                                \
+        for (int i = 0; i < 10; i++)                                                              \
+            if (clk_acc[i]) atomicAdd(&g_phase_clocks[warp * 16 + i], (unsigned long long)clk_acc[i]);
+#else
+#define FDF_CLK_BEGIN
+#define FDF_CLK(slot)
+#define FDF_CLK_END
+#endif
 
-// One warp: copies the (surviving) keypoints of a chunk's list to a freshly reserved run of the staging buffer.
-template <int MODE>
-__device__ __forceinline__ void stage_list(int lane, const uint16_t *klist, const Pending &pd, uint32_t *scount,
-                                           uint32_t *s_total, const DetectParams &p) {
-    const uint32_t count = (MODE == NMS_OFF) ? pd.kn : *scount;
-    __syncwarp();
-    unsigned long long base = 0ull;
-    if (lane == 0) {
-        if (MODE != NMS_OFF) *scount = 0u;
-        if (count != 0u) {
-            base = atomicAdd(p.cursor, (unsigned long long)count);
-            p.run_base[(size_t)pd.slot * run_stride(MODE)] = base;   // (host and gather use the same stride)
-            p.run_count[(size_t)pd.slot * run_stride(MODE)] = count;
-        }
-        p.run_n[pd.slot] = count != 0u ? 1u : 0u;
-        const uint32_t tot = *s_total + count;
-        if (pd.last) p.item_count[pd.item] = tot;
-        *s_total = pd.last ? 0u : tot;
+// ---- the detection kernel ----------------------------------------------------------------------
+// Two groups of warps per CTA, coupled only through mbarriers (no CTA-wide barrier inside the chunk loop):
+//   filter warps (0 .. kFilterWarps-1): wait for chunk k's tile, run phase A into candidate queue k % 3,
+//       arrive on q_full[k % 3], go on to chunk k + 1;
+//   test warps (the others): wait on q_full[k % 3], run phase B, barrier among themselves, then one thread
+//       requests the tile of chunk k + 2 (the tile buffer of chunk k is free now), all run the NMS pass over
+//       the chunk's keypoint list, barrier, and the last warp copies the survivors to the staging buffer
+//       while the others already wait for chunk k + 1.
+// A landed tile k + 2 implies that chunk k - 1 is completely done, hence that queue (k + 2) % 3 is free again.
+__device__ __forceinline__ void bar_test_group() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kTestThreads) : "memory");
+}
+
+// Staging space is handed out in two levels: a CTA takes blocks of kStageBlock entries from the global cursor
+// (one contended atomic every few dozen chunks instead of one per chunk, which sat on the test warps' critical
+// path) and cuts its runs from the current block.  s_block[0] = next free entry, s_block[1] = end of the block.
+// Only thread t0 calls these, between barriers of the test group.
+// A chunk's run is opened before its size is known (room for a full keypoint list), written by the NMS pass, and
+// closed at its real size: the unused tail goes back to the block.
+__device__ __forceinline__ unsigned long long reserve_staging(uint32_t count, unsigned long long *s_block,
+                                                              const DetectParams &p) {
+    unsigned long long next = s_block[0];
+    if (next + count > s_block[1]) {
+        const unsigned long long n = count > (uint32_t)kStageBlock ? count : (unsigned long long)kStageBlock;
+        next = atomicAdd(p.cursor, n);
+        s_block[1] = next + n;
     }
-    if (count == 0u) return;
-    base = __shfl_sync(0xffffffffu, base, 0);
-    const uint32_t lt = (1u << lane) - 1u;
-    for (uint32_t i0 = 0; i0 < pd.kn; i0 += 32u) {
-        const uint32_t i = i0 + (uint32_t)lane;
-        const uint32_t ent = i < pd.kn ? klist[i] : 0u;
-        const bool take = (MODE == NMS_OFF) ? (i < pd.kn) : ((ent & kSurvivor) != 0u);
-        const uint32_t b = __ballot_sync(0xffffffffu, take);
-        if (take) {
-            const unsigned long long o = base + (unsigned long long)__popc(b & lt);
-            if (o < p.cap) p.staging[o] = staged_entry<MODE>((int)((ent >> 8) & 0x3fu), (int)(ent & 0xffu), pd.g);
-        }
-        base += (unsigned long long)__popc(b);
+    s_block[0] = next + count;
+    return next;
+}
+
+__device__ __forceinline__ unsigned long long open_run(unsigned long long *s_block, const DetectParams &p) {
+    if (s_block[0] + (unsigned long long)kQueueCap > s_block[1]) {
+        s_block[0] = atomicAdd(p.cursor, (unsigned long long)kStageBlock);
+        s_block[1] = s_block[0] + (unsigned long long)kStageBlock;
     }
+    return s_block[0];
 }
 
 template <int MODE, int SR>
@@ -231,209 +246,230 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     using L = Layout<MODE, SR>;
     constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;  // score halo (rows and columns) needed by the 3x3 NMS
     constexpr int OUT_R = out_rows(MODE, SR);
-    constexpr int RPC = run_stride(MODE);
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *tiles = smem;
     uint16_t *plane = reinterpret_cast<uint16_t *>(smem + L::plane_off);
-    uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L::queue_off);
-    uint16_t *klists = reinterpret_cast<uint16_t *>(smem + L::klist_off);               // [2][kQueueCap]
-    uint16_t *wq = reinterpret_cast<uint16_t *>(smem + L::wq_off) + (threadIdx.x >> 5) * kWarpQueueCap;
+    uint16_t *queues = reinterpret_cast<uint16_t *>(smem + L::queue_off);              // [kQueueBufs][kQueueCap]
+    uint16_t *wqs = reinterpret_cast<uint16_t *>(smem + L::wq_off);                    // [kFilterWarps][kWarpQueueCap]
     uint32_t *vtabs = reinterpret_cast<uint32_t *>(smem + L::vtab_off);                 // [3][kVtabWords]
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::misc_off);             // [2] tile landed
-    uint32_t *qcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 16);          // [2] queue fill (chunk parity)
-    uint32_t *kcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 24);          // [2] keypoints of the chunk
-    uint32_t *s_ticket = reinterpret_cast<uint32_t *>(smem + L::misc_off + 32);        // [2] next strip's ticket
-    uint32_t *scount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 40);          // [2] NMS survivors of the chunk
-    uint32_t *s_total = reinterpret_cast<uint32_t *>(smem + L::misc_off + 48);         // keypoints of the strip so far
-    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 56);
+    uint64_t *q_full = reinterpret_cast<uint64_t *>(smem + L::misc_off + 16);          // [3] candidate queue complete
+    uint32_t *qcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 40);          // [3] queue fill
+    uint32_t *s_ticket = reinterpret_cast<uint32_t *>(smem + L::misc_off + 52);        // [2] strip tickets (strip parity)
+    uint32_t *scount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 60);          // keypoints staged by the chunk so far
+    uint32_t *s_total = reinterpret_cast<uint32_t *>(smem + L::misc_off + 68);         // keypoints of the strip so far
+    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 72);
+    unsigned long long *s_block = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 80);   // [2] staging block
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = (int)p.w, H = (int)p.h;
     const int NC = (int)p.chunks_per_strip;
     const uint32_t total_items = p.n_frames * p.strips_per_frame;
+    const bool is_filter = warp < kFilterWarps;
+    const int ttid = tid - kFilterWarps * 32;  // thread index inside the test group
+    const bool t0 = ttid == 0;                 // the thread that draws tickets and requests tiles
 
-    if (tid == 0) {
-        tma_prefetch_desc(&tmap);
-        mbar_init(&full_bar[0], 1);
-        mbar_init(&full_bar[1], 1);
-        fence_mbar_init();
-        qcount[0] = qcount[1] = 0u;
-        kcount[0] = kcount[1] = 0u;
-        scount[0] = scount[1] = 0u;
-        *s_total = 0u;
-        s_ticket[0] = atomicAdd(p.ticket, 1u);
-    }
-    if (tid < 3 * kVtabWords) vtabs[tid] = valid_word<MODE>(W, vtab_chunk(tid / kVtabWords, NC), tid % kVtabWords);
-    auto clear_plane = [&]() {
-        uint4 *pz = reinterpret_cast<uint4 *>(plane);
-#pragma unroll
-        for (int i = 0; i < (L::plane_bytes / 16 + kThreads - 1) / kThreads; i++)
-            if (i * kThreads + tid < L::plane_bytes / 16) pz[i * kThreads + tid] = make_uint4(0u, 0u, 0u, 0u);
-    };
-    if (MODE != NMS_OFF) clear_plane();
-    __syncthreads();
-
-    const int t = (int)p.threshold, n = (int)p.count;
-    const uint32_t kbias = filter_kbias(p.threshold);
-    const int ahead = NC >= 2 ? 2 : 1;  // tiles requested this many chunks ahead (never beyond the next strip)
-    // `nxt` is the ticket of the strip after `cur`.  Thread 0 draws it when the tile look-ahead first needs
-    // it and publishes it through s_ticket[1 - parity]; everybody picks it up at the end of the strip.
-    uint32_t cur = s_ticket[0], nxt = 0xffffffffu;
+    uint32_t cur = 0u, nxt = 0xffffffffu;
     bool have_nxt = false;
-    uint32_t gc = 0;  // chunks processed by this CTA so far: tile stage = gc & 1, mbarrier parity = (gc >> 1) & 1
-    uint32_t tag = 1u;  // (gc % kTagPeriod) + 1
+    const int ahead = NC >= 2 ? 2 : 1;  // tiles requested this many chunks ahead (never beyond the next strip)
 
-    // request the tile of chunk c of the current strip (c < NC) or of chunk c - NC of the next strip
-    auto request_tile = [&](int c, uint32_t stream_index) {
+    // request the tile of chunk c of the current strip (c < NC) or of chunk c - NC of the next strip; `it` is the
+    // current strip's sequence number in this CTA.  When the work is exhausted the barrier is completed without
+    // a tile, so that the filter warps wake up and see the end ticket.
+    auto request_tile = [&](int c, uint32_t stream_index, uint32_t it) {
         uint32_t item = cur;
         if (c >= NC) {
             if (c - NC >= NC) return;
             if (!have_nxt) {
                 nxt = atomicAdd(p.ticket, 1u);
                 have_nxt = true;
+                s_ticket[(it + 1u) & 1u] = nxt;
             }
             item = nxt;
             c -= NC;
         }
-        if (item >= total_items) return;
+        const uint32_t stage = stream_index & 1u;
+        if (item >= total_items) {
+            mbar_arrive(&full_bar[stage]);
+            return;
+        }
         const uint32_t frame = item / p.strips_per_frame;
         const uint32_t strip = item - frame * p.strips_per_frame;
         const int ty0 = first_out_row(MODE) + (int)strip * OUT_R - HS - 3;  // image row of tile row 0
-        const uint32_t stage = stream_index & 1u;
         mbar_expect_tx(&full_bar[stage], (uint32_t)L::tile_bytes);
         tma_load_3d(tiles + stage * L::tile_bytes, &tmap, c * kChunkW - kTileLead, ty0, (int)frame, &full_bar[stage]);
     };
-    if (tid == 0)
-        for (int c = 0; c < ahead; c++) request_tile(c, (uint32_t)c);
 
-    Pending pd;
-    pd.nms = pd.out = false;
-    pd.kn = 0u;
+    if (t0) {
+        tma_prefetch_desc(&tmap);
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        for (int i = 0; i < kQueueBufs; i++) {
+            mbar_init(&q_full[i], kFilterWarps);
+            qcount[i] = 0u;
+        }
+        fence_mbar_init();
+        *scount = 0u;
+        *s_total = 0u;
+        s_block[0] = s_block[1] = 0ull;
+        *s_base = open_run(s_block, p);
+        cur = atomicAdd(p.ticket, 1u);
+        s_ticket[0] = cur;
+    }
+    if (tid < 3 * kVtabWords) vtabs[tid] = valid_word<MODE>(W, vtab_chunk(tid / kVtabWords, NC), tid % kVtabWords);
+    auto clear_plane = [&](int i0, int n) {  // by n threads, i0 = index of this one
+        uint4 *pz = reinterpret_cast<uint4 *>(plane);
+        for (int i = i0; i < L::plane_bytes / 16; i += n) pz[i] = make_uint4(0u, 0u, 0u, 0u);
+    };
+    clear_plane(tid, kThreads);
+    __syncthreads();
+    cur = s_ticket[0];
+    if (t0)
+        for (int c = 0; c < ahead; c++) request_tile(c, (uint32_t)c, 0u);
 
+    const int t = (int)p.threshold, n = (int)p.count;
+    const uint32_t kbias = filter_kbias(p.threshold);
+    uint32_t gc = 0;   // chunks processed by this CTA so far: tile stage = gc & 1, mbarrier parity = (gc >> 1) & 1
+    uint32_t qb = 0, qpar = 0;  // queue buffer gc % 3 and the parity of its q_full phase ((gc / 3) & 1)
+
+    if (is_filter) {
+        // ================================ filter warps =================================================
+        uint16_t *wq = wqs + warp * kWarpQueueCap;
+        FDF_CLK_BEGIN
+        for (uint32_t it = 0; cur < total_items; it++) {
+            const uint32_t frame = cur / p.strips_per_frame;
+            const uint32_t strip = cur - frame * p.strips_per_frame;
+            for (int c = 0; c < NC; c++, gc++) {
+                const uint32_t stage = gc & 1u;
+                const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
+                mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags);  // (also: queue qb is free again)
+                FDF_CLK(0)
+                phase_a_warp<MODE, SR, kFilterWarps>(warp, lane, tiles + stage * L::tile_bytes, wq,
+                                                     vtabs + vtab_variant(c, NC) * kVtabWords, queues + qb * kQueueCap,
+                                                     &qcount[qb], g, kbias, 0, SR);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&q_full[qb]);
+                FDF_CLK(1)
+                if (++qb == (uint32_t)kQueueBufs) {
+                    qb = 0;
+                    qpar ^= 1u;
+                }
+            }
+            // the next strip's ticket is published before its first tile is requested (or the end is signalled)
+            mbar_wait(&full_bar[gc & 1u], (gc >> 1) & 1u, p.flags);
+            FDF_CLK(2)
+            cur = s_ticket[(it + 1u) & 1u];
+        }
+        FDF_CLK_END
+        return;
+    }
+
+    // ==================================== test warps ===================================================
+    uint32_t tag = 1u;  // (gc % kTagPeriod) + 1
+    const int twarp = warp - kFilterWarps;
+    // t0, between the group's barriers: the chunk's run record and the strip's running total
+    auto close_run = [&](uint32_t slot, uint32_t count, bool last) {
+        if (count != 0u) {
+            p.run_base[slot] = *s_base;
+            p.run_count[slot] = count;
+        }
+        p.run_n[slot] = count != 0u ? 1u : 0u;
+        const uint32_t tot = *s_total + count;
+        if (last) p.item_count[cur] = tot;
+        *s_total = last ? 0u : tot;
+    };
+    FDF_CLK_BEGIN
     for (uint32_t it = 0; cur < total_items; it++) {
         const uint32_t frame = cur / p.strips_per_frame;
         const uint32_t strip = cur - frame * p.strips_per_frame;
-
         for (int c = 0; c < NC; c++, gc++) {
-            const uint32_t stage = gc & 1u, cp = gc & 1u;
+            const uint32_t stage = gc & 1u;
             const uint8_t *tile = tiles + stage * L::tile_bytes;
+            uint16_t *queue = queues + qb * kQueueCap;
             const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
-            const uint32_t *vtab = vtabs + vtab_variant(c, NC) * kVtabWords;
-
-            // -- interval 1: NMS of the previous chunk, dense filter of this one ----------------------------
-            if (MODE != NMS_OFF && pd.nms) {
-                nms_list<MODE, SR>(tid, pd.kn, klists + (cp ^ 1u) * kQueueCap, plane, &scount[cp ^ 1u], pd.g, pd.tag);
-                pd.nms = false;
-            }
-            mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags);
-            phase_a_warp<MODE, SR>(warp, lane, tile, wq, vtab, queue, &qcount[cp], g, kbias, 0, SR);
-            __syncthreads();  // B1: queue complete; previous chunk fully suppressed
-
-            const uint32_t qn = qcount[cp];
-            if (tid == 0) {
-                qcount[cp ^ 1u] = 0u;
-                kcount[cp ^ 1u] = 0u;
-            }
-            if (MODE != NMS_OFF && tag == 1u && gc != 0u) {  // every 15 chunks: restart the tags on a cleared plane
-                clear_plane();
-                __syncthreads();
-            }
-            // -- interval 2: the last warp stages the previous chunk's keypoints, everybody tests candidates ---
-            if (pd.out && warp == kComputeWarps - 1) stage_list<MODE>(lane, klists + (cp ^ 1u) * kQueueCap, pd, &scount[cp ^ 1u], s_total, p);
-            pd.out = false;
-
             const uint32_t slot = cur * (uint32_t)NC + (uint32_t)c;
+            if (tag == 1u && gc != 0u) {  // every 15 chunks: restart the tags on a cleared plane
+                clear_plane(ttid, kTestThreads);
+                bar_test_group();
+            }
+            mbar_wait(&q_full[qb], qpar, p.flags);
+            mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags);  // (completed long ago: makes the tile visible here too)
+            FDF_CLK(4)
+            const uint32_t qn = qcount[qb];
             if (qn <= (uint32_t)kQueueCap) {
-                phase_b<MODE, SR>(tid, qn, tile, queue, plane, klists + cp * kQueueCap, &kcount[cp], t, n, tag);
-                __syncthreads();  // B2: tile[stage] is free again; every score of this chunk is in the plane
-                if (tid == 0) request_tile(c + ahead, gc + (uint32_t)ahead);
-                pd.g = g;
-                pd.kn = kcount[cp];
-                pd.tag = tag;
-                pd.slot = slot;
-                pd.item = cur;
-                pd.last = c == NC - 1;
-                pd.nms = MODE != NMS_OFF;
-                pd.out = true;
+                phase_b<MODE, SR, kTestUnroll>(ttid, kTestThreads, qn, tile, queue, plane, t, n, tag);
+                FDF_CLK(5)
+                bar_test_group();  // every score of this chunk is in the plane; tile[stage] is free again
+                if (t0) {
+                    qcount[qb] = 0u;
+                    request_tile(c + ahead, gc + (uint32_t)ahead, it);
+                }
+                emit_list<MODE, SR, kTestUnroll>(ttid, kTestThreads, qn, queue, plane, scount, *s_base, p.staging_cap,
+                                                 p.staging, g, tag);
+                FDF_CLK(7)
+                bar_test_group();  // the run is complete; queue qb is free
+                if (t0) {
+                    const uint32_t count = *scount;
+                    *scount = 0u;
+                    close_run(slot, count, c == NC - 1);
+                    s_block[0] = *s_base + count;  // give the unused tail back
+                    *s_base = open_run(s_block, p);
+                }
+                FDF_CLK(8)
             } else {
-                // very dense content: redo the chunk kGroupRows rows at a time and stage it right away
-                uint32_t runs = 0u, chunk_total = 0u;
+                // very dense content: redo the chunk kGroupRows rows at a time (the test warps filter for themselves;
+                // their warp queues live in the queue buffer nobody uses before the next tile is requested), then
+                // emit from the score plane: count, reserve, write
+                uint16_t *wq = queues + ((qb + 2u) % (uint32_t)kQueueBufs) * kQueueCap + twarp * kWarpQueueCap;
+                const uint32_t *vtab = vtabs + vtab_variant(c, NC) * kVtabWords;
                 for (int lo = 0; lo < SR; lo += kGroupRows) {
-                    __syncthreads();
-                    if (tid == 0) {
-                        qcount[cp] = 0u;
-                        if (MODE == NMS_OFF) kcount[cp] = 0u;
-                    }
-                    __syncthreads();
-                    phase_a_warp<MODE, SR>(warp, lane, tile, wq, vtab, queue, &qcount[cp], g, kbias, lo, lo + kGroupRows);
-                    __syncthreads();
-                    phase_b<MODE, SR>(tid, qcount[cp], tile, queue, plane, klists + cp * kQueueCap, &kcount[cp], t, n, tag);
-                    if (MODE == NMS_OFF) {  // Off mode: the group's keypoints are final -> one run per group
-                        __syncthreads();
-                        const uint32_t kn = kcount[cp];
-                        if (kn != 0u) {
-                            if (tid == 0) {
-                                *s_base = atomicAdd(p.cursor, (unsigned long long)kn);
-                                p.run_base[(size_t)slot * RPC + runs] = *s_base;
-                                p.run_count[(size_t)slot * RPC + runs] = kn;
-                            }
-                            __syncthreads();
-                            const unsigned long long base = *s_base;
-                            const uint16_t *kl = klists + cp * kQueueCap;
-                            for (uint32_t i = (uint32_t)tid; i < kn; i += (uint32_t)kThreads)
-                                if (base + i < p.cap)
-                                    p.staging[base + i] = staged_entry<MODE>((int)(kl[i] >> 8), (int)(kl[i] & 0xffu), g);
-                            runs++;
-                            chunk_total += kn;
-                        }
-                    }
+                    bar_test_group();
+                    if (t0) qcount[qb] = 0u;
+                    bar_test_group();
+                    phase_a_warp<MODE, SR, kTestWarps>(twarp, lane, tile, wq, vtab, queue, &qcount[qb], g, kbias, lo,
+                                                       lo + kGroupRows);
+                    bar_test_group();
+                    phase_b<MODE, SR, kTestUnroll>(ttid, kTestThreads, qcount[qb], tile, queue, plane, t, n, tag);
                 }
-                __syncthreads();  // every score of this chunk is in the plane; tile[stage] is free again
-                if (tid == 0) request_tile(c + ahead, gc + (uint32_t)ahead);
-                if (MODE != NMS_OFF) {  // NMS modes: scan the whole plane (count, reserve, write)
-                    if (tid == 0) kcount[cp] = 0u;
-                    __syncthreads();
-                    nms_dense<MODE, SR>(tid, 0, plane, &kcount[cp], 0ull, p.cap, p.staging, g, tag);
-                    __syncthreads();
-                    const uint32_t kn = kcount[cp];
-                    if (tid == 0) {
-                        kcount[cp] = 0u;
-                        if (kn != 0u) {
-                            *s_base = atomicAdd(p.cursor, (unsigned long long)kn);
-                            p.run_base[(size_t)slot * RPC] = *s_base;
-                            p.run_count[(size_t)slot * RPC] = kn;
-                        }
-                    }
-                    __syncthreads();
-                    if (kn != 0u) nms_dense<MODE, SR>(tid, 1, plane, &kcount[cp], *s_base, p.cap, p.staging, g, tag);
-                    runs = kn != 0u ? 1u : 0u;
-                    chunk_total = kn;
-                    __syncthreads();
+                bar_test_group();  // every score of this chunk is in the plane; tile[stage] is free again
+                if (t0) {
+                    qcount[qb] = 0u;
+                    request_tile(c + ahead, gc + (uint32_t)ahead, it);
                 }
-                if (tid == 0) {
-                    p.run_n[slot] = runs;
-                    const uint32_t tot = *s_total + chunk_total;
-                    if (c == NC - 1) p.item_count[cur] = tot;
-                    *s_total = c == NC - 1 ? 0u : tot;
-                    kcount[cp] = 0u;
+                nms_dense<MODE, SR>(ttid, kTestThreads, 0, plane, scount, 0ull, p.staging_cap, p.staging, g, tag);
+                bar_test_group();
+                const uint32_t kn = *scount;
+                bar_test_group();
+                if (t0) {
+                    *scount = 0u;
+                    s_block[0] = *s_base;  // the run opened for this chunk is not used: the exact size is known now
+                    *s_base = reserve_staging(kn, s_block, p);
                 }
-                __syncthreads();
+                bar_test_group();
+                if (kn != 0u) nms_dense<MODE, SR>(ttid, kTestThreads, 1, plane, scount, *s_base, p.staging_cap, p.staging, g, tag);
+                bar_test_group();
+                if (t0) {
+                    *scount = 0u;
+                    close_run(slot, kn, c == NC - 1);
+                    *s_base = open_run(s_block, p);
+                }
             }
             tag = tag == (uint32_t)kTagPeriod ? 1u : tag + 1u;
+            if (++qb == (uint32_t)kQueueBufs) {
+                qb = 0;
+                qpar ^= 1u;
+            }
         }
-        if (tid == 0) {
-            if (!have_nxt) nxt = atomicAdd(p.ticket, 1u);  // (only when the look-ahead never reached the next strip)
+        if (t0 && !have_nxt) {  // (only when the look-ahead never reached the next strip: cannot happen with ahead >= 1)
+            nxt = atomicAdd(p.ticket, 1u);
             s_ticket[(it + 1u) & 1u] = nxt;
-            have_nxt = false;
         }
-        __syncthreads();  // the next ticket is visible
+        have_nxt = false;
+        bar_test_group();  // the next ticket and the next run's base are visible to the whole group
         cur = s_ticket[(it + 1u) & 1u];
     }
-    // what the last chunk still owes
-    if (MODE != NMS_OFF && pd.nms) nms_list<MODE, SR>(tid, pd.kn, klists + ((gc - 1u) & 1u) * kQueueCap, plane, &scount[(gc - 1u) & 1u], pd.g, pd.tag);
-    __syncthreads();
-    if (pd.out && warp == kComputeWarps - 1) stage_list<MODE>(lane, klists + ((gc - 1u) & 1u) * kQueueCap, pd, &scount[(gc - 1u) & 1u], s_total, p);
+    FDF_CLK_END
 }
 
 // ---- ordered compaction, step 2: exclusive scan of the per-strip counts -------------------------------
@@ -506,7 +542,7 @@ __global__ void __launch_bounds__(kThreads) fdf_gather_kernel(const DetectParams
     const int WW = (int)p.words_per_row, NC = (int)p.chunks_per_strip;
     const int nwords = out_rows(mode, sr) * WW;
     const int nsum = (nwords + 31) / 32;  // level-2 words
-    const int rpc = run_stride(mode);
+    const int rpc = 1;
     uint32_t *bits = gsm, *summary = gsm + nsum * 32;
     for (int i = tid; i < nsum * 33; i += kThreads) gsm[i] = 0u;
     __syncthreads();
@@ -523,7 +559,7 @@ __global__ void __launch_bounds__(kThreads) fdf_gather_kernel(const DetectParams
                 const unsigned long long base = p.run_base[slot * rpc + r];
                 const uint32_t cnt = p.run_count[slot * rpc + r];
                 for (uint32_t i = (uint32_t)lane; i < cnt; i += 32u) {
-                    if (base + i >= p.cap) break;
+                    if (base + i >= p.staging_cap) break;
                     const uint32_t e = p.staging[base + i];
                     const uint32_t x = e & 0xffffu, w1 = (e >> 16) * (uint32_t)WW + (x >> 5);
                     atomicOr(&bits[w1], 1u << (x & 31u));
@@ -589,6 +625,17 @@ __global__ void fdf_synth_kernel(uint8_t *frames, uint32_t n_frames, uint32_t w,
     }
 }
 
+#ifdef FDF_PHASE_CLOCKS
+}  // namespace
+cudaError_t read_phase_clocks(unsigned long long out[128]) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_phase_clocks, 128 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return e;
+    unsigned long long zero[128] = {0};
+    return cudaMemcpyToSymbol(g_phase_clocks, zero, sizeof(zero));
+}
+namespace {
+#endif
+
 template <int MODE, int SR>
 cudaError_t launch_t(const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream) {
     auto kern = fdf_detect_kernel<MODE, SR>;
@@ -613,10 +660,10 @@ cudaError_t launch_t(const CUtensorMap &tmap, const DetectParams &p, cudaStream_
 
 size_t detect_smem_bytes(int mode, int sr) {
     const size_t tile = (size_t)tile_rows(sr) * kTileW;
-    const size_t plane = mode == NMS_OFF ? 0 : (size_t)sr * kPlaneW * 2;
-    const size_t queue = (size_t)kQueueCap * 2, klist = (size_t)2 * kQueueCap * 2;
-    const size_t wq = (size_t)kComputeWarps * kWarpQueueCap * 2, vtab = (size_t)3 * (kTileW / 4) * 4;
-    return 2 * tile + plane + queue + klist + wq + vtab + 128;
+    (void)mode;
+    const size_t plane = (size_t)sr * kPlaneW * 2;
+    const size_t queues = (size_t)kQueueBufs * kQueueCap * 2, wq = (size_t)kFilterWarps * kWarpQueueCap * 2;
+    return 2 * tile + plane + queues + wq + (size_t)3 * kVtabWords * 4 + 128;
 }
 
 size_t gather_smem_bytes(int mode, int sr, uint32_t words_per_row) {

@@ -27,8 +27,18 @@ constexpr int kTagPeriod = 15;  // score plane entries carry a 4-bit chunk tag (
 constexpr int kQueueCap = 1024; // candidate queue entries per chunk (typical fill: ~320 at 64 rows); more -> fallback below.
                                 // The keypoint lists have the same capacity, so they cannot overflow when the queue did not.
 constexpr int kGroupRows = 4;   // fallback for dense content: filter kGroupRows x 256 <= kQueueCap centres at a time
-constexpr int kWarpQueueCap = 128;  // 16-pixel groups one warp can pass from filter stage 1 to stage 2 per chunk
-                                    // (= 32 lanes x 4 rows, the most stage 1 looks at)
+constexpr int kStageBlock = 4096;   // staging entries a CTA reserves at a time from the global cursor
+constexpr unsigned long long kStageSlack = 1024ull * kStageBlock;  // what partly used blocks can waste (<= 1024 CTAs)
+constexpr int kFilterWarps = 4;     // warps 0 .. 3 run phase A (dense filter), warps 4 .. 7 everything per candidate
+constexpr int kTestWarps = kComputeWarps - kFilterWarps;
+constexpr int kTestThreads = kTestWarps * 32;
+#ifndef FDF_TEST_UNROLL
+#define FDF_TEST_UNROLL 1
+#endif
+constexpr int kTestUnroll = FDF_TEST_UNROLL;  // queue entries a test thread works on at once (measured: 1 is best;
+                                              // 2 / 3 interleave the dependency chains but cost registers and issue slots)
+constexpr int kWarpQueueCap = 256;  // 16-pixel groups one warp can pass from filter stage 1 to stage 2 per chunk
+                                    // (= 32 lanes x 8 rows, the most stage 1 looks at)
 
 __host__ __device__ constexpr int chunks_per_row(int w) { return (w + kChunkW - 1) / kChunkW; }
 
@@ -36,9 +46,7 @@ __host__ __device__ constexpr int chunks_per_row(int w) { return (w + kChunkW - 
 __host__ __device__ constexpr int tile_rows(int sr) { return sr + 6; }                             // +-3 ring rows
 __host__ __device__ constexpr int out_rows(int mode, int sr) { return mode == 0 ? sr : sr - 2; }  // NMS needs a 1-row score halo
 __host__ __device__ constexpr int first_out_row(int mode) { return mode == 0 ? 3 : 4; }          // fast_simd.rs:342 / :589-596
-// runs of staged keypoints one chunk can produce: 1, except that the Off-mode dense fallback flushes once per row group
-__host__ __device__ constexpr int runs_per_chunk(int mode, int sr) { return mode == 0 ? sr / kGroupRows : 1; }
-__host__ __device__ constexpr int run_stride(int mode) { return runs_per_chunk(mode, 64); }  // run-record slots per chunk
+__host__ __device__ constexpr int run_stride(int) { return 1; }  // run records per chunk
 
 struct DetectParams {
     uint32_t w, h, n_frames;
@@ -47,9 +55,10 @@ struct DetectParams {
     uint32_t words_per_row;  // ceil(w / 32): bit-plane words per row (gather kernel)
     uint32_t threshold, count;
     uint32_t mode, sr;       // (the gather kernel is not templated)
-    unsigned long long cap;  // capacity of out (and of staging), in points
+    unsigned long long cap;  // capacity of out, in points
+    unsigned long long staging_cap;   // capacity of staging: cap * 3 / 2 + kStageSlack (blocks are not used to the end)
     uint2 *out;              // fdf_point[cap], packed over the whole batch, row-major per frame
-    uint32_t *staging;       // [cap] keypoints as (row in strip << 16 | x), one unordered run per chunk
+    uint32_t *staging;       // [staging_cap] keypoints as (row in strip << 16 | x), one unordered run per chunk
     unsigned long long *offsets;      // n_frames + 1
     unsigned long long *cursor;       // staging bump allocator (zeroed per launch)
     uint32_t *item_count;             // [items] keypoints of each (frame, strip)

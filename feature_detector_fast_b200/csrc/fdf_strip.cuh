@@ -96,18 +96,24 @@ FDF_HD int vtab_chunk(int variant, int nc) { return variant == 2 ? nc - 1 : vari
 // own queue (ballot + rank, no atomics, no block barrier); stage 2 then runs the full two-pair filter with one
 // lane per queued group and pushes every surviving centre (~2 % of the pixels) to the CTA's candidate queue.
 //
-// Lane l of warp v handles 16-pixel group q = l & 15 of scored rows 16 * it + 2 * v + (l >> 4), it = 0 .. SR/16 - 1.
 // Warp queue entry: scored row << 4 | group.  Candidate entry: scored row << 9 | group << 5 | mask bit.
 
+// scored rows [lo, hi) of a strip that can hold a centre at all (fast_simd.rs:342: image rows 3 .. h-4),
+// intersected with the row range the caller asks for
+struct RowRange {
+    int lo, hi;
+};
+FDF_HD RowRange live_rows(const ChunkGeo &g, int row_lo, int row_hi) {
+    RowRange r;
+    r.lo = max(row_lo, 3 - g.ys0);
+    r.hi = min(row_hi, g.h - 3 - g.ys0);
+    return r;
+}
+
 // stage 1 for one lane and row: non-zero iff the group needs stage 2
-template <int MODE, int SR>
-FDF_HD uint32_t stage1_lane(const uint8_t *tile, int rr, int q, const ChunkGeo &g, uint32_t kbias, int row_lo,
-                            int row_hi) {
-    const int y = g.ys0 + rr;
-    const bool live = y >= 3 && y < g.h - 3 && rr >= row_lo && rr < row_hi;  // fast_simd.rs:342
+FDF_HD uint32_t stage1_lane(const uint8_t *tile, int rr, int q, uint32_t kbias) {
     const uint8_t *rowp = tile + (rr + 3) * kTileW + q * 16;
-    const uint32_t any = vertical_any(load16(rowp), load16(rowp - 3 * kTileW), load16(rowp + 3 * kTileW), kbias);
-    return live ? any : 0u;
+    return vertical_any(load16(rowp), load16(rowp - 3 * kTileW), load16(rowp + 3 * kTileW), kbias);
 }
 
 // stage 2 for one queued group: candidate mask, then one queue entry per surviving centre.  When the queue is
@@ -139,26 +145,31 @@ FDF_HD void stage2_entry(uint32_t e, const uint8_t *tile, const uint32_t *vtab, 
     }
 }
 
-// One warp's phase A.  On the device the 32 lanes run it together (lane = threadIdx.x & 31); on the host the
-// emulator calls it once per warp and the lane loops below run sequentially, in the same order as the ballot
-// ranks.  wq is the warp's private queue (kWarpQueueCap entries).
-template <int MODE, int SR>
+// One warp's phase A; NW warps share a chunk.  On the device the 32 lanes run it together (lane = threadIdx.x & 31);
+// on the host the emulator calls it once per warp and the lane loops below run sequentially, in the same order as
+// the ballot ranks.  wq is the warp's private queue (kWarpQueueCap entries).
+// Lane l of warp v handles 16-pixel group q = l & 15 of scored rows 2 * v + (l >> 4) + 2 * NW * it.
+template <int MODE, int SR, int NW>
 FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint16_t *wq, const uint32_t *vtab,
                          uint16_t *queue, uint32_t *qcount, const ChunkGeo &g, uint32_t kbias, int row_lo,
                          int row_hi) {
-    constexpr int IT = SR / 16;
+    constexpr int IT = SR / (2 * NW);
+    static_assert(IT * 32 <= kWarpQueueCap, "a warp queue must hold every group stage 1 looks at");
+    const RowRange live = live_rows(g, row_lo, row_hi);
     uint32_t n = 0u;  // entries in wq (warp-uniform)
 #if defined(__CUDA_ARCH__)
     const int lane = lane_or_minus1;
     const int q = lane & 15, r0 = 2 * warp + (lane >> 4);
-    uint32_t any[IT];
-#pragma unroll
-    for (int it = 0; it < IT; it++) any[it] = stage1_lane<MODE, SR>(tile, 16 * it + r0, q, g, kbias, row_lo, row_hi);
     const uint32_t lt = (1u << lane) - 1u;
+    const uint8_t *lanep = tile + r0 * kTileW + q * 16;
+    uint32_t ent = (uint32_t)((r0 << 4) | q);
 #pragma unroll
     for (int it = 0; it < IT; it++) {
-        const uint32_t b = __ballot_sync(0xffffffffu, any[it] != 0u);
-        if (any[it] != 0u) wq[n + (uint32_t)__popc(b & lt)] = (uint16_t)(((16 * it + r0) << 4) | q);
+        const int rr = r0 + 2 * NW * it;
+        uint32_t any = stage1_lane(lanep + 2 * NW * it * kTileW, 0, 0, kbias);
+        if (rr < live.lo || rr >= live.hi) any = 0u;
+        const uint32_t b = __ballot_sync(0xffffffffu, any != 0u);
+        if (any != 0u) wq[n + (uint32_t)__popc(b & lt)] = (uint16_t)(ent + (uint32_t)(2 * NW * it << 4));
         n += (uint32_t)__popc(b);
     }
     __syncwarp();
@@ -167,42 +178,62 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
     (void)lane_or_minus1;
     for (int it = 0; it < IT; it++)
         for (int lane = 0; lane < 32; lane++) {
-            const int q = lane & 15, rr = 16 * it + 2 * warp + (lane >> 4);
-            if (stage1_lane<MODE, SR>(tile, rr, q, g, kbias, row_lo, row_hi) != 0u) wq[n++] = (uint16_t)((rr << 4) | q);
+            const int q = lane & 15, rr = 2 * warp + (lane >> 4) + 2 * NW * it;
+            if (rr < live.lo || rr >= live.hi) continue;
+            if (stage1_lane(tile, rr, q, kbias) != 0u) wq[n++] = (uint16_t)((rr << 4) | q);
         }
     for (uint32_t i = 0; i < n; i++) stage2_entry(wq[i], tile, vtab, kbias, queue, qcount);
 #endif
 }
 
 // ---- phase B: exact segment test (+ score) per candidate (replaces fast_simd.rs:115-297, 623-749)
-// One thread per queue entry.  Every confirmed keypoint is appended to the chunk's keypoint list as
-// (scored row << 8 | tile column); the list has the queue's capacity, so it cannot overflow.  NMS modes also
-// write (tag << 12 | score) into the score plane at (scored row, tile column - kPlaneLead).
-template <int MODE, int SR>
-FDF_HD void phase_b(int tid, uint32_t qn, const uint8_t *tile, const uint16_t *queue, uint16_t *plane,
-                    uint16_t *klist, uint32_t *kcount, int t, int n, uint32_t tag) {
-    for (uint32_t i = (uint32_t)tid; i < qn; i += (uint32_t)kComputeThreads) {
-        const uint32_t ent = queue[i];
-        const int rr = (int)(ent >> 9);
-        const int j = (int)((ent >> 5) & 15u) * 16 + mask_bit_to_px((int)(ent & 31u));
-        const uint8_t *pc = tile + (rr + 3) * kTileW + j;
-        const int cv = pc[0];
-        Ring2 ring;
+// One thread per queue entry, U entries per thread and step: their loads, arithmetic and stores are kept in
+// separate, branch-free sections so that the U dependency chains interleave (the test warps are few and would
+// otherwise sit in instruction latency).  The entry is rewritten in place: kKeypoint | scored row << 8 |
+// tile column for a confirmed keypoint, 0 otherwise -- the candidate queue thereby becomes the chunk's keypoint
+// list.  Every keypoint also writes (tag << 12 | score) into the score plane at (scored row, tile column -
+// kPlaneLead); in Off mode the score is 1 and only the dense fallback reads it.
+constexpr uint32_t kKeypoint = 0x8000u;  // (row << 8 | column) needs 14 bits
+
+template <int MODE, int SR, int U>
+FDF_HD void phase_b(int tid, int nthreads, uint32_t qn, const uint8_t *tile, uint16_t *queue, uint16_t *plane, int t,
+                    int n, uint32_t tag) {
+    for (uint32_t i0 = (uint32_t)tid; i0 < qn; i0 += (uint32_t)(U * nthreads)) {
+        int pos[U], cv[U];
+        Ring2 ring[U];
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-            ring.p[k] = mad32((uint32_t)pc[FDF_RING_DY(k + 8) * kTileW + FDF_RING_DX(k + 8)], 0x10000u,
-                              (uint32_t)pc[FDF_RING_DY(k) * kTileW + FDF_RING_DX(k)]);
-        const RingMasks rm = ring_masks(cv, ring, t);
-        const bool arc_bright = has_arc(rm.bright, n);
-        const bool arc_dark = has_arc(rm.dark, n);
-        if (arc_bright || arc_dark) {
-            if (MODE != NMS_OFF) {
-                const uint32_t sc = (MODE == NMS_MAX_THRESHOLD) ? score_max_threshold(cv, ring, n, arc_bright)
-                                                                : score_sum_abs(cv, ring, t);  // <= 4080 < 2^12
-                plane[rr * kPlaneW + j - kPlaneLead] = (uint16_t)((tag << 12) | sc);
+        for (int u = 0; u < U; u++) {  // loads (a missing entry repeats the first one and is dropped at the end)
+            const uint32_t i = i0 + (uint32_t)(u * nthreads);
+            const uint32_t ent = queue[i < qn ? i : i0];
+            const int rr = (int)(ent >> 9);
+            const int j = (int)((ent >> 5) & 15u) * 16 + mask_bit_to_px((int)(ent & 31u));
+            pos[u] = (rr << 8) | j;
+            const uint8_t *pc = tile + (rr + 3) * kTileW + j;
+            cv[u] = pc[0];
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                ring[u].p[k] = mad32((uint32_t)pc[FDF_RING_DY(k + 8) * kTileW + FDF_RING_DX(k + 8)], 0x10000u,
+                                     (uint32_t)pc[FDF_RING_DY(k) * kTileW + FDF_RING_DX(k)]);
+        }
+        bool kp[U];
+        uint32_t sc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {  // arithmetic
+            const RingMasks rm = ring_masks(cv[u], ring[u], t);
+            const bool arc_bright = has_arc(rm.bright, n);
+            kp[u] = arc_bright || has_arc(rm.dark, n);
+            sc[u] = 1u;  // Off mode: the plane only records "keypoint here" (used by the dense fallback)
+            if (MODE == NMS_MAX_THRESHOLD) sc[u] = score_max_threshold(cv[u], ring[u], n, arc_bright);  // (garbage unless kp)
+            if (MODE == NMS_SUM_ABSOLUTE) sc[u] = score_sum_abs(cv[u], ring[u], t);                      // <= 4080 < 2^12
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {  // stores
+            const uint32_t i = i0 + (uint32_t)(u * nthreads);
+            if (i < qn) {
+                if (kp[u])
+                    plane[(pos[u] >> 8) * kPlaneW + (pos[u] & 0xff) - kPlaneLead] = (uint16_t)((tag << 12) | sc[u]);
+                queue[i] = (uint16_t)(kp[u] ? (kKeypoint | (uint32_t)pos[u]) : 0u);
             }
-            const uint32_t k = atomic_add_u32(kcount, 1u);
-            if (k < (uint32_t)kQueueCap) klist[k] = (uint16_t)((rr << 8) | j);
         }
     }
 }
@@ -210,37 +241,43 @@ FDF_HD void phase_b(int tid, uint32_t qn, const uint8_t *tile, const uint16_t *q
 // ---- NMS: strict maximum over the 8 neighbours (replaces fast_simd.rs:588-616) -------------------
 // Only this chunk's own columns and this strip's own rows are emitted; rows 3 and h-4 are scored
 // (they act as neighbours) but never emitted (fast_simd.rs:589-596, opencv_compat.rs:238-240).
-// A plane entry belongs to the current chunk iff its tag does; anything else is stale = "no keypoint".
-FDF_HD uint32_t live_score(uint32_t v, uint32_t tag_floor) { return v >= tag_floor ? (v & 0xfffu) : 0u; }
-
-// does the keypoint at (scored row rr, tile column j) survive?
-template <int MODE, int SR>
-FDF_HD bool nms_keep(int rr, int j, const uint16_t *plane, const ChunkGeo &g, uint32_t floor) {
-    const int y = g.ys0 + rr, x = g.xt0 + j;
-    if (rr < 1 || rr > SR - 2 || x < g.x0 || x >= g.x1 || y >= g.h - 4) return false;
-    const uint16_t *pp = plane + rr * kPlaneW + j - kPlaneLead;
-    const uint32_t s = live_score(pp[0], floor);
-    if (s == 0u) return false;
-    return s > live_score(pp[-kPlaneW - 1], floor) && s > live_score(pp[-kPlaneW], floor) &&
-           s > live_score(pp[-kPlaneW + 1], floor) && s > live_score(pp[-1], floor) &&
-           s > live_score(pp[1], floor) && s > live_score(pp[kPlaneW - 1], floor) &&
-           s > live_score(pp[kPlaneW], floor) && s > live_score(pp[kPlaneW + 1], floor);
+// A plane entry belongs to the current chunk iff it carries the current tag; anything else is stale = "no
+// keypoint".  Tags only grow between two clears of the plane, so v - (tag << 12) is the score for a current
+// entry and negative for a stale one: one add-and-clamp per cell.
+FDF_HD uint32_t live_score(uint32_t v, uint32_t tag_floor) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__viaddmax_s32((int)v, -(int)tag_floor, 0);
+#else
+    return (uint32_t)max((int)v - (int)tag_floor, 0);
+#endif
 }
 
-constexpr uint32_t kSurvivor = 0x8000u;  // keypoint-list entries use 14 bits; bit 15 marks "emit this one"
+FDF_HD uint32_t max3u(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    return __vimax3_u32(a, b, c);
+#else
+    return max(a, max(b, c));
+#endif
+}
 
-// The chunk's keypoint list: survivors are marked in place and counted.  (Off mode never calls this: every
-// list entry is emitted.)
+// may the keypoint at (scored row rr, tile column j) be emitted by this chunk at all?
 template <int MODE, int SR>
-FDF_HD void nms_list(int tid, uint32_t kn, uint16_t *klist, const uint16_t *plane, uint32_t *scount,
-                     const ChunkGeo &g, uint32_t tag) {
-    for (uint32_t i = (uint32_t)tid; i < kn; i += (uint32_t)kComputeThreads) {
-        const uint32_t ent = klist[i];
-        if (nms_keep<MODE, SR>((int)(ent >> 8), (int)(ent & 0xffu), plane, g, tag << 12)) {
-            klist[i] = (uint16_t)(ent | kSurvivor);
-            atomic_add_u32(scount, 1u);
-        }
-    }
+FDF_HD bool nms_emits(int rr, int j, const ChunkGeo &g) {
+    const int y = g.ys0 + rr, x = g.xt0 + j;
+    if (MODE == NMS_OFF) return x >= g.x0 && x < g.x1;  // (rows and the image border were settled by the filter)
+    return !(rr < 1 || rr > SR - 2 || x < g.x0 || x >= g.x1 || y >= g.h - 4);
+}
+
+// is the score at plane cell pp a strict maximum of its 3x3 neighbourhood?  (branch-free; pp must have a full
+// neighbourhood inside the plane)
+FDF_HD bool nms_is_max(const uint16_t *pp, uint32_t floor) {
+    const uint32_t s = live_score(pp[0], floor);
+    const uint32_t a = max3u(live_score(pp[-kPlaneW - 1], floor), live_score(pp[-kPlaneW], floor),
+                             live_score(pp[-kPlaneW + 1], floor));
+    const uint32_t b = max3u(live_score(pp[kPlaneW - 1], floor), live_score(pp[kPlaneW], floor),
+                             live_score(pp[kPlaneW + 1], floor));
+    const uint32_t c = max3u(live_score(pp[-1], floor), live_score(pp[1], floor), a);
+    return s > max(b, c);
 }
 
 // staged form of a keypoint: row inside the strip's emitted rows << 16 | image column
@@ -249,15 +286,50 @@ FDF_HD uint32_t staged_entry(int rr, int j, const ChunkGeo &g) {
     return (uint32_t)((rr - (MODE == NMS_OFF ? 0 : 1)) << 16) | (uint32_t)(g.xt0 + j);
 }
 
-// Dense fallback (queue overflow: very dense content), NMS modes: every cell of the plane.  Pass 0 counts the
+// The chunk's keypoint list (the rewritten candidate queue): every keypoint that survives the NMS (Off mode: every
+// keypoint) is written to the staging buffer at base + slot, slots handed out through *scount.
+template <int MODE, int SR, int U>
+FDF_HD void emit_list(int tid, int nthreads, uint32_t qn, const uint16_t *klist, const uint16_t *plane,
+                      uint32_t *scount, unsigned long long base, unsigned long long cap, uint32_t *staging,
+                      const ChunkGeo &g, uint32_t tag) {
+    for (uint32_t i0 = (uint32_t)tid; i0 < qn; i0 += (uint32_t)(U * nthreads)) {
+        uint32_t ent[U];
+        bool keep[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t i = i0 + (uint32_t)(u * nthreads);
+            ent[u] = i < qn ? klist[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int rr = (int)((ent[u] >> 8) & 0x3fu), j = (int)(ent[u] & 0xffu);
+            const bool in = ent[u] != 0u && nms_emits<MODE, SR>(rr, j, g);
+            // (an entry that cannot be emitted is looked up at a harmless cell with a full neighbourhood)
+            keep[u] = in;
+            if (MODE != NMS_OFF)
+                keep[u] = nms_is_max(plane + (in ? rr * kPlaneW + j - kPlaneLead : kPlaneW + 1), tag << 12) && in;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (keep[u]) {
+                const unsigned long long o = base + atomic_add_u32(scount, 1u);
+                if (o < cap)
+                    staging[o] = staged_entry<MODE>((int)((ent[u] >> 8) & 0x3fu), (int)(ent[u] & 0xffu), g);
+            }
+        }
+    }
+}
+
+// Dense fallback (queue overflow: very dense content): every cell of the plane.  Pass 0 counts the
 // survivors, pass 1 writes them to staging[base + slot] with slots handed out through *slot_counter.
 template <int MODE, int SR>
-FDF_HD void nms_dense(int tid, int pass, const uint16_t *plane, uint32_t *counter, unsigned long long base,
+FDF_HD void nms_dense(int tid, int nthreads, int pass, const uint16_t *plane, uint32_t *counter, unsigned long long base,
                       unsigned long long cap, uint32_t *staging, const ChunkGeo &g, uint32_t tag) {
-    for (int i = tid; i < SR * kPlaneW; i += kComputeThreads) {
+    for (int i = tid; i < SR * kPlaneW; i += nthreads) {
         if (plane[i] < (tag << 12)) continue;
         const int rr = i / kPlaneW, j = i % kPlaneW + kPlaneLead;
-        if (!nms_keep<MODE, SR>(rr, j, plane, g, tag << 12)) continue;
+        if (!nms_emits<MODE, SR>(rr, j, g)) continue;
+        if (MODE != NMS_OFF && !nms_is_max(plane + i, tag << 12)) continue;
         const uint32_t slot = atomic_add_u32(counter, 1u);
         if (pass == 1 && base + slot < cap) staging[base + slot] = staged_entry<MODE>(rr, j, g);
     }

@@ -17,10 +17,10 @@ namespace {
 
 using namespace fdf;
 
-// Mirrors the kernel's per-chunk schedule: phase A warp by warp, barrier, phase B (or the row-group fallback
-// when the candidate queue overflowed), barrier, NMS pass over the chunk's keypoint list (the kernel runs it next
-// to the following chunk's phase A), then the chunk's surviving keypoints go to the staging buffer as one
-// unordered run.  At the end of a strip the gather kernel's part follows: runs -> bit plane -> row-major points.
+// Mirrors what the kernel does with one chunk: phase A by the filter warps, phase B by the test threads (or the
+// row-group fallback when the candidate queue overflowed), NMS pass over the chunk's keypoint list (the rewritten
+// candidate queue), then the chunk's surviving keypoints go to the staging buffer as one unordered run.  At the
+// end of a strip the gather kernel's part follows: runs -> bit plane -> row-major points.
 template <int MODE, int SR>
 int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2 *out, size_t cap, int *fallbacks) {
     constexpr int OUT_R = out_rows(MODE, SR);
@@ -31,11 +31,11 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
     const int NC = chunks_per_row(w);
     const int WW = (w + 31) / 32;
     alignas(16) static uint8_t tile[tile_rows(64) * kTileW];
-    std::vector<uint16_t> plane((size_t)SR * kPlaneW), queue(kQueueCap), klists(2 * kQueueCap), wq(kWarpQueueCap);
+    std::vector<uint16_t> plane((size_t)SR * kPlaneW), queue(kQueueCap), wq(kWarpQueueCap);
     alignas(16) uint32_t vtab[3][kVtabWords];  // validity tables: first / middle / last chunk of a row
     for (int v = 0; v < 3; v++)
         for (int i = 0; i < kVtabWords; i++) vtab[v][i] = valid_word<MODE>(w, vtab_chunk(v, NC), i);
-    uint32_t qcount[2] = {0, 0}, kcount[2] = {0, 0}, scount = 0;
+    uint32_t qcount = 0;
     std::vector<uint32_t> bits((size_t)OUT_R * WW), staged;
     const uint32_t kbias = filter_kbias((uint32_t)t);
     unsigned long long total = 0;
@@ -43,7 +43,6 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
     for (int strip = 0; strip < S; strip++) {
         staged.clear();
         for (int c = 0; c < NC; c++, gc++) {
-            const uint32_t cp = gc & 1u;
             const ChunkGeo g = make_geo<MODE>(w, h, strip, c, SR);
             const int ty0 = g.ys0 - 3;
             if (g.xt0 % 16 != 0) return -16;  // TMA: innermost box start must be 16-byte aligned
@@ -53,58 +52,44 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
                     tile[r * kTileW + j] = (y >= 0 && y < h && x >= 0 && x < w) ? img[(size_t)y * pitch + x] : 0;
                 }
             const uint32_t *vt = vtab[vtab_variant(c, NC)];
-            for (int warp = 0; warp < kComputeWarps; warp++)
-                phase_a_warp<MODE, SR>(warp, -1, tile, wq.data(), vt, queue.data(), &qcount[cp], g, kbias, 0, SR);
-            const uint32_t qn = qcount[cp];
-            qcount[cp ^ 1u] = 0;
-            kcount[cp ^ 1u] = 0;
-            if (MODE != NMS_OFF && tag == 1u && gc != 0u) std::fill(plane.begin(), plane.end(), (uint16_t)0);
-            uint16_t *kl = klists.data() + cp * kQueueCap;
+            qcount = 0;
+            for (int warp = 0; warp < kFilterWarps; warp++)
+                phase_a_warp<MODE, SR, kFilterWarps>(warp, -1, tile, wq.data(), vt, queue.data(), &qcount, g, kbias, 0, SR);
+            const uint32_t qn = qcount;
+            if (tag == 1u && gc != 0u) std::fill(plane.begin(), plane.end(), (uint16_t)0);
             if (qn <= (uint32_t)kQueueCap) {
-                for (int tid = 0; tid < kComputeThreads; tid++)
-                    phase_b<MODE, SR>(tid, qn, tile, queue.data(), plane.data(), kl, &kcount[cp], t, n, tag);
-                const uint32_t kn = kcount[cp];
-                if (kn > (uint32_t)kQueueCap) return -19;
-                if (MODE != NMS_OFF) {
-                    scount = 0;
-                    for (int tid = 0; tid < kComputeThreads; tid++)
-                        nms_list<MODE, SR>(tid, kn, kl, plane.data(), &scount, g, tag);
-                }
-                uint32_t taken = 0;
-                for (uint32_t i = 0; i < kn; i++)
-                    if (MODE == NMS_OFF || (kl[i] & kSurvivor)) {
-                        staged.push_back(staged_entry<MODE>((kl[i] >> 8) & 0x3f, kl[i] & 0xff, g));
-                        taken++;
-                    }
-                if (MODE != NMS_OFF && taken != scount) return -20;
+                for (int tid = 0; tid < kTestThreads; tid++)
+                    phase_b<MODE, SR, kTestUnroll>(tid, kTestThreads, qn, tile, queue.data(), plane.data(), t, n, tag);
+                std::vector<uint32_t> run(qn + 1);
+                uint32_t scount = 0;
+                for (int tid = 0; tid < kTestThreads; tid++)
+                    emit_list<MODE, SR, kTestUnroll>(tid, kTestThreads, qn, queue.data(), plane.data(), &scount, 0ull, qn, run.data(), g, tag);
+                if (scount > qn) return -20;
+                staged.insert(staged.end(), run.begin(), run.begin() + scount);
             } else {
                 if (fallbacks) fallbacks[0]++;
                 for (int lo = 0; lo < SR; lo += kGroupRows) {
-                    qcount[cp] = 0;
-                    if (MODE == NMS_OFF) kcount[cp] = 0;
-                    for (int warp = 0; warp < kComputeWarps; warp++)
-                        phase_a_warp<MODE, SR>(warp, -1, tile, wq.data(), vt, queue.data(), &qcount[cp], g, kbias, lo,
-                                               lo + kGroupRows);
-                    if (qcount[cp] > (uint32_t)kQueueCap) return -18;
-                    for (int tid = 0; tid < kComputeThreads; tid++)
-                        phase_b<MODE, SR>(tid, qcount[cp], tile, queue.data(), plane.data(), kl, &kcount[cp], t, n, tag);
-                    if (MODE == NMS_OFF)
-                        for (uint32_t i = 0; i < kcount[cp]; i++) staged.push_back(staged_entry<MODE>(kl[i] >> 8, kl[i] & 0xff, g));
+                    qcount = 0;
+                    for (int warp = 0; warp < kTestWarps; warp++)
+                        phase_a_warp<MODE, SR, kTestWarps>(warp, -1, tile, wq.data(), vt, queue.data(), &qcount, g, kbias, lo,
+                                                           lo + kGroupRows);
+                    if (qcount > (uint32_t)kQueueCap) return -18;
+                    for (int tid = 0; tid < kTestThreads; tid++)
+                        phase_b<MODE, SR, kTestUnroll>(tid, kTestThreads, qcount, tile, queue.data(), plane.data(), t, n, tag);
                 }
-                if (MODE != NMS_OFF) {
+                {
                     if (fallbacks) fallbacks[1]++;
                     uint32_t counter = 0;
-                    for (int tid = 0; tid < kComputeThreads; tid++)
-                        nms_dense<MODE, SR>(tid, 0, plane.data(), &counter, 0ull, 0ull, nullptr, g, tag);
+                    for (int tid = 0; tid < kTestThreads; tid++)
+                        nms_dense<MODE, SR>(tid, kTestThreads, 0, plane.data(), &counter, 0ull, 0ull, nullptr, g, tag);
                     std::vector<uint32_t> run(counter + 1);
                     const uint32_t kn = counter;
                     counter = 0;
-                    for (int tid = 0; tid < kComputeThreads; tid++)
-                        nms_dense<MODE, SR>(tid, 1, plane.data(), &counter, 0ull, kn, run.data(), g, tag);
+                    for (int tid = 0; tid < kTestThreads; tid++)
+                        nms_dense<MODE, SR>(tid, kTestThreads, 1, plane.data(), &counter, 0ull, kn, run.data(), g, tag);
                     if (counter != kn) return -21;
                     staged.insert(staged.end(), run.begin(), run.begin() + kn);
                 }
-                kcount[cp] = 0;
             }
             tag = tag == (uint32_t)kTagPeriod ? 1u : tag + 1u;
         }

@@ -5,8 +5,9 @@ import subprocess
 import sys
 
 
-def main(rep, top=60):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+def main(rep, top=60, kernel=None):
+    kern = ["--kernel-name", "regex:" + kernel] if kernel else []
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + kern,
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     cur_file, hdr = None, None
@@ -38,4 +39,4 @@ def main(rep, top=60):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 60)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 60, sys.argv[3] if len(sys.argv) > 3 else None)

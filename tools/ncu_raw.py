@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Key raw metrics of one ncu report (read here, no GPU needed)."""
 import csv, subprocess, sys
-out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+kern = ["--kernel-name", "regex:" + sys.argv[2]] if len(sys.argv) > 2 else []
+out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"] + kern, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'launch__registers_per_thread',
