@@ -44,7 +44,7 @@ struct DeviceBuffer {
 
 #ifdef FDF_PHASE_CLOCKS
 namespace fdf {
-cudaError_t read_phase_clocks(unsigned long long out[128]);
+cudaError_t read_phase_clocks(unsigned long long out[256]);
 }
 #endif
 
@@ -99,7 +99,7 @@ int choose_scored_rows(uint32_t n_frames, uint32_t h, int mode) {
     const long long rows = (long long)h - 2 * fdf::first_out_row(mode);
     if (const char *force = getenv("FDF_FORCE_SR")) {  // tuning knob for experiments: 32 or 64
         const int v = atoi(force);
-        if (v == 32 || v == 64) return v;
+        if (v == 32 || v == 48 || v == 64) return v;
     }
     const long long strips64 = (rows + fdf::out_rows(mode, 64) - 1) / fdf::out_rows(mode, 64);
     return (long long)n_frames * strips64 >= 2 * 148 ? 64 : 32;
@@ -390,7 +390,7 @@ fdf_status fdf_detect(fdf_ctx *ctx, const uint8_t *img, uint32_t w, uint32_t h, 
 
 #ifdef FDF_PHASE_CLOCKS
 // (debug builds only, not part of include/fdf.h) cycles per kernel phase since the last call
-fdf_status fdf_debug_phase_clocks(fdf_ctx *ctx, uint64_t out[128]) {
+fdf_status fdf_debug_phase_clocks(fdf_ctx *ctx, uint64_t out[256]) {
     if (!ctx || !out) return FDF_ERR_INVALID_ARGUMENT;
     FDF_CUDA(ctx, cudaDeviceSynchronize());
     FDF_CUDA(ctx, fdf::read_phase_clocks(reinterpret_cast<unsigned long long *>(out)));

@@ -43,6 +43,7 @@ constexpr unsigned long long kStatusAggregate = 1ull << 62;
 constexpr unsigned long long kStatusPrefix = 2ull << 62;
 constexpr unsigned long long kStatusValueMask = (1ull << 62) - 1ull;
 constexpr uint32_t kSpinLimit = 1u << 22;
+constexpr uint32_t kWaitHintNs = 100000u;  // mbarrier.try_wait suspend-time hint
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -64,16 +65,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// try_wait suspends the thread (no issue slots used) until the phase completes or the time hint (ns) runs out
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(kWaitHintNs)
         : "memory");
     return ok != 0;
 }
@@ -85,7 +87,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32
             atomicOr(flags, kFlagTmaTimeout);
             break;
         }
-        __nanosleep(64);  // the other warp group is busy: leave it the issue slots
     }
 }
 
@@ -112,6 +113,9 @@ __device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned l
 }
 
 // ---- shared-memory carve-up ------------------------------------------------------------------
+#ifndef FDF_ABLATE
+#define FDF_ABLATE 0  // (experiments only: skip phase B = 1, the NMS pass = 2, phase A = 4; results are wrong)
+#endif
 constexpr int kQueueBufs = 3;  // candidate queues in flight: being filled, being tested, being staged
   // queue entries a test thread works on at once (interleaved dependency chains)
 
@@ -133,7 +137,9 @@ struct Layout {
     static_assert(tile_bytes % 128 == 0, "TMA destination must stay 128-byte aligned");
     static_assert(plane_bytes % 16 == 0 && plane_off % 16 == 0, "the plane is cleared with 128-bit stores");
     static_assert(SR % (2 * kFilterWarps) == 0 && SR <= 64, "filter warps take row pairs; queue entries hold 6 row bits");
-    static_assert(kTestWarps * kWarpQueueCap * 2 <= kQueueCap * 2, "the dense fallback borrows a queue buffer for its warp queues");
+    static_assert(kFallbackWarps * kWarpQueueCap * 2 <= kQueueCap * 2 && kFallbackWarps <= kTestWarps,
+                  "the dense fallback borrows a queue buffer for its warp queues");
+    static_assert(SR % (2 * kFallbackWarps) == 0, "fallback filter warps take row pairs");
     static_assert(vtab_off % 16 == 0, "the validity tables are read with 128-bit loads");
     static_assert(kGroupRows * kTileW <= kQueueCap, "a row group must always fit the candidate queue");
     static_assert(SR % kGroupRows == 0, "the dense fallback walks whole row groups");
@@ -181,7 +187,7 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long *statu
 // Optional phase clocks (tools/phase_clocks.py builds the library with -DFDF_PHASE_CLOCKS): cycles per phase, summed over
 // the warps of a group (lane 0 of each) and over all CTAs.
 #ifdef FDF_PHASE_CLOCKS
-__device__ unsigned long long g_phase_clocks[8 * 16];  // [warp][slot]
+__device__ unsigned long long g_phase_clocks[16 * 16];  // [warp][slot]
 #define FDF_CLK_BEGIN                 \
     long long clk_prev = clock64();   \
     long long clk_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -241,7 +247,7 @@ __device__ __forceinline__ unsigned long long open_run(unsigned long long *s_blo
 }
 
 template <int MODE, int SR>
-__global__ void __launch_bounds__(kThreads, SR >= 64 ? 3 : 4)
+__global__ void __launch_bounds__(kThreads, SR >= 48 ? 3 : 4)
 fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p) {
     using L = Layout<MODE, SR>;
     constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;  // score halo (rows and columns) needed by the 3x3 NMS
@@ -297,6 +303,9 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         const uint32_t frame = item / p.strips_per_frame;
         const uint32_t strip = item - frame * p.strips_per_frame;
         const int ty0 = first_out_row(MODE) + (int)strip * OUT_R - HS - 3;  // image row of tile row 0
+#ifdef FDF_PHASE_CLOCKS
+        reinterpret_cast<volatile long long *>(smem + L::misc_off + 96)[stage] = clock64();
+#endif
         mbar_expect_tx(&full_bar[stage], (uint32_t)L::tile_bytes);
         tma_load_3d(tiles + stage * L::tile_bytes, &tmap, c * kChunkW - kTileLead, ty0, (int)frame, &full_bar[stage]);
     };
@@ -343,11 +352,25 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
             for (int c = 0; c < NC; c++, gc++) {
                 const uint32_t stage = gc & 1u;
                 const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
+#ifdef FDF_PHASE_CLOCKS
+                uint32_t landed;
+                asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                             : "=r"(landed) : "r"(smem_u32(&full_bar[stage])), "r"((gc >> 1) & 1u) : "memory");
+                const bool had_to_wait = landed == 0u;
+#endif
                 mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags);  // (also: queue qb is free again)
+#ifdef FDF_PHASE_CLOCKS
+                if (had_to_wait) {
+                    clk_acc[8] += clock64() - reinterpret_cast<volatile long long *>(smem + L::misc_off + 96)[stage];
+                    clk_acc[9] += 1;
+                }
+#endif
                 FDF_CLK(0)
+#if !(FDF_ABLATE & 4)
                 phase_a_warp<MODE, SR, kFilterWarps>(warp, lane, tiles + stage * L::tile_bytes, wq,
                                                      vtabs + vtab_variant(c, NC) * kVtabWords, queues + qb * kQueueCap,
                                                      &qcount[qb], g, kbias, 0, SR);
+#endif
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&q_full[qb]);
                 FDF_CLK(1)
@@ -398,15 +421,19 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
             FDF_CLK(4)
             const uint32_t qn = qcount[qb];
             if (qn <= (uint32_t)kQueueCap) {
+#if !(FDF_ABLATE & 1)
                 phase_b<MODE, SR, kTestUnroll>(ttid, kTestThreads, qn, tile, queue, plane, t, n, tag);
+#endif
                 FDF_CLK(5)
                 bar_test_group();  // every score of this chunk is in the plane; tile[stage] is free again
                 if (t0) {
                     qcount[qb] = 0u;
                     request_tile(c + ahead, gc + (uint32_t)ahead, it);
                 }
-                emit_list<MODE, SR, kTestUnroll>(ttid, kTestThreads, qn, queue, plane, scount, *s_base, p.staging_cap,
+#if !(FDF_ABLATE & 2)
+                emit_list<MODE, SR, kEmitUnroll>(ttid, kTestThreads, qn, queue, plane, scount, *s_base, p.staging_cap,
                                                  p.staging, g, tag);
+#endif
                 FDF_CLK(7)
                 bar_test_group();  // the run is complete; queue qb is free
                 if (t0) {
@@ -427,8 +454,9 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                     bar_test_group();
                     if (t0) qcount[qb] = 0u;
                     bar_test_group();
-                    phase_a_warp<MODE, SR, kTestWarps>(twarp, lane, tile, wq, vtab, queue, &qcount[qb], g, kbias, lo,
-                                                       lo + kGroupRows);
+                    if (twarp < kFallbackWarps)
+                        phase_a_warp<MODE, SR, kFallbackWarps>(twarp, lane, tile, wq, vtab, queue, &qcount[qb], g, kbias,
+                                                               lo, lo + kGroupRows);
                     bar_test_group();
                     phase_b<MODE, SR, kTestUnroll>(ttid, kTestThreads, qcount[qb], tile, queue, plane, t, n, tag);
                 }
@@ -534,9 +562,9 @@ __global__ void __launch_bounds__(kScanThreads) fdf_scan_kernel(const DetectPara
 // prefix sum turns the counts into offsets, and the same walk expands the bits to (x, y) points at the strip's
 // final position (fast_simd.rs:550, 596-613: the output is row-major).  Every word that is read is cleared, so
 // the bitmap is zeroed only once per CTA and the work per strip is proportional to its keypoints.
-__global__ void __launch_bounds__(kThreads) fdf_gather_kernel(const DetectParams p, uint32_t n_items) {
+__global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const DetectParams p, uint32_t n_items) {
     extern __shared__ __align__(16) uint32_t gsm[];
-    __shared__ uint32_t warp_sums[kThreads / 32];
+    __shared__ uint32_t warp_sums[kGatherThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mode = (int)p.mode, sr = (int)p.sr;
     const int WW = (int)p.words_per_row, NC = (int)p.chunks_per_strip;
@@ -544,7 +572,7 @@ __global__ void __launch_bounds__(kThreads) fdf_gather_kernel(const DetectParams
     const int nsum = (nwords + 31) / 32;  // level-2 words
     const int rpc = 1;
     uint32_t *bits = gsm, *summary = gsm + nsum * 32;
-    for (int i = tid; i < nsum * 33; i += kThreads) gsm[i] = 0u;
+    for (int i = tid; i < nsum * 33; i += kGatherThreads) gsm[i] = 0u;
     __syncthreads();
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t total = p.item_count[item];
@@ -552,7 +580,7 @@ __global__ void __launch_bounds__(kThreads) fdf_gather_kernel(const DetectParams
         const uint32_t strip = item % p.strips_per_frame;
         const uint32_t y0 = (uint32_t)(first_out_row(mode) + (int)strip * out_rows(mode, sr));
         // one warp per chunk: its runs -> bits
-        for (int c = warp; c < NC; c += kThreads / 32) {
+        for (int c = warp; c < NC; c += kGatherThreads / 32) {
             const size_t slot = (size_t)item * NC + c;
             const uint32_t nr = p.run_n[slot];
             for (uint32_t r = 0; r < nr; r++) {
@@ -570,7 +598,7 @@ __global__ void __launch_bounds__(kThreads) fdf_gather_kernel(const DetectParams
         __syncthreads();
         unsigned long long o = p.item_dst[item];
         uint32_t block_off = 0u;
-        for (int t0 = 0; t0 < nsum; t0 += kThreads) {  // (one round unless the image is wider than ~8000 pixels)
+        for (int t0 = 0; t0 < nsum; t0 += kGatherThreads) {  // (one round unless the image is wider than ~8000 pixels)
             const int ts = t0 + tid;
             const uint32_t sm = ts < nsum ? summary[ts] : 0u;
             uint32_t cnt = 0u;
@@ -585,7 +613,7 @@ __global__ void __launch_bounds__(kThreads) fdf_gather_kernel(const DetectParams
             __syncthreads();
             uint32_t before = block_off, all = 0u;
 #pragma unroll
-            for (int w2 = 0; w2 < kThreads / 32; w2++) {
+            for (int w2 = 0; w2 < kGatherThreads / 32; w2++) {
                 const uint32_t ws = warp_sums[w2];
                 if (w2 < warp) before += ws;
                 all += ws;
@@ -627,10 +655,10 @@ __global__ void fdf_synth_kernel(uint8_t *frames, uint32_t n_frames, uint32_t w,
 
 #ifdef FDF_PHASE_CLOCKS
 }  // namespace
-cudaError_t read_phase_clocks(unsigned long long out[128]) {
-    cudaError_t e = cudaMemcpyFromSymbol(out, g_phase_clocks, 128 * sizeof(unsigned long long));
+cudaError_t read_phase_clocks(unsigned long long out[256]) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_phase_clocks, 256 * sizeof(unsigned long long));
     if (e != cudaSuccess) return e;
-    unsigned long long zero[128] = {0};
+    unsigned long long zero[256] = {0};
     return cudaMemcpyToSymbol(g_phase_clocks, zero, sizeof(zero));
 }
 namespace {
@@ -674,10 +702,13 @@ cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const Detec
 #define FDF_CASE(M, S) \
     if (mode == M && sr == S) return launch_t<M, S>(tmap, p, stream);
     FDF_CASE(0, 32)
+    FDF_CASE(0, 48)
     FDF_CASE(0, 64)
     FDF_CASE(1, 32)
+    FDF_CASE(1, 48)
     FDF_CASE(1, 64)
     FDF_CASE(2, 32)
+    FDF_CASE(2, 48)
     FDF_CASE(2, 64)
 #undef FDF_CASE
     return cudaErrorInvalidValue;
@@ -700,11 +731,11 @@ cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream) {
     int dev = 0, sms = 0, per_sm = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fdf_gather_kernel, kThreads, smem)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fdf_gather_kernel, kGatherThreads, smem)) != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     unsigned long long grid = (unsigned long long)sms * (unsigned)per_sm;
     if (grid > items) grid = items;
-    fdf_gather_kernel<<<(unsigned)grid, kThreads, smem, stream>>>(p, (uint32_t)items);
+    fdf_gather_kernel<<<(unsigned)grid, kGatherThreads, smem, stream>>>(p, (uint32_t)items);
     return cudaGetLastError();
 }
 

@@ -9,9 +9,16 @@ namespace fdf {
 // Geometry shared by host and device.  A frame is cut into STRIPS of full-width rows; a CTA
 // takes one strip at a time (atomic ticket) and walks it left to right in CHUNKS.  For every chunk a 256-byte-wide tile
 // (chunk + halo) is staged into shared memory by one TMA 3-D tiled load.
-constexpr int kComputeWarps = 8;
-constexpr int kComputeThreads = kComputeWarps * 32;
-constexpr int kThreads = kComputeThreads;              // threads per CTA
+#ifndef FDF_TEST_WARPS
+#define FDF_TEST_WARPS 6
+#endif
+constexpr int kFilterWarps = 4;     // warps 0 .. 3 run phase A (dense filter), the others everything per candidate
+constexpr int kTestWarps = FDF_TEST_WARPS;
+constexpr int kComputeWarps = kFilterWarps + kTestWarps;
+constexpr int kThreads = kComputeWarps * 32;           // threads per CTA of the detection kernel
+constexpr int kTestThreads = kTestWarps * 32;
+constexpr int kFallbackWarps = 4;   // test warps that redo the filter in the dense fallback
+constexpr int kGatherThreads = 256; // threads per CTA of the gather kernel
 constexpr int kTileW = 256;     // tile width in bytes = TMA box inner extent (the maximum)
 constexpr int kChunkW = 240;    // output columns per chunk (the last chunk of a row may take one more)
 constexpr int kTileLead = 16;   // chunk c's tile starts at image column c*kChunkW - kTileLead: TMA needs the
@@ -29,12 +36,13 @@ constexpr int kQueueCap = 1024; // candidate queue entries per chunk (typical fi
 constexpr int kGroupRows = 4;   // fallback for dense content: filter kGroupRows x 256 <= kQueueCap centres at a time
 constexpr int kStageBlock = 4096;   // staging entries a CTA reserves at a time from the global cursor
 constexpr unsigned long long kStageSlack = 1024ull * kStageBlock;  // what partly used blocks can waste (<= 1024 CTAs)
-constexpr int kFilterWarps = 4;     // warps 0 .. 3 run phase A (dense filter), warps 4 .. 7 everything per candidate
-constexpr int kTestWarps = kComputeWarps - kFilterWarps;
-constexpr int kTestThreads = kTestWarps * 32;
 #ifndef FDF_TEST_UNROLL
 #define FDF_TEST_UNROLL 1
 #endif
+#ifndef FDF_EMIT_UNROLL
+#define FDF_EMIT_UNROLL 1
+#endif
+constexpr int kEmitUnroll = FDF_EMIT_UNROLL;  // same for the (short) NMS pass
 constexpr int kTestUnroll = FDF_TEST_UNROLL;  // queue entries a test thread works on at once (measured: 1 is best;
                                               // 2 / 3 interleave the dependency chains but cost registers and issue slots)
 constexpr int kWarpQueueCap = 256;  // 16-pixel groups one warp can pass from filter stage 1 to stage 2 per chunk

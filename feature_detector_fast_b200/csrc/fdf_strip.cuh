@@ -110,10 +110,41 @@ FDF_HD RowRange live_rows(const ChunkGeo &g, int row_lo, int row_hi) {
     return r;
 }
 
-// stage 1 for one lane and row: non-zero iff the group needs stage 2
-FDF_HD uint32_t stage1_lane(const uint8_t *tile, int rr, int q, uint32_t kbias) {
-    const uint8_t *rowp = tile + (rr + 3) * kTileW + q * 16;
-    return vertical_any(load16(rowp), load16(rowp - 3 * kTileW), load16(rowp + 3 * kTileW), kbias);
+// Stage 1 for one lane: the 16-pixel group q of BH consecutive scored rows rr0 .. rr0+BH-1.  Returns bit i set iff
+// row rr0 + i has a centre whose north or south ring pixel differs from it by more than t.
+// The rows are walked top to bottom with everything kept in registers: every tile row is loaded once (LDS.128)
+// and the vertical difference D(y) = |p(y) - p(y-3)| is computed once and used twice (as the north difference of
+// centre y and the south difference of centre y - 3).
+template <int BH>
+FDF_HD uint32_t stage1_band(const uint8_t *tile, int rr0, int q, uint32_t kbias) {
+    const uint8_t *p = tile + rr0 * kTileW + q * 16;  // tile row rr0 is the north ring row of scored row rr0
+    Px16 row[BH + 6], d[BH + 3];
+    uint32_t anymask = 0u;
+#pragma unroll
+    for (int i = 0; i < BH + 6; i++) {
+        row[i] = load16(p + i * kTileW);
+        if (i >= 3) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) d[i - 3].w[k] = absdiff4(row[i].w[k], row[i - 3].w[k]);
+        }
+        if (i >= 6) {  // centre = tile row i - 3: north difference d[i - 6], south difference d[i - 3]
+            uint32_t o = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; k++) o |= exceeds4(d[i - 6].w[k] | d[i - 3].w[k], kbias);
+            if ((o & 0x80808080u) != 0u) anymask |= 1u << (i - 6);
+        }
+    }
+    return anymask;
+}
+
+// bit i set iff scored row rr0 + i may hold a centre at all (fast_simd.rs:342: image rows 3 .. h-4) and lies in
+// the row range the caller asks for
+FDF_HD uint32_t live_mask(const ChunkGeo &g, int rr0, int bh, int row_lo, int row_hi) {
+    const RowRange live = live_rows(g, row_lo, row_hi);
+    uint32_t m = 0u;
+    for (int i = 0; i < bh; i++)
+        if (rr0 + i >= live.lo && rr0 + i < live.hi) m |= 1u << i;
+    return m;
 }
 
 // stage 2 for one queued group: candidate mask, then one queue entry per surviving centre.  When the queue is
@@ -148,40 +179,38 @@ FDF_HD void stage2_entry(uint32_t e, const uint8_t *tile, const uint32_t *vtab, 
 // One warp's phase A; NW warps share a chunk.  On the device the 32 lanes run it together (lane = threadIdx.x & 31);
 // on the host the emulator calls it once per warp and the lane loops below run sequentially, in the same order as
 // the ballot ranks.  wq is the warp's private queue (kWarpQueueCap entries).
-// Lane l of warp v handles 16-pixel group q = l & 15 of scored rows 2 * v + (l >> 4) + 2 * NW * it.
+// Lane l of warp v handles 16-pixel group q = l & 15 of the BH = SR / (2 NW) scored rows starting at
+// (2 v + (l >> 4)) * BH.
 template <int MODE, int SR, int NW>
 FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint16_t *wq, const uint32_t *vtab,
                          uint16_t *queue, uint32_t *qcount, const ChunkGeo &g, uint32_t kbias, int row_lo,
                          int row_hi) {
-    constexpr int IT = SR / (2 * NW);
-    static_assert(IT * 32 <= kWarpQueueCap, "a warp queue must hold every group stage 1 looks at");
-    const RowRange live = live_rows(g, row_lo, row_hi);
+    constexpr int BH = SR / (2 * NW);
+    static_assert(BH * 32 <= kWarpQueueCap, "a warp queue must hold every group stage 1 looks at");
     uint32_t n = 0u;  // entries in wq (warp-uniform)
 #if defined(__CUDA_ARCH__)
     const int lane = lane_or_minus1;
-    const int q = lane & 15, r0 = 2 * warp + (lane >> 4);
+    const int q = lane & 15, rr0 = (2 * warp + (lane >> 4)) * BH;
     const uint32_t lt = (1u << lane) - 1u;
-    const uint8_t *lanep = tile + r0 * kTileW + q * 16;
-    uint32_t ent = (uint32_t)((r0 << 4) | q);
+    const uint32_t need = stage1_band<BH>(tile, rr0, q, kbias) & live_mask(g, rr0, BH, row_lo, row_hi);
+    const uint32_t ent = (uint32_t)((rr0 << 4) | q);
 #pragma unroll
-    for (int it = 0; it < IT; it++) {
-        const int rr = r0 + 2 * NW * it;
-        uint32_t any = stage1_lane(lanep + 2 * NW * it * kTileW, 0, 0, kbias);
-        if (rr < live.lo || rr >= live.hi) any = 0u;
-        const uint32_t b = __ballot_sync(0xffffffffu, any != 0u);
-        if (any != 0u) wq[n + (uint32_t)__popc(b & lt)] = (uint16_t)(ent + (uint32_t)(2 * NW * it << 4));
+    for (int i = 0; i < BH; i++) {
+        const bool mine = (need >> i) & 1u;
+        const uint32_t b = __ballot_sync(0xffffffffu, mine);
+        if (mine) wq[n + (uint32_t)__popc(b & lt)] = (uint16_t)(ent + (uint32_t)(i << 4));
         n += (uint32_t)__popc(b);
     }
     __syncwarp();
     for (uint32_t i = (uint32_t)lane; i < n; i += 32u) stage2_entry(wq[i], tile, vtab, kbias, queue, qcount);
 #else
     (void)lane_or_minus1;
-    for (int it = 0; it < IT; it++)
-        for (int lane = 0; lane < 32; lane++) {
-            const int q = lane & 15, rr = 2 * warp + (lane >> 4) + 2 * NW * it;
-            if (rr < live.lo || rr >= live.hi) continue;
-            if (stage1_lane(tile, rr, q, kbias) != 0u) wq[n++] = (uint16_t)((rr << 4) | q);
-        }
+    for (int lane = 0; lane < 32; lane++) {
+        const int q = lane & 15, rr0 = (2 * warp + (lane >> 4)) * BH;
+        const uint32_t need = stage1_band<BH>(tile, rr0, q, kbias) & live_mask(g, rr0, BH, row_lo, row_hi);
+        for (int i = 0; i < BH; i++)
+            if ((need >> i) & 1u) wq[n++] = (uint16_t)(((rr0 + i) << 4) | q);
+    }
     for (uint32_t i = 0; i < n; i++) stage2_entry(wq[i], tile, vtab, kbias, queue, qcount);
 #endif
 }
@@ -343,7 +372,7 @@ struct EmitRange {
 };
 
 FDF_HD EmitRange emit_range(int warp, int nunits) {
-    const int upw = (nunits + kThreads / 32 - 1) / (kThreads / 32);
+    const int upw = (nunits + kGatherThreads / 32 - 1) / (kGatherThreads / 32);
     EmitRange r;
     r.begin = min(warp * upw, nunits);
     r.end = min(r.begin + upw, nunits);

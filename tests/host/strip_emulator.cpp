@@ -63,15 +63,15 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
                 std::vector<uint32_t> run(qn + 1);
                 uint32_t scount = 0;
                 for (int tid = 0; tid < kTestThreads; tid++)
-                    emit_list<MODE, SR, kTestUnroll>(tid, kTestThreads, qn, queue.data(), plane.data(), &scount, 0ull, qn, run.data(), g, tag);
+                    emit_list<MODE, SR, kEmitUnroll>(tid, kTestThreads, qn, queue.data(), plane.data(), &scount, 0ull, qn, run.data(), g, tag);
                 if (scount > qn) return -20;
                 staged.insert(staged.end(), run.begin(), run.begin() + scount);
             } else {
                 if (fallbacks) fallbacks[0]++;
                 for (int lo = 0; lo < SR; lo += kGroupRows) {
                     qcount = 0;
-                    for (int warp = 0; warp < kTestWarps; warp++)
-                        phase_a_warp<MODE, SR, kTestWarps>(warp, -1, tile, wq.data(), vt, queue.data(), &qcount, g, kbias, lo,
+                    for (int warp = 0; warp < kFallbackWarps; warp++)
+                        phase_a_warp<MODE, SR, kFallbackWarps>(warp, -1, tile, wq.data(), vt, queue.data(), &qcount, g, kbias, lo,
                                                            lo + kGroupRows);
                     if (qcount > (uint32_t)kQueueCap) return -18;
                     for (int tid = 0; tid < kTestThreads; tid++)
@@ -130,7 +130,7 @@ int64_t fdf_emulate_detect(const uint8_t *img, uint32_t w, uint32_t h, uint32_t 
     if (fallbacks) fallbacks[0] = fallbacks[1] = 0;  // [0] queue overflow -> row groups, [1] dense NMS
 #define CASE(M, S) \
     if (nms == M && sr == S) return emulate<M, S>(img, (int)w, (int)h, (int)pitch, t, n, o, cap, fallbacks);
-    CASE(0, 32) CASE(0, 64) CASE(1, 32) CASE(1, 64) CASE(2, 32) CASE(2, 64)
+    CASE(0, 32) CASE(0, 48) CASE(0, 64) CASE(1, 32) CASE(1, 48) CASE(1, 64) CASE(2, 32) CASE(2, 48) CASE(2, 64)
 #undef CASE
     return -1;
 }
