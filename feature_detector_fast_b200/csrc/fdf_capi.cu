@@ -214,7 +214,8 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     p.out = reinterpret_cast<uint2 *>(d_out);
     p.offsets = reinterpret_cast<unsigned long long *>(d_offsets);
 
-    if (fdf::gather_smem_bytes(mode, sr, p.words_per_row) > 200 * 1024 || w > 65535u)
+    if (fdf::gather_smem_bytes(mode, sr, p.words_per_row) > 200 * 1024 || w > 65535u ||
+        p.chunks_per_strip > (uint32_t)fdf::kGatherMaxChunks)
         return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "image too wide (%u) for the strip bit plane", w);
     const unsigned long long items = (unsigned long long)n_frames * p.strips_per_frame;
     if (items > 0x7fffffffull) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "batch too large");

@@ -30,6 +30,8 @@
 // the detection kernel cost 30 KB of shared memory per CTA, i.e. one resident CTA per SM.)
 #include "fdf_kernels.cuh"
 
+#include <cstdlib>
+
 #include "fdf_core.cuh"
 #include "fdf_strip.cuh"
 #include "fdf_synth.cuh"
@@ -561,54 +563,94 @@ __global__ void __launch_bounds__(kScanThreads) fdf_scan_kernel(const DetectPara
 // 32t .. 32t+31 (in row-major order): it counts their bits by walking the set bits of its level-2 word, a block
 // prefix sum turns the counts into offsets, and the same walk expands the bits to (x, y) points at the strip's
 // final position (fast_simd.rs:550, 596-613: the output is row-major).  Every word that is read is cleared, so
-// the bitmap is zeroed only once per CTA and the work per strip is proportional to its keypoints.
+// the bitmap is zeroed only once per CTA and the work per strip is proportional to its keypoints.  The run
+// records of the next strip are fetched while the current one is processed (the kernel is latency-bound).
+struct StripRecord {
+    unsigned long long dst;
+    uint32_t total;
+};
+
 __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const DetectParams p, uint32_t n_items) {
     extern __shared__ __align__(16) uint32_t gsm[];
     __shared__ uint32_t warp_sums[kGatherThreads / 32];
+    __shared__ unsigned long long s_run_base[kGatherMaxChunks];
+    __shared__ uint32_t s_run_count[kGatherMaxChunks];
+    __shared__ StripRecord s_rec;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mode = (int)p.mode, sr = (int)p.sr;
     const int WW = (int)p.words_per_row, NC = (int)p.chunks_per_strip;
     const int nwords = out_rows(mode, sr) * WW;
     const int nsum = (nwords + 31) / 32;  // level-2 words
-    const int rpc = 1;
     uint32_t *bits = gsm, *summary = gsm + nsum * 32;
     for (int i = tid; i < nsum * 33; i += kGatherThreads) gsm[i] = 0u;
-    __syncthreads();
+
+    // records of a strip: thread c < NC holds chunk c's run, thread NC the strip's total and destination
+    unsigned long long r_base = 0ull;
+    uint32_t r_count = 0u;
+    auto fetch = [&](uint32_t item) {
+        r_base = 0ull;
+        r_count = 0u;
+        if (item >= n_items) return;
+        if (tid < NC) {
+            const size_t slot = (size_t)item * NC + tid;
+            r_count = p.run_n[slot] != 0u ? p.run_count[slot] : 0u;
+            r_base = r_count != 0u ? p.run_base[slot] : 0ull;
+        } else if (tid == NC) {
+            r_count = p.item_count[item];
+            r_base = p.item_dst[item];
+        }
+    };
+    fetch(blockIdx.x);
+    // (row, column) of the first level-1 word of each round of this thread: fixed for the whole kernel
+    const int row_first = (32 * tid) / WW, col_first = 32 * tid - row_first * WW;
+    const int row_step = (32 * kGatherThreads) / WW, col_step = 32 * kGatherThreads - row_step * WW;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const uint32_t total = p.item_count[item];
-        if (total == 0u) continue;  // (block-uniform)
+        __syncthreads();  // the previous strip is finished with the records (and, the first time, the bitmap is zero)
+        if (tid < NC) {
+            s_run_base[tid] = r_base;
+            s_run_count[tid] = r_count;
+        } else if (tid == NC) {
+            s_rec.dst = r_base;
+            s_rec.total = r_count;
+        }
+        __syncthreads();
+        fetch(item + gridDim.x);  // in flight while this strip is processed
+        if (s_rec.total == 0u) continue;  // (block-uniform)
         const uint32_t strip = item % p.strips_per_frame;
         const uint32_t y0 = (uint32_t)(first_out_row(mode) + (int)strip * out_rows(mode, sr));
-        // one warp per chunk: its runs -> bits
+        // one warp per chunk: its run -> bits
         for (int c = warp; c < NC; c += kGatherThreads / 32) {
-            const size_t slot = (size_t)item * NC + c;
-            const uint32_t nr = p.run_n[slot];
-            for (uint32_t r = 0; r < nr; r++) {
-                const unsigned long long base = p.run_base[slot * rpc + r];
-                const uint32_t cnt = p.run_count[slot * rpc + r];
-                for (uint32_t i = (uint32_t)lane; i < cnt; i += 32u) {
-                    if (base + i >= p.staging_cap) break;
-                    const uint32_t e = p.staging[base + i];
-                    const uint32_t x = e & 0xffffu, w1 = (e >> 16) * (uint32_t)WW + (x >> 5);
-                    atomicOr(&bits[w1], 1u << (x & 31u));
-                    atomicOr(&summary[w1 >> 5], 1u << (w1 & 31u));
-                }
+            const unsigned long long base = s_run_base[c];
+            const uint32_t cnt = s_run_count[c];
+            for (uint32_t i = (uint32_t)lane; i < cnt; i += 32u) {
+                if (base + i >= p.staging_cap) break;
+                const uint32_t e = p.staging[base + i];
+                const uint32_t x = e & 0xffffu, w1 = (e >> 16) * (uint32_t)WW + (x >> 5);
+                atomicOr(&bits[w1], 1u << (x & 31u));
+                atomicOr(&summary[w1 >> 5], 1u << (w1 & 31u));
             }
         }
         __syncthreads();
-        unsigned long long o = p.item_dst[item];
+        const unsigned long long o = s_rec.dst;
         uint32_t block_off = 0u;
+        int row0 = row_first, col0 = col_first;  // of level-1 word 32 * ts
         for (int t0 = 0; t0 < nsum; t0 += kGatherThreads) {  // (one round unless the image is wider than ~8000 pixels)
             const int ts = t0 + tid;
-            const uint32_t sm = ts < nsum ? summary[ts] : 0u;
+            // the level-2 word bit-reversed: its set bits are then walked from the top (one FLO each) in ascending word order
+            const uint32_t sm = ts < nsum ? __brev(summary[ts]) : 0u;
             uint32_t cnt = 0u;
-            for (uint32_t m = sm; m != 0u; m &= m - 1u) cnt += (uint32_t)__popc(bits[32 * ts + lowest_set_bit(m)]);
+            for (uint32_t m = sm; m != 0u;) {
+                const int b = __clz(m);
+                m &= ~(0x80000000u >> b);
+                cnt += (uint32_t)__popc(bits[32 * ts + b]);
+            }
             uint32_t incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += v;
             }
+            if (t0 != 0) __syncthreads();  // warp_sums of the previous round have been read
             if (lane == 31) warp_sums[warp] = incl;
             __syncthreads();
             uint32_t before = block_off, all = 0u;
@@ -620,16 +662,26 @@ __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const Detect
             }
             block_off += all;
             unsigned long long oo = o + before + (incl - cnt);
-            for (uint32_t m = sm; m != 0u; m &= m - 1u) {
-                const int w1 = 32 * ts + lowest_set_bit(m);
-                const uint32_t word = bits[w1];
-                bits[w1] = 0u;
-                const int row = w1 / WW, col = w1 - row * WW;
+            for (uint32_t m = sm; m != 0u;) {
+                const int b = __clz(m);
+                m &= ~(0x80000000u >> b);
+                const uint32_t word = bits[32 * ts + b];
+                bits[32 * ts + b] = 0u;
+                int row = row0, col = col0 + b;
+                while (col >= WW) {
+                    col -= WW;
+                    row++;
+                }
                 emit_word(word, (uint32_t)col * 32u, y0 + (uint32_t)row, oo, p.cap, p.out);
                 oo += (unsigned long long)__popc(word);
             }
             if (sm != 0u) summary[ts] = 0u;
-            __syncthreads();  // warp_sums and the bitmap are free again
+            row0 += row_step;
+            col0 += col_step;
+            if (col0 >= WW) {
+                col0 -= WW;
+                row0++;
+            }
         }
     }
 }
@@ -678,6 +730,10 @@ cudaError_t launch_t(const CUtensorMap &tmap, const DetectParams &p, cudaStream_
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem)) != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    if (const char *lim = getenv("FDF_CTAS_PER_SM")) {  // tuning knob for experiments
+        const int v = atoi(lim);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
     unsigned long long grid = (unsigned long long)sms * (unsigned)per_sm;
     if (grid > items) grid = items;
     kern<<<(unsigned)grid, kThreads, smem, stream>>>(tmap, p);

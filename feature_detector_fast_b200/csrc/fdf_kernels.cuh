@@ -19,6 +19,7 @@ constexpr int kThreads = kComputeWarps * 32;           // threads per CTA of the
 constexpr int kTestThreads = kTestWarps * 32;
 constexpr int kFallbackWarps = 4;   // test warps that redo the filter in the dense fallback
 constexpr int kGatherThreads = 256; // threads per CTA of the gather kernel
+constexpr int kGatherMaxChunks = kGatherThreads - 1;  // chunks per strip the gather kernel holds records for
 constexpr int kTileW = 256;     // tile width in bytes = TMA box inner extent (the maximum)
 constexpr int kChunkW = 240;    // output columns per chunk (the last chunk of a row may take one more)
 constexpr int kTileLead = 16;   // chunk c's tile starts at image column c*kChunkW - kTileLead: TMA needs the

@@ -384,10 +384,7 @@ FDF_HD void emit_word(uint32_t m, uint32_t xw, uint32_t y, unsigned long long o,
     while (m) {
         const int b = lowest_set_bit(m);
         m &= m - 1u;
-        if (o < cap) {
-            out[o].x = xw + (uint32_t)b;
-            out[o].y = y;
-        }
+        if (o < cap) out[o] = make_uint2(xw + (uint32_t)b, y);
         o++;
     }
 }
