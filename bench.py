@@ -308,7 +308,7 @@ def main():
     achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": committed_traffic(), "peak_source": peak_src,
-                "kernel": "fdf_detect_kernel<MaxThreshold,32>", "kernel_ms": round(kern_ms, 4),
+                "kernel": "fdf_detect_kernel<MaxThreshold,64>", "kernel_ms": round(kern_ms, 4),
                 "other_kernels_ms": {"fdf_scan_kernel": round(scan_ms, 4), "fdf_gather_kernel": round(gather_ms, 4)},
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "read_only_frac": round(F * W * H / (kern_ms * 1e-3) / 1e9 / peak, 4)}

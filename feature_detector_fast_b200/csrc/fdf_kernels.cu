@@ -46,6 +46,7 @@ constexpr unsigned long long kStatusPrefix = 2ull << 62;
 constexpr unsigned long long kStatusValueMask = (1ull << 62) - 1ull;
 constexpr uint32_t kSpinLimit = 1u << 22;
 constexpr uint32_t kWaitHintNs = 100000u;  // mbarrier.try_wait suspend-time hint
+constexpr unsigned long long kWaitLimitNs = 4000000000ull;  // 4 s
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,11 +83,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     return ok != 0;
 }
 
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *flags) {
-    uint32_t spins = 0;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Waits for the phase; a wait that lasts longer than kWaitLimitNs can only be a bug in the pipeline: it is turned
+// into an error flag (the host reports FDF_ERR_INTERNAL) instead of a hung GPU.
+// (`abort` is a flag in shared memory: once one wait of the CTA has timed out, no other wait of the CTA blocks, so
+// that the kernel still ends quickly.)
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *flags, volatile uint32_t *abort) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = global_timer_ns();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > kSpinLimit) {  // never expected; turns a would-be hang into an error flag
+        if (*abort != 0u) break;
+        if (global_timer_ns() - t0 > kWaitLimitNs) {
             atomicOr(flags, kFlagTmaTimeout);
+            *abort = 1u;
             break;
         }
     }
@@ -269,6 +283,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     uint32_t *s_total = reinterpret_cast<uint32_t *>(smem + L::misc_off + 68);         // keypoints of the strip so far
     unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 72);
     unsigned long long *s_block = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 80);   // [2] staging block
+    volatile uint32_t *s_abort = reinterpret_cast<volatile uint32_t *>(smem + L::misc_off + 96);     // a wait timed out
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = (int)p.w, H = (int)p.h;
@@ -323,6 +338,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         fence_mbar_init();
         *scount = 0u;
         *s_total = 0u;
+        *s_abort = 0u;
         s_block[0] = s_block[1] = 0ull;
         *s_base = open_run(s_block, p);
         cur = atomicAdd(p.ticket, 1u);
@@ -360,7 +376,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                              : "=r"(landed) : "r"(smem_u32(&full_bar[stage])), "r"((gc >> 1) & 1u) : "memory");
                 const bool had_to_wait = landed == 0u;
 #endif
-                mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags);  // (also: queue qb is free again)
+                mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags, s_abort);  // (also: queue qb is free again)
 #ifdef FDF_PHASE_CLOCKS
                 if (had_to_wait) {
                     clk_acc[8] += clock64() - reinterpret_cast<volatile long long *>(smem + L::misc_off + 96)[stage];
@@ -382,7 +398,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                 }
             }
             // the next strip's ticket is published before its first tile is requested (or the end is signalled)
-            mbar_wait(&full_bar[gc & 1u], (gc >> 1) & 1u, p.flags);
+            mbar_wait(&full_bar[gc & 1u], (gc >> 1) & 1u, p.flags, s_abort);
             FDF_CLK(2)
             cur = s_ticket[(it + 1u) & 1u];
         }
@@ -418,8 +434,8 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                 clear_plane(ttid, kTestThreads);
                 bar_test_group();
             }
-            mbar_wait(&q_full[qb], qpar, p.flags);
-            mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags);  // (completed long ago: makes the tile visible here too)
+            mbar_wait(&q_full[qb], qpar, p.flags, s_abort);
+            mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags, s_abort);  // (completed long ago: makes the tile visible here too)
             FDF_CLK(4)
             const uint32_t qn = qcount[qb];
             if (qn <= (uint32_t)kQueueCap) {

@@ -29,13 +29,15 @@ def func_of(fn, ln):
         if m: return "fdf_detect_kernel"
     return None
 
-HELPERS = {"mad32", "absdiff4", "byte_perm", "popc32", "highest_set_bit", "swap16", "min_u16x2", "max_u16x2",
+HELPERS = {"max3u", "mad32", "absdiff4", "byte_perm", "popc32", "highest_set_bit", "swap16", "min_u16x2", "max_u16x2",
            "min3_u16x2", "max3_u16x2", "addrelu_s16x2", "exceeds4", "load16", "atomic_add_u32", "atomic_or_u32",
            "lowest_set_bit", "live_score", "filter_kbias", "mask_bit_to_px", "smem_u32"}
 PHASE = {"vertical_any": "A1 stage1", "stage1_lane": "A1 stage1", "candidate_mask16": "A2 stage2", "stage2_entry": "A2 stage2",
          "phase_a_warp": "A1 stage1", "ring_masks": "B test", "has_arc": "B test", "phase_b": "B test",
          "score_max_threshold": "B score", "max_of_extended": "B score", "score_sum_abs": "B score",
-         "nms_keep": "NMS", "nms_list": "NMS", "nms_dense": "NMS", "staged_entry": "stage-out", "stage_list": "stage-out",
+         "nms_emits": "NMS+stage", "nms_is_max": "NMS+stage", "emit_list": "NMS+stage", "nms_dense": "NMS+stage",
+         "staged_entry": "NMS+stage", "stage1_band": "A1 stage1", "live_mask": "A1 stage1", "live_rows": "A1 stage1",
+         "close_run": "NMS+stage", "open_run": "NMS+stage", "reserve_staging": "NMS+stage",
          "fdf_detect_kernel": "main loop", "mbar_wait": "main loop", "mbar_try_wait": "main loop", "tma_load_3d": "main loop",
          "make_geo": "main loop", "valid_word": "main loop", "vtab_variant": "main loop"}
 cur_file, hdr, line = None, None, None
