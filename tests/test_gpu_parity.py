@@ -239,3 +239,51 @@ def test_cpp_binding_and_cli_regenerate_the_shipped_renders(golden, tmp_path):
     res = subprocess.run([cli, str(pgm), str(tmp_path / "x.ppm"), "16", "8", "off"], capture_output=True, text=True,
                          timeout=120)
     assert res.returncode == 101 and "needs to exceed 9" in res.stderr
+
+
+@pytest.mark.parametrize("sr", [32, 48, 64])
+def test_forced_strip_heights(detector, oracle_mod, monkeypatch, sr):
+    """The launcher picks 32- or 64-row strips by batch size; every compiled strip height must give the same list."""
+    monkeypatch.setenv("FDF_FORCE_SR", str(sr))
+    img = oracle_mod.synth_frame(1920, 1080, seed=77, frame=sr, kind=0, amp=5)
+    for nms in (0, 1, 2):
+        assert same_points(detector.detect_array(img, _cfg(16, 9, nms)), oracle_mod.port_detect(img, 16, 9, nms)), nms
+    # heights around the strip boundaries of this strip height
+    for h in (sr - 1, sr, sr + 1, sr + 5, sr + 6, sr + 7, 2 * sr + 3):
+        small = oracle_mod.synth_frame(300, h, seed=h, frame=1, kind=1)
+        for nms in (0, 1):
+            assert same_points(detector.detect_array(small, _cfg(25, 9, nms)), oracle_mod.detect(small, 25, 9, nms)), (h, nms)
+
+
+@pytest.mark.parametrize("sr", [32, 64])
+def test_dense_and_sparse_chunks_in_one_strip(detector, oracle_mod, monkeypatch, sr):
+    """Noise next to flat and scene content: the same CTA alternates between the candidate-queue path and the
+    row-group fallback (queue overflow), in all three modes, and the staging blocks are reused across both."""
+    monkeypatch.setenv("FDF_FORCE_SR", str(sr))
+    scene = oracle_mod.synth_frame(1500, 200, seed=5, frame=0, kind=0, amp=4)
+    noise = oracle_mod.synth_frame(1500, 200, seed=6, frame=0, kind=1)
+    img = scene.copy()
+    img[:, 300:700] = noise[:, 300:700]
+    img[:, 900:1000] = 128
+    img[:, 1200:1500] = noise[:, 1200:1500]
+    for t, nms in [(5, 0), (5, 1), (5, 2), (16, 1)]:
+        assert same_points(detector.detect_array(img, _cfg(t, 9, nms)), oracle_mod.port_detect(img, t, 9, nms)), (t, nms)
+    assert detector.device_flags() == 0
+
+
+def test_noise_batch_takes_the_fallback_everywhere(detector, oracle_mod):
+    """A resident batch of noise frames (64-row strips, every chunk overflows the queue): counts and hashes per frame."""
+    import torch
+
+    n = 40
+    frames = detector.synth_frames(n, 1280, 720, seed=31, first_frame=0, kind=1, amp=0)
+    for nms in (0, 1):
+        pts, offs = detector.detect_device(frames, _cfg(12, 9, nms))
+        torch.cuda.synchronize()
+        assert detector.device_flags() == 0
+        offs_h = offs.cpu().numpy()
+        pts_h = pts[: int(offs_h[-1])].cpu().numpy().astype(np.uint32)
+        counts, hashes = oracle_mod.port_detect_many(frames.cpu().numpy(), 12, 9, nms, n_threads=8)
+        assert (np.diff(offs_h) == counts).all()
+        for f in range(n):
+            assert oracle_mod.hash_points(pts_h[offs_h[f]:offs_h[f + 1]]) == int(hashes[f]), (nms, f)
