@@ -45,6 +45,9 @@ constexpr unsigned long long kStatusAggregate = 1ull << 62;
 constexpr unsigned long long kStatusPrefix = 2ull << 62;
 constexpr unsigned long long kStatusValueMask = (1ull << 62) - 1ull;
 constexpr uint32_t kSpinLimit = 1u << 22;
+#ifndef FDF_WAIT_SLEEP_NS
+#define FDF_WAIT_SLEEP_NS 0
+#endif
 constexpr uint32_t kWaitHintNs = 100000u;  // mbarrier.try_wait suspend-time hint
 constexpr unsigned long long kWaitLimitNs = 4000000000ull;  // 4 s
 
@@ -95,13 +98,21 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // that the kernel still ends quickly.)
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *flags, volatile uint32_t *abort) {
     if (mbar_try_wait(bar, parity)) return;
-    const unsigned long long t0 = global_timer_ns();
-    while (!mbar_try_wait(bar, parity)) {
-        if (*abort != 0u) break;
-        if (global_timer_ns() - t0 > kWaitLimitNs) {
-            atomicOr(flags, kFlagTmaTimeout);
-            *abort = 1u;
-            break;
+    unsigned long long t0 = 0ull;
+    for (uint32_t spins = 1;; spins++) {
+        if (mbar_try_wait(bar, parity)) return;
+#if FDF_WAIT_SLEEP_NS > 0
+        __nanosleep(FDF_WAIT_SLEEP_NS);  // the other warp group is busy: leave it the issue slots
+#endif
+        if ((spins & 63u) == 0u) {  // (rarely reached: a wait normally ends within a few rounds)
+            if (*abort != 0u) return;
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0ull) t0 = now;
+            if (now - t0 > kWaitLimitNs) {
+                atomicOr(flags, kFlagTmaTimeout);
+                *abort = 1u;
+                return;
+            }
         }
     }
 }
@@ -130,7 +141,8 @@ __device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned l
 
 // ---- shared-memory carve-up ------------------------------------------------------------------
 #ifndef FDF_ABLATE
-#define FDF_ABLATE 0  // (experiments only: skip phase B = 1, the NMS pass = 2, phase A = 4; results are wrong)
+#define FDF_ABLATE 0  // (timing experiments only, results are wrong: skip phase B = 1, the NMS pass = 2, phase A = 4,
+                      //  B arithmetic = 8, B ring loads = 16, stage 2 = 32, the candidate push = 64)
 #endif
 constexpr int kQueueBufs = 3;  // candidate queues in flight: being filled, being tested, being staged
   // queue entries a test thread works on at once (interleaved dependency chains)

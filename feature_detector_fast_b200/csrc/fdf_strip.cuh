@@ -162,6 +162,10 @@ FDF_HD void stage2_entry(uint32_t e, const uint8_t *tile, const uint32_t *vtab, 
     const uint32_t valid[4] = {vv.x, vv.y, vv.z, vv.w};
     uint32_t m = candidate_mask16(load16(rowp), load16(rowp - 3 * kTileW), load16(rowp + 3 * kTileW), cl, cr, valid,
                                   kbias);
+#if defined(FDF_ABLATE) && (FDF_ABLATE & 64)  // timing experiment: stage 2 without the candidate push
+    if (m == 0xdeadbeefu) queue[0] = (uint16_t)m;
+    return;
+#endif
     if (m != 0u) {
         const uint32_t cnt = (uint32_t)popc32(m);
         uint32_t slot = atomic_add_u32(qcount, cnt);
@@ -202,7 +206,9 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
         n += (uint32_t)__popc(b);
     }
     __syncwarp();
+#if !(defined(FDF_ABLATE) && (FDF_ABLATE & 32))  // timing experiment: stage 1 only
     for (uint32_t i = (uint32_t)lane; i < n; i += 32u) stage2_entry(wq[i], tile, vtab, kbias, queue, qcount);
+#endif
 #else
     (void)lane_or_minus1;
     for (int lane = 0; lane < 32; lane++) {
@@ -238,16 +244,29 @@ FDF_HD void phase_b(int tid, int nthreads, uint32_t qn, const uint8_t *tile, uin
             const int j = (int)((ent >> 5) & 15u) * 16 + mask_bit_to_px((int)(ent & 31u));
             pos[u] = (rr << 8) | j;
             const uint8_t *pc = tile + (rr + 3) * kTileW + j;
+#if defined(FDF_ABLATE) && (FDF_ABLATE & 16)  // timing experiment (wrong results): arithmetic without the ring loads
+            cv[u] = (int)(ent & 0xffu);
+#pragma unroll
+            for (int k = 0; k < 8; k++) ring[u].p[k] = mad32(ent + k, 0x10000u, ent * (k + 3)) & 0x00ff00ffu;
+#else
             cv[u] = pc[0];
 #pragma unroll
             for (int k = 0; k < 8; k++)
                 ring[u].p[k] = mad32((uint32_t)pc[FDF_RING_DY(k + 8) * kTileW + FDF_RING_DX(k + 8)], 0x10000u,
                                      (uint32_t)pc[FDF_RING_DY(k) * kTileW + FDF_RING_DX(k)]);
+#endif
         }
         bool kp[U];
         uint32_t sc[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {  // arithmetic
+#if defined(FDF_ABLATE) && (FDF_ABLATE & 8)  // timing experiment (wrong results): the ring loads without the arithmetic
+            uint32_t x = (uint32_t)cv[u];
+            for (int k = 0; k < 8; k++) x ^= ring[u].p[k];
+            kp[u] = (x & 0x10001u) == 0x10001u;
+            sc[u] = x & 0xffu;
+            continue;
+#endif
             const RingMasks rm = ring_masks(cv[u], ring[u], t);
             const bool arc_bright = has_arc(rm.bright, n);
             kp[u] = arc_bright || has_arc(rm.dark, n);
