@@ -50,7 +50,10 @@ cudaError_t read_phase_clocks(unsigned long long out[256]);
 
 struct fdf_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // kernels of the host-memory entry points
+    cudaStream_t copy_stream = nullptr;  // their host->device copies (overlap the kernels of earlier sub-batches)
+    cudaStream_t back_stream = nullptr;  // their device->host copies of points
+    std::vector<cudaEvent_t> pipe_events;  // per sub-batch: frames landed, kernels done
     EncodeTiledFn encode = nullptr;
     DeviceBuffer<uint8_t> workspace;            // tickets | flags | cursor | scan status | per-strip count/dst | run records
     DeviceBuffer<uint32_t> staging;             // per-chunk unordered runs of (row << 16 | x) before the gather
@@ -141,7 +144,9 @@ fdf_status fdf_create(int device, fdf_ctx **out_ctx) {
     if (!ctx) return FDF_ERR_INTERNAL;
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->back_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
         return FDF_ERR_CUDA;
     }
@@ -163,6 +168,9 @@ void fdf_destroy(fdf_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->back_stream) cudaStreamDestroy(ctx->back_stream);
     ctx->workspace.release();
     ctx->staging.release();
     ctx->staged_frames.release();
@@ -324,55 +332,88 @@ fdf_status fdf_detect_batch(fdf_ctx *ctx, const uint8_t *frames, uint32_t n_fram
     if (frame_stride < (uint64_t)pitch * h) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "frame_stride smaller than one frame");
     FDF_CUDA(ctx, cudaSetDevice(ctx->device));
 
-    // stage the frames with a 16-byte multiple pitch (TMA requirement); one copy when the layout allows
+    // Frames are staged with a 16-byte multiple pitch (TMA requirement) and processed in sub-batches: the
+    // host->device copy of sub-batch j+1 (copy stream) overlaps the kernels of sub-batch j (compute stream) and the
+    // device->host copy of its points (back stream).  The packed output needs every sub-batch's base offset, so the
+    // host reads each sub-batch's (tiny) offsets before it launches the next one; the copy stream never waits.
     const uint32_t dpitch = (w + 15u) & ~15u;
     const uint64_t dstride = (uint64_t)dpitch * h;
     FDF_CUDA(ctx, ctx->staged_frames.reserve((size_t)dstride * n_frames));
-    if (pitch == dpitch && frame_stride == dstride) {
-        FDF_CUDA(ctx, cudaMemcpyAsync(ctx->staged_frames.ptr, frames, (size_t)dstride * n_frames,
-                                      cudaMemcpyHostToDevice, ctx->stream));
-    } else if (frame_stride == (uint64_t)pitch * h) {
-        FDF_CUDA(ctx, cudaMemcpy2DAsync(ctx->staged_frames.ptr, dpitch, frames, pitch, w, (size_t)h * n_frames,
-                                        cudaMemcpyHostToDevice, ctx->stream));
-    } else {
-        for (uint32_t f = 0; f < n_frames; f++)
-            FDF_CUDA(ctx, cudaMemcpy2DAsync(ctx->staged_frames.ptr + (size_t)f * dstride, dpitch,
-                                            frames + (size_t)f * frame_stride, pitch, w, h, cudaMemcpyHostToDevice,
-                                            ctx->stream));
-    }
     const size_t worst = (size_t)n_frames * (size_t)(w - 6) * (size_t)(h - 6);
     const size_t dcap = cap < worst ? cap : worst;
     FDF_CUDA(ctx, ctx->staged_points.reserve(dcap ? dcap : 1));
-    FDF_CUDA(ctx, ctx->staged_offsets.reserve((size_t)n_frames + 1));
-    if (ctx->pinned_offsets_count < (size_t)n_frames + 1) {
+    FDF_CUDA(ctx, ctx->staged_offsets.reserve((size_t)n_frames + 2));
+    if (ctx->pinned_offsets_count < (size_t)n_frames + 2) {
         if (ctx->pinned_offsets) cudaFreeHost(ctx->pinned_offsets);
         ctx->pinned_offsets = nullptr;
         ctx->pinned_offsets_count = 0;
         FDF_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(&ctx->pinned_offsets),
-                                     ((size_t)n_frames + 1) * sizeof(unsigned long long)));
-        ctx->pinned_offsets_count = (size_t)n_frames + 1;
+                                     ((size_t)n_frames + 2) * sizeof(unsigned long long)));
+        ctx->pinned_offsets_count = (size_t)n_frames + 2;
     }
-
-    st = fdf_detect_device(ctx, ctx->staged_frames.ptr, n_frames, w, h, dpitch, dstride, threshold, count, nms,
-                           ctx->staged_points.ptr, dcap, reinterpret_cast<uint64_t *>(ctx->staged_offsets.ptr),
-                           ctx->stream);
-    if (st != FDF_OK) return st;
-    FDF_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_offsets, ctx->staged_offsets.ptr,
-                                  ((size_t)n_frames + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-    uint32_t *flags_dev = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + 4);
-    uint32_t flags = 0;
-    FDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    memcpy(offsets, ctx->pinned_offsets, ((size_t)n_frames + 1) * sizeof(uint64_t));
-    const uint64_t found = offsets[n_frames];
-    const size_t ncopy = found < dcap ? (size_t)found : dcap;
-    if (ncopy)
-        FDF_CUDA(ctx, cudaMemcpyAsync(out, ctx->staged_points.ptr, ncopy * sizeof(fdf_point), cudaMemcpyDeviceToHost,
+    // sub-batch size: about 128 MB of pixels, at least enough strips to fill the GPU several times over
+    unsigned long long sub_bytes = 128ull << 20;
+    if (const char *mb = getenv("FDF_SUB_BATCH_MB")) {  // tuning / test knob
+        const long v = atol(mb);
+        if (v >= 1 && v <= 65536) sub_bytes = (unsigned long long)v << 20;
+    }
+    uint32_t sub = (uint32_t)(sub_bytes / (dstride ? dstride : 1));
+    if (sub < 1u) sub = 1u;
+    if (sub > n_frames) sub = n_frames;
+    const uint32_t nsub = (n_frames + sub - 1) / sub;
+    while (ctx->pipe_events.size() < 2 * (size_t)nsub) {
+        cudaEvent_t e;
+        FDF_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_events.push_back(e);
+    }
+    for (uint32_t j = 0; j < nsub; j++) {  // all host->device copies are queued up front
+        const uint32_t f0 = j * sub, fn = (f0 + sub <= n_frames) ? sub : n_frames - f0;
+        uint8_t *dst = ctx->staged_frames.ptr + (size_t)f0 * dstride;
+        const uint8_t *src = frames + (size_t)f0 * frame_stride;
+        if (pitch == dpitch && frame_stride == dstride) {
+            FDF_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)dstride * fn, cudaMemcpyHostToDevice, ctx->copy_stream));
+        } else if (frame_stride == (uint64_t)pitch * h) {
+            FDF_CUDA(ctx, cudaMemcpy2DAsync(dst, dpitch, src, pitch, w, (size_t)h * fn, cudaMemcpyHostToDevice,
+                                            ctx->copy_stream));
+        } else {
+            for (uint32_t f = 0; f < fn; f++)
+                FDF_CUDA(ctx, cudaMemcpy2DAsync(dst + (size_t)f * dstride, dpitch, src + (size_t)f * frame_stride, pitch,
+                                                w, h, cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+        FDF_CUDA(ctx, cudaEventRecord(ctx->pipe_events[2 * j], ctx->copy_stream));
+    }
+    uint64_t found = 0;  // keypoints of the sub-batches so far (also beyond the capacity)
+    uint32_t flags_all = 0;
+    offsets[0] = 0;
+    for (uint32_t j = 0; j < nsub; j++) {
+        const uint32_t f0 = j * sub, fn = (f0 + sub <= n_frames) ? sub : n_frames - f0;
+        const size_t used = found < dcap ? (size_t)found : dcap;
+        FDF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[2 * j], 0));
+        unsigned long long *d_off = ctx->staged_offsets.ptr;  // (fn + 1 local offsets; reused by every sub-batch)
+        st = fdf_detect_device(ctx, ctx->staged_frames.ptr + (size_t)f0 * dstride, fn, w, h, dpitch, dstride, threshold,
+                               count, nms, ctx->staged_points.ptr + used, dcap - used,
+                               reinterpret_cast<uint64_t *>(d_off), ctx->stream);
+        if (st != FDF_OK) return st;
+        FDF_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_offsets, d_off, ((size_t)fn + 1) * sizeof(unsigned long long),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        uint32_t *flags_dev = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + 4);
+        FDF_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_offsets + fn + 1, flags_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                       ctx->stream));
-    if (ctx->workspace.ptr)
-        FDF_CUDA(ctx, cudaMemcpyAsync(&flags, flags_dev, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
-    FDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (flags) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x (look-back or TMA wait timed out)", flags);
+        FDF_CUDA(ctx, cudaEventRecord(ctx->pipe_events[2 * j + 1], ctx->stream));
+        FDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        flags_all |= *reinterpret_cast<const uint32_t *>(ctx->pinned_offsets + fn + 1);
+        for (uint32_t f = 0; f < fn; f++) offsets[f0 + f + 1] = found + ctx->pinned_offsets[f + 1];
+        const uint64_t got = ctx->pinned_offsets[fn];
+        const size_t ncopy = (found + got <= dcap) ? (size_t)got : (dcap - used);
+        if (ncopy) {  // this sub-batch's points go home while the next one is computed
+            FDF_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, ctx->pipe_events[2 * j + 1], 0));
+            FDF_CUDA(ctx, cudaMemcpyAsync(out + used, ctx->staged_points.ptr + used, ncopy * sizeof(fdf_point),
+                                          cudaMemcpyDeviceToHost, ctx->back_stream));
+        }
+        found += got;
+    }
+    FDF_CUDA(ctx, cudaStreamSynchronize(ctx->back_stream));
+    if (flags_all) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x (look-back or pipeline wait timed out)", flags_all);
     if (found > cap) return fail(ctx, FDF_ERR_CAPACITY, "%llu keypoints found, capacity %zu", (unsigned long long)found, cap);
     return FDF_OK;
 }

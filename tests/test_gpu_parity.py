@@ -287,3 +287,24 @@ def test_noise_batch_takes_the_fallback_everywhere(detector, oracle_mod):
         assert (np.diff(offs_h) == counts).all()
         for f in range(n):
             assert oracle_mod.hash_points(pts_h[offs_h[f]:offs_h[f + 1]]) == int(hashes[f]), (nms, f)
+
+
+def test_host_batch_is_pipelined_in_sub_batches(detector, oracle_mod, monkeypatch):
+    """fdf_detect_batch splits large batches into sub-batches (copy of the next one overlaps the kernels of the
+    current one); the packed CSR output must not depend on the split, including when the capacity runs out."""
+    import feature_detector_fast_b200 as fdf
+
+    frames = np.stack([oracle_mod.synth_frame(1280, 720, seed=12, frame=f, kind=0, amp=4) for f in range(7)])
+    monkeypatch.setenv("FDF_SUB_BATCH_MB", "4096")
+    pts1, offs1 = detector.detect_batch(frames, _cfg(16, 9, 1))
+    monkeypatch.setenv("FDF_SUB_BATCH_MB", "2")  # 2 frames per sub-batch -> 4 sub-batches
+    pts4, offs4 = detector.detect_batch(frames, _cfg(16, 9, 1))
+    assert (np.asarray(offs1) == np.asarray(offs4)).all()
+    assert same_points(pts1, pts4)
+    for f in (0, 3, 6):
+        assert same_points(pts4[int(offs4[f]):int(offs4[f + 1])], oracle_mod.port_detect(frames[f], 16, 9, 1))
+    total = int(offs4[-1])
+    small = np.zeros((total // 2, 2), np.uint32)
+    with pytest.raises(fdf.FdfError) as ei:
+        detector.detect_batch(frames, _cfg(16, 9, 1), out=small)
+    assert ei.value.status == 4  # FDF_ERR_CAPACITY
