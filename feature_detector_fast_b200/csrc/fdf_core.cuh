@@ -322,4 +322,68 @@ FDF_HD uint32_t score_sum_abs(int c, const Ring2 &r, int t) {
     return max(sb, sd);
 }
 
+
+// ---- exact test + scores on 16 "dual" words (the form the detection kernel uses) ---------------------------
+//
+// One word per ring pixel:  lane 0 = 256 + (p_i - c),  lane 1 = 256 - (p_i - c)   (both in [1, 511]).
+// A single multiply-add builds it straight from the loaded byte:  p * (1 - 2^16) + ((256 + c) << 16 | (256 - c)),
+// so there is no separate packing step and no lane swap anywhere below: the cyclic windows are plain index
+// arithmetic mod 16.
+//
+// Segment test and MaxThreshold score in one go.  With W_k the cyclic window of n ring positions starting at k:
+//   lane 0 of max_k min_{W_k} word  =  256 + max_k min_{W_k} (p - c)   > 256 + t  <=>  a brighter arc of >= n
+//   lane 1                          =  256 + max_k min_{W_k} (c - p)   > 256 + t  <=>  a darker arc of >= n
+// (fast_simd.rs:218-296 asks for exactly that: some window whose pixels are all > c + t, or all < c - t.)
+// Any two windows of >= 9 of 16 positions overlap, so when one lane exceeds 256 + t the other one is below 256:
+// best = max(lane 0, lane 1) is the keypoint's MaxThreshold score + 256 (see the derivation above
+// score_max_threshold) and  keypoint <=> best > 256 + t.
+struct RingDual {
+    uint32_t w[16];
+};
+
+FDF_HD uint32_t dual_bias(int c) { return ((uint32_t)(256 + c) << 16) | (uint32_t)(256 - c); }
+FDF_HD uint32_t dual_word(uint32_t p, uint32_t bias) { return mad32(p, 0xffff0001u, bias); }
+
+template <int K>  // K = n - 9
+FDF_HD uint32_t best_window_k(const uint32_t u[16]) {
+    uint32_t v[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = (K == 0) ? u[i] : min_u16x2(u[i], u[(i + K) & 15]);
+    const uint32_t a0 = max3_u16x2(v[0], v[1], v[2]), a1 = max3_u16x2(v[3], v[4], v[5]);
+    const uint32_t a2 = max3_u16x2(v[6], v[7], v[8]), a3 = max3_u16x2(v[9], v[10], v[11]);
+    const uint32_t a4 = max3_u16x2(v[12], v[13], v[14]);
+    return max_u16x2(max3_u16x2(a0, a1, a2), max3_u16x2(a3, a4, v[15]));
+}
+
+// per lane: 256 + max over the 16 cyclic windows of n positions of the window's minimum
+FDF_HD uint32_t best_window(const RingDual &r, int n) {
+    uint32_t t3[16], u[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) t3[i] = min3_u16x2(r.w[i], r.w[(i + 1) & 15], r.w[(i + 2) & 15]);
+#pragma unroll
+    for (int i = 0; i < 16; i++) u[i] = min3_u16x2(t3[i], t3[(i + 3) & 15], t3[(i + 6) & 15]);  // 9-windows
+    switch (n) {
+        case 9: return best_window_k<0>(u);
+        case 10: return best_window_k<1>(u);
+        case 11: return best_window_k<2>(u);
+        case 12: return best_window_k<3>(u);
+        case 13: return best_window_k<4>(u);
+        case 14: return best_window_k<5>(u);
+        case 15: return best_window_k<6>(u);
+        default: return best_window_k<7>(u);
+    }
+}
+
+// max of the two lanes of best_window: > 256 + t  <=>  keypoint;  minus 256 = MaxThreshold score of a keypoint
+FDF_HD uint32_t best_of_lanes(uint32_t m) { return max(m & 0xffffu, m >> 16); }
+
+// SumAbsolute on dual words: lane 0 accumulates max(p - c - t, 0), lane 1 max(c - p - t, 0)  (opencv_compat.rs:278-299)
+FDF_HD uint32_t score_sum_abs_dual(const RingDual &r, int t) {
+    const uint32_t k = (uint32_t)((0x10000 - (256 + t)) & 0xffff) * 0x00010001u;  // -(256 + t) per lane
+    uint32_t s = 0u;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += addrelu_s16x2(r.w[i], k);  // lane sums <= 16 * 255
+    return max(s & 0xffffu, s >> 16);
+}
+
 }  // namespace fdf

@@ -144,8 +144,7 @@ __device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned l
 #define FDF_ABLATE 0  // (timing experiments only, results are wrong: skip phase B = 1, the NMS pass = 2, phase A = 4,
                       //  B arithmetic = 8, B ring loads = 16, stage 2 = 32, the candidate push = 64)
 #endif
-constexpr int kQueueBufs = 3;  // candidate queues in flight: being filled, being tested, being staged
-  // queue entries a test thread works on at once (interleaved dependency chains)
+constexpr int kQueueBufs = 2;  // candidate queues in flight: being filled, being tested
 
 template <int MODE, int SR>
 struct Layout {
@@ -154,8 +153,10 @@ struct Layout {
     static constexpr int plane_off = 2 * tile_bytes;
     static constexpr int plane_bytes = SR * kPlaneW * 2;  // u16: tag << 12 | score (Off mode: score 1)
     static constexpr int queue_off = plane_off + plane_bytes;
-    static constexpr int queue_bytes = kQueueBufs * kQueueCap * 2;      // candidate queue = keypoint list, per chunk
-    static constexpr int wq_off = queue_off + queue_bytes;              // filter warps' stage-1 -> stage-2 queues
+    static constexpr int queue_bytes = kQueueBufs * kQueueCap * 2;      // candidate queues, per chunk
+    static constexpr int klist_off = queue_off + queue_bytes;           // keypoint list of the chunk being tested
+    static constexpr int klist_bytes = kQueueCap * 2;
+    static constexpr int wq_off = klist_off + klist_bytes;              // filter warps' stage-1 -> stage-2 queues
     static constexpr int wq_bytes = kFilterWarps * kWarpQueueCap * 2;
     static constexpr int vtab_off = wq_off + wq_bytes;                  // validity tables: first / middle / last chunk
     static constexpr int vtab_bytes = 3 * kVtabWords * 4;
@@ -166,7 +167,7 @@ struct Layout {
     static_assert(plane_bytes % 16 == 0 && plane_off % 16 == 0, "the plane is cleared with 128-bit stores");
     static_assert(SR % (2 * kFilterWarps) == 0 && SR <= 64, "filter warps take row pairs; queue entries hold 6 row bits");
     static_assert(kFallbackWarps * kWarpQueueCap * 2 <= kQueueCap * 2 && kFallbackWarps <= kTestWarps,
-                  "the dense fallback borrows a queue buffer for its warp queues");
+                  "the dense fallback borrows the keypoint list buffer for its warp queues");
     static_assert(SR % (2 * kFallbackWarps) == 0, "fallback filter warps take row pairs");
     static_assert(vtab_off % 16 == 0, "the validity tables are read with 128-bit loads");
     static_assert(kGroupRows * kTileW <= kQueueCap, "a row group must always fit the candidate queue");
@@ -285,6 +286,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     uint8_t *tiles = smem;
     uint16_t *plane = reinterpret_cast<uint16_t *>(smem + L::plane_off);
     uint16_t *queues = reinterpret_cast<uint16_t *>(smem + L::queue_off);              // [kQueueBufs][kQueueCap]
+    uint16_t *klist = reinterpret_cast<uint16_t *>(smem + L::klist_off);               // [kQueueCap]
     uint16_t *wqs = reinterpret_cast<uint16_t *>(smem + L::wq_off);                    // [kFilterWarps][kWarpQueueCap]
     uint32_t *vtabs = reinterpret_cast<uint32_t *>(smem + L::vtab_off);                 // [3][kVtabWords]
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::misc_off);             // [2] tile landed
@@ -296,6 +298,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 72);
     unsigned long long *s_block = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 80);   // [2] staging block
     volatile uint32_t *s_abort = reinterpret_cast<volatile uint32_t *>(smem + L::misc_off + 96);     // a wait timed out
+    uint32_t *kcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 112);         // [2] keypoint list fill (chunk parity)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = (int)p.w, H = (int)p.h;
@@ -351,6 +354,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         *scount = 0u;
         *s_total = 0u;
         *s_abort = 0u;
+        kcount[0] = kcount[1] = 0u;
         s_block[0] = s_block[1] = 0ull;
         *s_base = open_run(s_block, p);
         cur = atomicAdd(p.ticket, 1u);
@@ -452,23 +456,25 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
             const uint32_t qn = qcount[qb];
             if (qn <= (uint32_t)kQueueCap) {
 #if !(FDF_ABLATE & 1)
-                phase_b<MODE, SR, kTestUnroll>(ttid, kTestThreads, qn, tile, queue, plane, t, n, tag);
+                phase_b<MODE, SR>(ttid, lane, kTestThreads, qn, tile, queue, klist, &kcount[gc & 1u], plane, t, n, tag);
 #endif
                 FDF_CLK(5)
-                bar_test_group();  // every score of this chunk is in the plane; tile[stage] is free again
+                bar_test_group();  // every score of this chunk is in the plane and its keypoint list is complete;
+                                   // tile[stage] and queue qb are free again
                 if (t0) {
                     qcount[qb] = 0u;
                     request_tile(c + ahead, gc + (uint32_t)ahead, it);
                 }
 #if !(FDF_ABLATE & 2)
-                emit_list<MODE, SR, kEmitUnroll>(ttid, kTestThreads, qn, queue, plane, scount, *s_base, p.staging_cap,
-                                                 p.staging, g, tag);
+                emit_list<MODE, SR>(ttid, kTestThreads, kcount[gc & 1u], klist, plane, scount, *s_base, p.staging_cap,
+                                    p.staging, g);
 #endif
                 FDF_CLK(7)
-                bar_test_group();  // the run is complete; queue qb is free
+                bar_test_group();  // the run is complete; the keypoint list is free
                 if (t0) {
                     const uint32_t count = *scount;
                     *scount = 0u;
+                    kcount[gc & 1u] = 0u;  // (next used two chunks from now)
                     close_run(slot, count, c == NC - 1);
                     s_block[0] = *s_base + count;  // give the unused tail back
                     *s_base = open_run(s_block, p);
@@ -476,9 +482,9 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                 FDF_CLK(8)
             } else {
                 // very dense content: redo the chunk kGroupRows rows at a time (the test warps filter for themselves;
-                // their warp queues live in the queue buffer nobody uses before the next tile is requested), then
+                // their warp queues live in the keypoint list buffer, which this path does not use), then
                 // emit from the score plane: count, reserve, write
-                uint16_t *wq = queues + ((qb + 2u) % (uint32_t)kQueueBufs) * kQueueCap + twarp * kWarpQueueCap;
+                uint16_t *wq = klist + twarp * kWarpQueueCap;
                 const uint32_t *vtab = vtabs + vtab_variant(c, NC) * kVtabWords;
                 for (int lo = 0; lo < SR; lo += kGroupRows) {
                     bar_test_group();
@@ -488,7 +494,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                         phase_a_warp<MODE, SR, kFallbackWarps>(twarp, lane, tile, wq, vtab, queue, &qcount[qb], g, kbias,
                                                                lo, lo + kGroupRows);
                     bar_test_group();
-                    phase_b<MODE, SR, kTestUnroll>(ttid, kTestThreads, qcount[qb], tile, queue, plane, t, n, tag);
+                    phase_b<MODE, SR>(ttid, lane, kTestThreads, qcount[qb], tile, queue, nullptr, nullptr, plane, t, n, tag);
                 }
                 bar_test_group();  // every score of this chunk is in the plane; tile[stage] is free again
                 if (t0) {
@@ -774,7 +780,7 @@ size_t detect_smem_bytes(int mode, int sr) {
     const size_t tile = (size_t)tile_rows(sr) * kTileW;
     (void)mode;
     const size_t plane = (size_t)sr * kPlaneW * 2;
-    const size_t queues = (size_t)kQueueBufs * kQueueCap * 2, wq = (size_t)kFilterWarps * kWarpQueueCap * 2;
+    const size_t queues = (size_t)(kQueueBufs + 1) * kQueueCap * 2, wq = (size_t)kFilterWarps * kWarpQueueCap * 2;
     return 2 * tile + plane + queues + wq + (size_t)3 * kVtabWords * 4 + 128;
 }
 

@@ -222,84 +222,58 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
 }
 
 // ---- phase B: exact segment test (+ score) per candidate (replaces fast_simd.rs:115-297, 623-749)
-// One thread per queue entry, U entries per thread and step: their loads, arithmetic and stores are kept in
-// separate, branch-free sections so that the U dependency chains interleave (the test warps are few and would
-// otherwise sit in instruction latency).  The entry is rewritten in place: kKeypoint | scored row << 8 |
-// tile column for a confirmed keypoint, 0 otherwise -- the candidate queue thereby becomes the chunk's keypoint
-// list.  Every keypoint also writes (tag << 12 | score) into the score plane at (scored row, tile column -
-// kPlaneLead); in Off mode the score is 1 and only the dense fallback reads it.
-constexpr uint32_t kKeypoint = 0x8000u;  // (row << 8 | column) needs 14 bits
-
-template <int MODE, int SR, int U>
-FDF_HD void phase_b(int tid, int nthreads, uint32_t qn, const uint8_t *tile, uint16_t *queue, uint16_t *plane, int t,
-                    int n, uint32_t tag) {
-    for (uint32_t i0 = (uint32_t)tid; i0 < qn; i0 += (uint32_t)(U * nthreads)) {
-        int pos[U], cv[U];
-        Ring2 ring[U];
+// One thread per queue entry: 16 ring bytes + the centre from the tile, one dual word per ring pixel (fdf_core.cuh),
+// best window -> keypoint yes / no and the MaxThreshold score in the same ~50 instructions.  Every keypoint writes
+// (tag << 12 | score) into the score plane at (scored row, tile column - kPlaneLead) -- in Off mode the score is 1
+// and only the dense fallback reads it -- and is appended to the chunk's keypoint list as scored row << 8 | tile
+// column (one ballot per warp step, one shared atomic per warp step that found a keypoint).  klist == nullptr
+// (dense fallback): no list.
+// On the device the 32 lanes of a warp call it together (lane >= 0); the host emulator calls it once per thread
+// with lane = -1.
+template <int MODE, int SR>
+FDF_HD void phase_b(int tid, int lane, int nthreads, uint32_t qn, const uint8_t *tile, const uint16_t *queue,
+                    uint16_t *klist, uint32_t *kcount, uint16_t *plane, int t, int n, uint32_t tag) {
+    const int l = lane < 0 ? 0 : lane;
+    for (uint32_t ib = (uint32_t)(tid - l); ib < qn; ib += (uint32_t)nthreads) {  // (warp-uniform trip count)
+        const uint32_t i = ib + (uint32_t)l;
+        const bool valid = i < qn;
+        const uint32_t ent = queue[valid ? i : ib];
+        const int rr = (int)(ent >> 9);
+        const int j = (int)((ent >> 5) & 15u) * 16 + mask_bit_to_px((int)(ent & 31u));
+        const uint8_t *pc = tile + (rr + 3) * kTileW + j;
+        const uint32_t bias = dual_bias((int)pc[0]);
+        RingDual ring;
 #pragma unroll
-        for (int u = 0; u < U; u++) {  // loads (a missing entry repeats the first one and is dropped at the end)
-            const uint32_t i = i0 + (uint32_t)(u * nthreads);
-            const uint32_t ent = queue[i < qn ? i : i0];
-            const int rr = (int)(ent >> 9);
-            const int j = (int)((ent >> 5) & 15u) * 16 + mask_bit_to_px((int)(ent & 31u));
-            pos[u] = (rr << 8) | j;
-            const uint8_t *pc = tile + (rr + 3) * kTileW + j;
-#if defined(FDF_ABLATE) && (FDF_ABLATE & 16)  // timing experiment (wrong results): arithmetic without the ring loads
-            cv[u] = (int)(ent & 0xffu);
-#pragma unroll
-            for (int k = 0; k < 8; k++) ring[u].p[k] = mad32(ent + k, 0x10000u, ent * (k + 3)) & 0x00ff00ffu;
-#else
-            cv[u] = pc[0];
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                ring[u].p[k] = mad32((uint32_t)pc[FDF_RING_DY(k + 8) * kTileW + FDF_RING_DX(k + 8)], 0x10000u,
-                                     (uint32_t)pc[FDF_RING_DY(k) * kTileW + FDF_RING_DX(k)]);
-#endif
-        }
-        bool kp[U];
-        uint32_t sc[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {  // arithmetic
-#if defined(FDF_ABLATE) && (FDF_ABLATE & 8)  // timing experiment (wrong results): the ring loads without the arithmetic
-            uint32_t x = (uint32_t)cv[u];
-            for (int k = 0; k < 8; k++) x ^= ring[u].p[k];
-            kp[u] = (x & 0x10001u) == 0x10001u;
-            sc[u] = x & 0xffu;
-            continue;
-#endif
-            const RingMasks rm = ring_masks(cv[u], ring[u], t);
-            const bool arc_bright = has_arc(rm.bright, n);
-            kp[u] = arc_bright || has_arc(rm.dark, n);
-            sc[u] = 1u;  // Off mode: the plane only records "keypoint here" (used by the dense fallback)
-            if (MODE == NMS_MAX_THRESHOLD) sc[u] = score_max_threshold(cv[u], ring[u], n, arc_bright);  // (garbage unless kp)
-            if (MODE == NMS_SUM_ABSOLUTE) sc[u] = score_sum_abs(cv[u], ring[u], t);                      // <= 4080 < 2^12
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {  // stores
-            const uint32_t i = i0 + (uint32_t)(u * nthreads);
-            if (i < qn) {
-                if (kp[u])
-                    plane[(pos[u] >> 8) * kPlaneW + (pos[u] & 0xff) - kPlaneLead] = (uint16_t)((tag << 12) | sc[u]);
-                queue[i] = (uint16_t)(kp[u] ? (kKeypoint | (uint32_t)pos[u]) : 0u);
+        for (int k = 0; k < 16; k++) ring.w[k] = dual_word((uint32_t)pc[FDF_RING_DY(k) * kTileW + FDF_RING_DX(k)], bias);
+        const uint32_t best = best_of_lanes(best_window(ring, n));
+        const bool kp = valid && best > (uint32_t)(256 + t);
+        uint32_t sc = 1u;  // Off mode: the plane only records "keypoint here" (used by the dense fallback)
+        if (MODE == NMS_MAX_THRESHOLD) sc = best - 256u;                  // (garbage unless kp)
+        if (MODE == NMS_SUM_ABSOLUTE) sc = score_sum_abs_dual(ring, t);  // <= 4080 < 2^12
+        const uint32_t pos = (uint32_t)((rr << 8) | j);
+        if (kp) plane[rr * kPlaneW + j - kPlaneLead] = (uint16_t)((tag << 12) | sc);
+#if defined(__CUDA_ARCH__)
+        if (klist != nullptr) {
+            const uint32_t b = __ballot_sync(0xffffffffu, kp);
+            if (b != 0u) {
+                uint32_t base = 0u;
+                if (lane == 0) base = atomicAdd(kcount, (uint32_t)__popc(b));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (kp) klist[base + (uint32_t)__popc(b & ((1u << lane) - 1u))] = (uint16_t)pos;
             }
         }
+#else
+        if (klist != nullptr && kp) klist[(*kcount)++] = (uint16_t)pos;
+#endif
     }
 }
 
 // ---- NMS: strict maximum over the 8 neighbours (replaces fast_simd.rs:588-616) -------------------
 // Only this chunk's own columns and this strip's own rows are emitted; rows 3 and h-4 are scored
 // (they act as neighbours) but never emitted (fast_simd.rs:589-596, opencv_compat.rs:238-240).
-// A plane entry belongs to the current chunk iff it carries the current tag; anything else is stale = "no
-// keypoint".  Tags only grow between two clears of the plane, so v - (tag << 12) is the score for a current
-// entry and negative for a stale one: one add-and-clamp per cell.
-FDF_HD uint32_t live_score(uint32_t v, uint32_t tag_floor) {
-#if defined(__CUDA_ARCH__)
-    return (uint32_t)__viaddmax_s32((int)v, -(int)tag_floor, 0);
-#else
-    return (uint32_t)max((int)v - (int)tag_floor, 0);
-#endif
-}
-
+// Plane cells hold tag << 12 | score with score >= 1.  Tags only grow between two clears of the plane, so a stale
+// cell (an earlier chunk's) is smaller than tag << 12, i.e. smaller than any current cell: comparing the raw cells
+// is the same as comparing the scores with stale cells read as "no keypoint".
 FDF_HD uint32_t max3u(uint32_t a, uint32_t b, uint32_t c) {
 #if defined(__CUDA_ARCH__)
     return __vimax3_u32(a, b, c);
@@ -316,16 +290,13 @@ FDF_HD bool nms_emits(int rr, int j, const ChunkGeo &g) {
     return !(rr < 1 || rr > SR - 2 || x < g.x0 || x >= g.x1 || y >= g.h - 4);
 }
 
-// is the score at plane cell pp a strict maximum of its 3x3 neighbourhood?  (branch-free; pp must have a full
+// is the (current) cell pp a strict maximum of its 3x3 neighbourhood?  (branch-free; pp must have a full
 // neighbourhood inside the plane)
-FDF_HD bool nms_is_max(const uint16_t *pp, uint32_t floor) {
-    const uint32_t s = live_score(pp[0], floor);
-    const uint32_t a = max3u(live_score(pp[-kPlaneW - 1], floor), live_score(pp[-kPlaneW], floor),
-                             live_score(pp[-kPlaneW + 1], floor));
-    const uint32_t b = max3u(live_score(pp[kPlaneW - 1], floor), live_score(pp[kPlaneW], floor),
-                             live_score(pp[kPlaneW + 1], floor));
-    const uint32_t c = max3u(live_score(pp[-1], floor), live_score(pp[1], floor), a);
-    return s > max(b, c);
+FDF_HD bool nms_is_max(const uint16_t *pp) {
+    const uint32_t a = max3u(pp[-kPlaneW - 1], pp[-kPlaneW], pp[-kPlaneW + 1]);
+    const uint32_t b = max3u(pp[kPlaneW - 1], pp[kPlaneW], pp[kPlaneW + 1]);
+    const uint32_t c = max3u(pp[-1], pp[1], a);
+    return (uint32_t)pp[0] > max(b, c);
 }
 
 // staged form of a keypoint: row inside the strip's emitted rows << 16 | image column
@@ -334,36 +305,22 @@ FDF_HD uint32_t staged_entry(int rr, int j, const ChunkGeo &g) {
     return (uint32_t)((rr - (MODE == NMS_OFF ? 0 : 1)) << 16) | (uint32_t)(g.xt0 + j);
 }
 
-// The chunk's keypoint list (the rewritten candidate queue): every keypoint that survives the NMS (Off mode: every
-// keypoint) is written to the staging buffer at base + slot, slots handed out through *scount.
-template <int MODE, int SR, int U>
-FDF_HD void emit_list(int tid, int nthreads, uint32_t qn, const uint16_t *klist, const uint16_t *plane,
+// The chunk's keypoint list: every keypoint that survives the NMS (Off mode: every keypoint of the chunk's own
+// columns) is written to the staging buffer at base + slot, slots handed out through *scount.
+template <int MODE, int SR>
+FDF_HD void emit_list(int tid, int nthreads, uint32_t kn, const uint16_t *klist, const uint16_t *plane,
                       uint32_t *scount, unsigned long long base, unsigned long long cap, uint32_t *staging,
-                      const ChunkGeo &g, uint32_t tag) {
-    for (uint32_t i0 = (uint32_t)tid; i0 < qn; i0 += (uint32_t)(U * nthreads)) {
-        uint32_t ent[U];
-        bool keep[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i = i0 + (uint32_t)(u * nthreads);
-            ent[u] = i < qn ? klist[i] : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int rr = (int)((ent[u] >> 8) & 0x3fu), j = (int)(ent[u] & 0xffu);
-            const bool in = ent[u] != 0u && nms_emits<MODE, SR>(rr, j, g);
-            // (an entry that cannot be emitted is looked up at a harmless cell with a full neighbourhood)
-            keep[u] = in;
-            if (MODE != NMS_OFF)
-                keep[u] = nms_is_max(plane + (in ? rr * kPlaneW + j - kPlaneLead : kPlaneW + 1), tag << 12) && in;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (keep[u]) {
-                const unsigned long long o = base + atomic_add_u32(scount, 1u);
-                if (o < cap)
-                    staging[o] = staged_entry<MODE>((int)((ent[u] >> 8) & 0x3fu), (int)(ent[u] & 0xffu), g);
-            }
+                      const ChunkGeo &g) {
+    for (uint32_t i = (uint32_t)tid; i < kn; i += (uint32_t)nthreads) {
+        const uint32_t ent = klist[i];
+        const int rr = (int)(ent >> 8), j = (int)(ent & 0xffu);
+        const bool in = nms_emits<MODE, SR>(rr, j, g);
+        bool keep = in;
+        // (a keypoint that cannot be emitted is looked up at a harmless cell with a full neighbourhood)
+        if (MODE != NMS_OFF) keep = nms_is_max(plane + (in ? rr * kPlaneW + j - kPlaneLead : kPlaneW + 1)) && in;
+        if (keep) {
+            const unsigned long long o = base + atomic_add_u32(scount, 1u);
+            if (o < cap) staging[o] = staged_entry<MODE>(rr, j, g);
         }
     }
 }
@@ -377,7 +334,7 @@ FDF_HD void nms_dense(int tid, int nthreads, int pass, const uint16_t *plane, ui
         if (plane[i] < (tag << 12)) continue;
         const int rr = i / kPlaneW, j = i % kPlaneW + kPlaneLead;
         if (!nms_emits<MODE, SR>(rr, j, g)) continue;
-        if (MODE != NMS_OFF && !nms_is_max(plane + i, tag << 12)) continue;
+        if (MODE != NMS_OFF && !nms_is_max(plane + i)) continue;
         const uint32_t slot = atomic_add_u32(counter, 1u);
         if (pass == 1 && base + slot < cap) staging[base + slot] = staged_entry<MODE>(rr, j, g);
     }

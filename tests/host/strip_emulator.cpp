@@ -31,7 +31,7 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
     const int NC = chunks_per_row(w);
     const int WW = (w + 31) / 32;
     alignas(16) static uint8_t tile[tile_rows(64) * kTileW];
-    std::vector<uint16_t> plane((size_t)SR * kPlaneW), queue(kQueueCap), wq(kWarpQueueCap);
+    std::vector<uint16_t> plane((size_t)SR * kPlaneW), queue(kQueueCap), klist(kQueueCap), wq(kWarpQueueCap);
     alignas(16) uint32_t vtab[3][kVtabWords];  // validity tables: first / middle / last chunk of a row
     for (int v = 0; v < 3; v++)
         for (int i = 0; i < kVtabWords; i++) vtab[v][i] = valid_word<MODE>(w, vtab_chunk(v, NC), i);
@@ -58,13 +58,15 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
             const uint32_t qn = qcount;
             if (tag == 1u && gc != 0u) std::fill(plane.begin(), plane.end(), (uint16_t)0);
             if (qn <= (uint32_t)kQueueCap) {
+                uint32_t kn = 0;
                 for (int tid = 0; tid < kTestThreads; tid++)
-                    phase_b<MODE, SR, kTestUnroll>(tid, kTestThreads, qn, tile, queue.data(), plane.data(), t, n, tag);
-                std::vector<uint32_t> run(qn + 1);
+                    phase_b<MODE, SR>(tid, -1, kTestThreads, qn, tile, queue.data(), klist.data(), &kn, plane.data(), t, n, tag);
+                if (kn > qn) return -19;
+                std::vector<uint32_t> run(kn + 1);
                 uint32_t scount = 0;
                 for (int tid = 0; tid < kTestThreads; tid++)
-                    emit_list<MODE, SR, kEmitUnroll>(tid, kTestThreads, qn, queue.data(), plane.data(), &scount, 0ull, qn, run.data(), g, tag);
-                if (scount > qn) return -20;
+                    emit_list<MODE, SR>(tid, kTestThreads, kn, klist.data(), plane.data(), &scount, 0ull, kn, run.data(), g);
+                if (scount > kn) return -20;
                 staged.insert(staged.end(), run.begin(), run.begin() + scount);
             } else {
                 if (fallbacks) fallbacks[0]++;
@@ -75,7 +77,7 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
                                                            lo + kGroupRows);
                     if (qcount > (uint32_t)kQueueCap) return -18;
                     for (int tid = 0; tid < kTestThreads; tid++)
-                        phase_b<MODE, SR, kTestUnroll>(tid, kTestThreads, qcount, tile, queue.data(), plane.data(), t, n, tag);
+                        phase_b<MODE, SR>(tid, -1, kTestThreads, qcount, tile, queue.data(), nullptr, nullptr, plane.data(), t, n, tag);
                 }
                 {
                     if (fallbacks) fallbacks[1]++;
@@ -185,6 +187,15 @@ int64_t fdf_core_check(uint64_t iterations, uint64_t seed) {
             md |= (uint32_t)pos[i] << i;
         }
         if ((rm.bright & 0xffffu) != mb || (rm.dark & 0xffffu) != md) bad++;
+        // the form the kernel uses: one dual word per ring pixel, test and MaxThreshold score from the best window
+        RingDual rd;
+        for (int i = 0; i < 16; i++) rd.w[i] = dual_word((uint32_t)ring[i], dual_bias(c));
+        const uint32_t best = best_of_lanes(best_window(rd, n));
+        if ((best > (uint32_t)(256 + t)) != (kp_bright || kp_dark)) bad++;
+        if ((kp_bright || kp_dark) &&
+            best - 256u != fdf_oracle_score_max_threshold_px((uint8_t)c, ring8, (uint8_t)n))
+            bad++;
+        if (score_sum_abs_dual(rd, t) != fdf_oracle_score_sum_abs_px((uint8_t)c, ring8, (uint8_t)t)) bad++;
         const bool ab = has_arc(rm.bright & 0xffffu, n), ad = has_arc(rm.dark & 0xffffu, n);
         if (ab != kp_bright || ad != kp_dark) bad++;
         if (score_sum_abs(c, rp, t) != fdf_oracle_score_sum_abs_px((uint8_t)c, ring8, (uint8_t)t)) bad++;
