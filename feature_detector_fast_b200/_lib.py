@@ -7,7 +7,7 @@ import re
 import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libfdf_cuda.so")
+LIB_PATH = os.environ.get("FDF_LIB") or os.path.join(_PKG, "lib", "libfdf_cuda.so")  # FDF_LIB: what-if builds (tools/)
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "fdf.h")
 _lib = None
 

@@ -144,13 +144,20 @@ __device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned l
 #define FDF_ABLATE 0  // (timing experiments only, results are wrong: skip phase B = 1, the NMS pass = 2, phase A = 4,
                       //  B arithmetic = 8, B ring loads = 16, stage 2 = 32, the candidate push = 64)
 #endif
-constexpr int kQueueBufs = 2;  // candidate queues in flight: being filled, being tested
+#ifndef FDF_TILE_STAGES
+#define FDF_TILE_STAGES 2
+#endif
+constexpr int kTileStages = FDF_TILE_STAGES;  // tile buffers per CTA: the tile of chunk k + kTileStages is requested when
+                                              // phase B of chunk k is done, so TMA latency (~1700 cycles under load)
+                                              // is hidden behind kTileStages - 1 chunks of work
+constexpr int kQueueBufs = kTileStages;       // candidate queues: the filter may run kTileStages - 1 chunks ahead of the test
+static_assert(kTileStages >= 2 && kTileStages <= 4, "misc layout holds up to 4 barriers of each kind");
 
 template <int MODE, int SR>
 struct Layout {
     static constexpr int TR = tile_rows(SR);
     static constexpr int tile_bytes = TR * kTileW;  // one TMA box
-    static constexpr int plane_off = 2 * tile_bytes;
+    static constexpr int plane_off = kTileStages * tile_bytes;
     static constexpr int plane_bytes = SR * kPlaneW * 2;  // u16: tag << 12 | score (Off mode: score 1)
     static constexpr int queue_off = plane_off + plane_bytes;
     static constexpr int queue_bytes = kQueueBufs * kQueueCap * 2;      // candidate queues, per chunk
@@ -161,7 +168,7 @@ struct Layout {
     static constexpr int vtab_off = wq_off + wq_bytes;                  // validity tables: first / middle / last chunk
     static constexpr int vtab_bytes = 3 * kVtabWords * 4;
     static constexpr int misc_off = vtab_off + vtab_bytes;
-    static constexpr int misc_bytes = 128;
+    static constexpr int misc_bytes = 192;
     static constexpr int total = misc_off + misc_bytes;
     static_assert(tile_bytes % 128 == 0, "TMA destination must stay 128-byte aligned");
     static_assert(plane_bytes % 16 == 0 && plane_off % 16 == 0, "the plane is cleared with 128-bit stores");
@@ -276,7 +283,10 @@ __device__ __forceinline__ unsigned long long open_run(unsigned long long *s_blo
 }
 
 template <int MODE, int SR>
-__global__ void __launch_bounds__(kThreads, SR >= 48 ? 3 : 4)
+#ifndef FDF_SMALL_SR_CTAS
+#define FDF_SMALL_SR_CTAS 4
+#endif
+__global__ void __launch_bounds__(kThreads, SR >= 48 ? 3 : FDF_SMALL_SR_CTAS)
 fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p) {
     using L = Layout<MODE, SR>;
     constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;  // score halo (rows and columns) needed by the 3x3 NMS
@@ -289,16 +299,18 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     uint16_t *klist = reinterpret_cast<uint16_t *>(smem + L::klist_off);               // [kQueueCap]
     uint16_t *wqs = reinterpret_cast<uint16_t *>(smem + L::wq_off);                    // [kFilterWarps][kWarpQueueCap]
     uint32_t *vtabs = reinterpret_cast<uint32_t *>(smem + L::vtab_off);                 // [3][kVtabWords]
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::misc_off);             // [2] tile landed
-    uint64_t *q_full = reinterpret_cast<uint64_t *>(smem + L::misc_off + 16);          // [3] candidate queue complete
-    uint32_t *qcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 40);          // [3] queue fill
-    uint32_t *s_ticket = reinterpret_cast<uint32_t *>(smem + L::misc_off + 52);        // [2] strip tickets (strip parity)
-    uint32_t *scount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 60);          // keypoints staged by the chunk so far
-    uint32_t *s_total = reinterpret_cast<uint32_t *>(smem + L::misc_off + 68);         // keypoints of the strip so far
-    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 72);
-    unsigned long long *s_block = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 80);   // [2] staging block
-    volatile uint32_t *s_abort = reinterpret_cast<volatile uint32_t *>(smem + L::misc_off + 96);     // a wait timed out
-    uint32_t *kcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 112);         // [2] keypoint list fill (chunk parity)
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::misc_off);             // [kTileStages] tile landed
+    uint64_t *q_full = reinterpret_cast<uint64_t *>(smem + L::misc_off + 32);          // [kQueueBufs] candidate queue complete
+    uint32_t *qcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 64);          // [kQueueBufs] queue fill
+    uint32_t *s_ticket = reinterpret_cast<uint32_t *>(smem + L::misc_off + 80);        // [2] strip tickets (strip parity)
+    uint32_t *scount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 88);          // keypoints staged by the chunk so far
+    uint32_t *s_total = reinterpret_cast<uint32_t *>(smem + L::misc_off + 92);         // keypoints of the strip so far
+    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 96);
+    unsigned long long *s_block = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 104);  // [2] staging block
+    volatile uint32_t *s_abort = reinterpret_cast<volatile uint32_t *>(smem + L::misc_off + 120);    // a wait timed out
+    uint32_t *kcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 124);         // [2] keypoint list fill (chunk parity)
+    [[maybe_unused]] volatile long long *clk_req =
+        reinterpret_cast<volatile long long *>(smem + L::misc_off + 136);              // [kTileStages] (phase clocks only)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = (int)p.w, H = (int)p.h;
@@ -306,11 +318,17 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     const uint32_t total_items = p.n_frames * p.strips_per_frame;
     const bool is_filter = warp < kFilterWarps;
     const int ttid = tid - kFilterWarps * 32;  // thread index inside the test group
-    const bool t0 = ttid == 0;                 // the thread that draws tickets and requests tiles
+#ifndef FDF_T0_WARP
+#define FDF_T0_WARP (kTestWarps - 1)
+#endif
+    // the thread that draws tickets, requests tiles and keeps the run records: lane 0 of the LAST test warp, which gets
+    // the smallest share of every candidate / keypoint list -- its serial work between the group's barriers then
+    // overlaps the other warps' list work instead of extending the critical path
+    const bool t0 = ttid == 32 * FDF_T0_WARP;
 
     uint32_t cur = 0u, nxt = 0xffffffffu;
     bool have_nxt = false;
-    const int ahead = NC >= 2 ? 2 : 1;  // tiles requested this many chunks ahead (never beyond the next strip)
+    const int ahead = NC >= kTileStages ? kTileStages : NC;  // tiles requested this many chunks ahead (never beyond the next strip)
 
     // request the tile of chunk c of the current strip (c < NC) or of chunk c - NC of the next strip; `it` is the
     // current strip's sequence number in this CTA.  When the work is exhausted the barrier is completed without
@@ -327,7 +345,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
             item = nxt;
             c -= NC;
         }
-        const uint32_t stage = stream_index & 1u;
+        const uint32_t stage = stream_index % (uint32_t)kTileStages;
         if (item >= total_items) {
             mbar_arrive(&full_bar[stage]);
             return;
@@ -336,7 +354,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         const uint32_t strip = item - frame * p.strips_per_frame;
         const int ty0 = first_out_row(MODE) + (int)strip * OUT_R - HS - 3;  // image row of tile row 0
 #ifdef FDF_PHASE_CLOCKS
-        reinterpret_cast<volatile long long *>(smem + L::misc_off + 96)[stage] = clock64();
+        clk_req[stage] = clock64();
 #endif
         mbar_expect_tx(&full_bar[stage], (uint32_t)L::tile_bytes);
         tma_load_3d(tiles + stage * L::tile_bytes, &tmap, c * kChunkW - kTileLead, ty0, (int)frame, &full_bar[stage]);
@@ -344,8 +362,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
 
     if (t0) {
         tma_prefetch_desc(&tmap);
-        mbar_init(&full_bar[0], 1);
-        mbar_init(&full_bar[1], 1);
+        for (int i = 0; i < kTileStages; i++) mbar_init(&full_bar[i], 1);
         for (int i = 0; i < kQueueBufs; i++) {
             mbar_init(&q_full[i], kFilterWarps);
             qcount[i] = 0u;
@@ -369,12 +386,12 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     __syncthreads();
     cur = s_ticket[0];
     if (t0)
-        for (int c = 0; c < ahead; c++) request_tile(c, (uint32_t)c, 0u);
+        for (int c = 0; c < ahead; c++) request_tile(c, (uint32_t)c, 0u);  // (ahead <= NC: all of the first strip)
 
     const int t = (int)p.threshold, n = (int)p.count;
     const uint32_t kbias = filter_kbias(p.threshold);
-    uint32_t gc = 0;   // chunks processed by this CTA so far: tile stage = gc & 1, mbarrier parity = (gc >> 1) & 1
-    uint32_t qb = 0, qpar = 0;  // queue buffer gc % 3 and the parity of its q_full phase ((gc / 3) & 1)
+    uint32_t gc = 0;   // chunks processed by this CTA so far
+    uint32_t qb = 0, qpar = 0;  // tile stage = queue buffer = gc % kTileStages, and the parity of their mbarrier phases
 
     if (is_filter) {
         // ================================ filter warps =================================================
@@ -384,25 +401,26 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
             const uint32_t frame = cur / p.strips_per_frame;
             const uint32_t strip = cur - frame * p.strips_per_frame;
             for (int c = 0; c < NC; c++, gc++) {
-                const uint32_t stage = gc & 1u;
+                const uint32_t stage = qb;
                 const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
 #ifdef FDF_PHASE_CLOCKS
                 uint32_t landed;
                 asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                             : "=r"(landed) : "r"(smem_u32(&full_bar[stage])), "r"((gc >> 1) & 1u) : "memory");
+                             : "=r"(landed) : "r"(smem_u32(&full_bar[stage])), "r"(qpar) : "memory");
                 const bool had_to_wait = landed == 0u;
 #endif
-                mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags, s_abort);  // (also: queue qb is free again)
+                mbar_wait(&full_bar[stage], qpar, p.flags, s_abort);  // (also: queue qb is free again)
 #ifdef FDF_PHASE_CLOCKS
                 if (had_to_wait) {
-                    clk_acc[8] += clock64() - reinterpret_cast<volatile long long *>(smem + L::misc_off + 96)[stage];
+                    clk_acc[8] += clock64() - clk_req[stage];
                     clk_acc[9] += 1;
                 }
 #endif
                 FDF_CLK(0)
 #if !(FDF_ABLATE & 4)
                 phase_a_warp<MODE, SR, kFilterWarps>(warp, lane, tiles + stage * L::tile_bytes, wq,
-                                                     vtabs + vtab_variant(c, NC) * kVtabWords, queues + qb * kQueueCap,
+                                                     vtabs + vtab_variant(c, NC) * kVtabWords, vtab_variant(c, NC),
+                                                     queues + qb * kQueueCap,
                                                      &qcount[qb], g, kbias, 0, SR);
 #endif
                 __syncwarp();
@@ -414,7 +432,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                 }
             }
             // the next strip's ticket is published before its first tile is requested (or the end is signalled)
-            mbar_wait(&full_bar[gc & 1u], (gc >> 1) & 1u, p.flags, s_abort);
+            mbar_wait(&full_bar[qb], qpar, p.flags, s_abort);
             FDF_CLK(2)
             cur = s_ticket[(it + 1u) & 1u];
         }
@@ -441,7 +459,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         const uint32_t frame = cur / p.strips_per_frame;
         const uint32_t strip = cur - frame * p.strips_per_frame;
         for (int c = 0; c < NC; c++, gc++) {
-            const uint32_t stage = gc & 1u;
+            const uint32_t stage = qb;
             const uint8_t *tile = tiles + stage * L::tile_bytes;
             uint16_t *queue = queues + qb * kQueueCap;
             const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
@@ -451,12 +469,12 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                 bar_test_group();
             }
             mbar_wait(&q_full[qb], qpar, p.flags, s_abort);
-            mbar_wait(&full_bar[stage], (gc >> 1) & 1u, p.flags, s_abort);  // (completed long ago: makes the tile visible here too)
+            mbar_wait(&full_bar[stage], qpar, p.flags, s_abort);  // (completed long ago: makes the tile visible here too)
             FDF_CLK(4)
             const uint32_t qn = qcount[qb];
             if (qn <= (uint32_t)kQueueCap) {
 #if !(FDF_ABLATE & 1)
-                phase_b<MODE, SR>(ttid, lane, kTestThreads, qn, tile, queue, klist, &kcount[gc & 1u], plane, t, n, tag);
+                phase_b<MODE, SR, kTestUnroll>(ttid, lane, kTestThreads, qn, tile, queue, klist, &kcount[gc & 1u], plane, t, n, tag);
 #endif
                 FDF_CLK(5)
                 bar_test_group();  // every score of this chunk is in the plane and its keypoint list is complete;
@@ -491,7 +509,8 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                     if (t0) qcount[qb] = 0u;
                     bar_test_group();
                     if (twarp < kFallbackWarps)
-                        phase_a_warp<MODE, SR, kFallbackWarps>(twarp, lane, tile, wq, vtab, queue, &qcount[qb], g, kbias,
+                        phase_a_warp<MODE, SR, kFallbackWarps>(twarp, lane, tile, wq, vtab, vtab_variant(c, NC), queue,
+                                                               &qcount[qb], g, kbias,
                                                                lo, lo + kGroupRows);
                     bar_test_group();
                     phase_b<MODE, SR>(ttid, lane, kTestThreads, qcount[qb], tile, queue, nullptr, nullptr, plane, t, n, tag);
@@ -781,7 +800,7 @@ size_t detect_smem_bytes(int mode, int sr) {
     (void)mode;
     const size_t plane = (size_t)sr * kPlaneW * 2;
     const size_t queues = (size_t)(kQueueBufs + 1) * kQueueCap * 2, wq = (size_t)kFilterWarps * kWarpQueueCap * 2;
-    return 2 * tile + plane + queues + wq + (size_t)3 * kVtabWords * 4 + 128;
+    return (size_t)kTileStages * tile + plane + queues + wq + (size_t)3 * kVtabWords * 4 + 192;
 }
 
 size_t gather_smem_bytes(int mode, int sr, uint32_t words_per_row) {

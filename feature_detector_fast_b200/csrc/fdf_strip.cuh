@@ -110,16 +110,26 @@ FDF_HD RowRange live_rows(const ChunkGeo &g, int row_lo, int row_hi) {
     return r;
 }
 
-// Stage 1 for one lane: the 16-pixel group q of BH consecutive scored rows rr0 .. rr0+BH-1.  Returns bit i set iff
-// row rr0 + i has a centre whose north or south ring pixel differs from it by more than t.
+// Stage 1 for one lane: the 16-pixel group q of BH consecutive scored rows rr0 .. rr0+BH-1.
+//   v bit i: row rr0 + i has a centre whose north or south ring pixel differs from it by more than t;
+//   h bit i: row rr0 + i has a pixel y in the group with |p(y + 3) - p(y)| > t.
+// A candidate centre x needs max(|E-c|, |W-c|) > t, i.e. the horizontal difference at y = x or at y = x - 3, and
+// y = x - 3 may lie in the group to the left: the caller ORs the left neighbour's h into this group's.  With
+// -DFDF_STAGE1_H a (row, group) goes on to stage 2 only if v and (h or left h): ~9 % of them instead of the ~18 %
+// that pass v alone.  Without it (default, see below) h is all ones and v alone decides.
 // The rows are walked top to bottom with everything kept in registers: every tile row is loaded once (LDS.128)
 // and the vertical difference D(y) = |p(y) - p(y-3)| is computed once and used twice (as the north difference of
 // centre y and the south difference of centre y - 3).
+struct Stage1Masks {
+    uint32_t v, h;
+};
+
 template <int BH>
-FDF_HD uint32_t stage1_band(const uint8_t *tile, int rr0, int q, uint32_t kbias) {
+FDF_HD Stage1Masks stage1_band(const uint8_t *tile, int rr0, int q, uint32_t kbias) {
     const uint8_t *p = tile + rr0 * kTileW + q * 16;  // tile row rr0 is the north ring row of scored row rr0
     Px16 row[BH + 6], d[BH + 3];
-    uint32_t anymask = 0u;
+    Stage1Masks m;
+    m.v = m.h = 0u;
 #pragma unroll
     for (int i = 0; i < BH + 6; i++) {
         row[i] = load16(p + i * kTileW);
@@ -128,13 +138,31 @@ FDF_HD uint32_t stage1_band(const uint8_t *tile, int rr0, int q, uint32_t kbias)
             for (int k = 0; k < 4; k++) d[i - 3].w[k] = absdiff4(row[i].w[k], row[i - 3].w[k]);
         }
         if (i >= 6) {  // centre = tile row i - 3: north difference d[i - 6], south difference d[i - 3]
-            uint32_t o = 0u;
+            uint32_t o = 0u, oh = 0u;
 #pragma unroll
             for (int k = 0; k < 4; k++) o |= exceeds4(d[i - 6].w[k] | d[i - 3].w[k], kbias);
-            if ((o & 0x80808080u) != 0u) anymask |= 1u << (i - 6);
+            if ((o & 0x80808080u) != 0u) m.v |= 1u << (i - 6);
+#if !defined(FDF_STAGE1_H)  // the horizontal group test below is a measured loss (1.077 vs 1.039 ms per 256 frames: its
+                            // dense work costs more than the stage-2 entries it saves), so it is off by default
+            m.h = 0xffffffffu;
+            continue;
+#endif
+            // the word right of the group = the first word of lane + 1's group (same rows); for q = 15 it is some
+            // other pixel word, which can only set h where it need not be set
+#if defined(__CUDA_ARCH__)
+            const uint32_t wr = __shfl_down_sync(0xffffffffu, row[i - 3].w[0], 1);  // (no shared-memory wavefronts)
+#else
+            const uint32_t wr = *reinterpret_cast<const uint32_t *>(p + (i - 3) * kTileW + 16);
+#endif
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t east = byte_perm(row[i - 3].w[k], k < 3 ? row[i - 3].w[k + 1] : wr, 0x6543u);
+                oh |= exceeds4(absdiff4(east, row[i - 3].w[k]), kbias);
+            }
+            if ((oh & 0x80808080u) != 0u) m.h |= 1u << (i - 6);
         }
     }
-    return anymask;
+    return m;
 }
 
 // bit i set iff scored row rr0 + i may hold a centre at all (fast_simd.rs:342: image rows 3 .. h-4) and lies in
@@ -147,35 +175,53 @@ FDF_HD uint32_t live_mask(const ChunkGeo &g, int rr0, int bh, int row_lo, int ro
     return m;
 }
 
-// stage 2 for one queued group: candidate mask, then one queue entry per surviving centre.  When the queue is
-// full the entries are dropped but still counted: *qcount > kQueueCap tells the caller to redo the chunk in
-// row groups.
-FDF_HD void stage2_entry(uint32_t e, const uint8_t *tile, const uint32_t *vtab, uint32_t kbias, uint16_t *queue,
-                         uint32_t *qcount) {
+// stage 2 for one queued group: the candidate mask of its 16 centres (bit layout: candidate_mask16)
+FDF_HD uint32_t stage2_mask(uint32_t e, const uint8_t *tile, const uint32_t *vtab, uint32_t all_valid_inside,
+                            uint32_t kbias) {
     const int rr = (int)(e >> 4), q = (int)(e & 15u);
     const uint8_t *rowp = tile + (rr + 3) * kTileW + q * 16;
     // the words left / right of the group: for q = 0 / q = 15 they belong to the neighbouring tile row, which
     // only reaches centres the validity table excludes (tile columns 0..2 and 253..255)
+#if defined(FDF_STAGE2_LDS64)  // timing experiments (measured slower: 1.079 vs 1.035 ms)
+    const uint32_t cl = reinterpret_cast<const uint2 *>(rowp - 8)->y;
+    const uint32_t cr = reinterpret_cast<const uint2 *>(rowp + 16)->x;
+#else
     const uint32_t cl = *reinterpret_cast<const uint32_t *>(rowp - 4);
     const uint32_t cr = *reinterpret_cast<const uint32_t *>(rowp + 16);
+#endif
+#if defined(FDF_STAGE2_VTAB_PRED)
+    // validity: only the first two and the last group of a tile row (and the row's last chunk) have excluded centres
+    uint32_t valid[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
+    if (q <= 1 || q == 15 || all_valid_inside == 0u) {
+        const uint4 vv = *reinterpret_cast<const uint4 *>(vtab + 4 * q);
+        valid[0] = vv.x, valid[1] = vv.y, valid[2] = vv.z, valid[3] = vv.w;
+    }
+#else
+    (void)all_valid_inside;
     const uint4 vv = *reinterpret_cast<const uint4 *>(vtab + 4 * q);
     const uint32_t valid[4] = {vv.x, vv.y, vv.z, vv.w};
-    uint32_t m = candidate_mask16(load16(rowp), load16(rowp - 3 * kTileW), load16(rowp + 3 * kTileW), cl, cr, valid,
-                                  kbias);
-#if defined(FDF_ABLATE) && (FDF_ABLATE & 64)  // timing experiment: stage 2 without the candidate push
-    if (m == 0xdeadbeefu) queue[0] = (uint16_t)m;
+#endif
+    return candidate_mask16(load16(rowp), load16(rowp - 3 * kTileW), load16(rowp + 3 * kTileW), cl, cr, valid, kbias);
+}
+
+// one queue entry per set bit of the group's candidate mask, at queue[slot ...]
+FDF_HD void push_candidates(uint32_t e, uint32_t m, uint16_t *queue, uint32_t slot) {
+    const uint32_t base = (e >> 4) << 9 | (e & 15u) << 5;
+    uint16_t *out = queue + slot;
+#if !defined(FDF_PUSH_STRAIGHT)  // bit walk (default; the predicated straight-line form below measured 0.7 % slower)
+    while (m != 0u) {
+        const uint32_t p = (uint32_t)highest_set_bit(m);
+        m ^= 1u << p;
+        *out++ = (uint16_t)(base + p);
+    }
     return;
 #endif
-    if (m != 0u) {
-        const uint32_t cnt = (uint32_t)popc32(m);
-        uint32_t slot = atomic_add_u32(qcount, cnt);
-        if (slot + cnt <= (uint32_t)kQueueCap) {
-            const uint32_t base = (uint32_t)((rr << 9) | (q << 5));
-            do {
-                const uint32_t p = (uint32_t)highest_set_bit(m);
-                m ^= 1u << p;
-                queue[slot++] = (uint16_t)(base + p);
-            } while (m != 0u);
+#pragma unroll
+    for (int p = 0; p < 32; p++) {
+        if (((0xf0f0f0f0u >> p) & 1u) == 0u) continue;  // candidate_mask16 uses bits 8b + 7 - k
+        if ((m >> p) & 1u) {
+            *out = (uint16_t)(base + (uint32_t)p);
+            out++;
         }
     }
 }
@@ -187,16 +233,21 @@ FDF_HD void stage2_entry(uint32_t e, const uint8_t *tile, const uint32_t *vtab, 
 // (2 v + (l >> 4)) * BH.
 template <int MODE, int SR, int NW>
 FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint16_t *wq, const uint32_t *vtab,
-                         uint16_t *queue, uint32_t *qcount, const ChunkGeo &g, uint32_t kbias, int row_lo,
+                         int variant, uint16_t *queue, uint32_t *qcount, const ChunkGeo &g, uint32_t kbias, int row_lo,
                          int row_hi) {
     constexpr int BH = SR / (2 * NW);
     static_assert(BH * 32 <= kWarpQueueCap, "a warp queue must hold every group stage 1 looks at");
     uint32_t n = 0u;  // entries in wq (warp-uniform)
+    // groups 2 .. 14 of a chunk are all-valid unless it is the last chunk of its row (variant 2)
+    const uint32_t inside = variant == 2 ? 0u : 1u;
 #if defined(__CUDA_ARCH__)
     const int lane = lane_or_minus1;
     const int q = lane & 15, rr0 = (2 * warp + (lane >> 4)) * BH;
     const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t need = stage1_band<BH>(tile, rr0, q, kbias) & live_mask(g, rr0, BH, row_lo, row_hi);
+    const Stage1Masks s1 = stage1_band<BH>(tile, rr0, q, kbias);
+    uint32_t hl = __shfl_up_sync(0xffffffffu, s1.h, 1);  // the group to the left, same rows
+    if (q == 0) hl = 0u;  // (tile columns 0 .. 15: the centres that count start at column 11, their x - 3 is in the group)
+    const uint32_t need = s1.v & (s1.h | hl) & live_mask(g, rr0, BH, row_lo, row_hi);
     const uint32_t ent = (uint32_t)((rr0 << 4) | q);
 #pragma unroll
     for (int i = 0; i < BH; i++) {
@@ -207,17 +258,41 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
     }
     __syncwarp();
 #if !(defined(FDF_ABLATE) && (FDF_ABLATE & 32))  // timing experiment: stage 1 only
-    for (uint32_t i = (uint32_t)lane; i < n; i += 32u) stage2_entry(wq[i], tile, vtab, kbias, queue, qcount);
+    // stage 2, one lane per queued group.  When the queue is full the entries are dropped but still counted:
+    // *qcount > kQueueCap tells the test warps to redo the chunk in row groups.
+    for (uint32_t i = (uint32_t)lane; i < n; i += 32u) {
+        const uint32_t e = wq[i];
+        const uint32_t m = stage2_mask(e, tile, vtab, inside, kbias);
+#if defined(FDF_ABLATE) && (FDF_ABLATE & 64)  // timing experiment: stage 2 without the candidate push
+        if (m == 0xdeadbeefu) queue[0] = (uint16_t)m;
+        continue;
+#endif
+        if (m != 0u) {
+            const uint32_t cnt = (uint32_t)__popc(m);
+            const uint32_t slot = atomicAdd(qcount, cnt);
+            if (slot + cnt <= (uint32_t)kQueueCap) push_candidates(e, m, queue, slot);
+        }
+    }
 #endif
 #else
     (void)lane_or_minus1;
+    uint32_t hprev = 0u;
     for (int lane = 0; lane < 32; lane++) {
         const int q = lane & 15, rr0 = (2 * warp + (lane >> 4)) * BH;
-        const uint32_t need = stage1_band<BH>(tile, rr0, q, kbias) & live_mask(g, rr0, BH, row_lo, row_hi);
+        const Stage1Masks s1 = stage1_band<BH>(tile, rr0, q, kbias);
+        const uint32_t need = s1.v & (s1.h | (q == 0 ? 0u : hprev)) & live_mask(g, rr0, BH, row_lo, row_hi);
+        hprev = s1.h;
         for (int i = 0; i < BH; i++)
             if ((need >> i) & 1u) wq[n++] = (uint16_t)(((rr0 + i) << 4) | q);
     }
-    for (uint32_t i = 0; i < n; i++) stage2_entry(wq[i], tile, vtab, kbias, queue, qcount);
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t m = stage2_mask(wq[i], tile, vtab, inside, kbias);
+        const uint32_t cnt = (uint32_t)popc32(m);
+        if (cnt != 0u) {
+            const uint32_t slot = atomic_add_u32(qcount, cnt);
+            if (slot + cnt <= (uint32_t)kQueueCap) push_candidates(wq[i], m, queue, slot);
+        }
+    }
 #endif
 }
 
@@ -230,41 +305,57 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
 // (dense fallback): no list.
 // On the device the 32 lanes of a warp call it together (lane >= 0); the host emulator calls it once per thread
 // with lane = -1.
-template <int MODE, int SR>
+template <int MODE, int SR, int U = 1>
 FDF_HD void phase_b(int tid, int lane, int nthreads, uint32_t qn, const uint8_t *tile, const uint16_t *queue,
                     uint16_t *klist, uint32_t *kcount, uint16_t *plane, int t, int n, uint32_t tag) {
     const int l = lane < 0 ? 0 : lane;
-    for (uint32_t ib = (uint32_t)(tid - l); ib < qn; ib += (uint32_t)nthreads) {  // (warp-uniform trip count)
-        const uint32_t i = ib + (uint32_t)l;
-        const bool valid = i < qn;
-        const uint32_t ent = queue[valid ? i : ib];
-        const int rr = (int)(ent >> 9);
-        const int j = (int)((ent >> 5) & 15u) * 16 + mask_bit_to_px((int)(ent & 31u));
-        const uint8_t *pc = tile + (rr + 3) * kTileW + j;
-        const uint32_t bias = dual_bias((int)pc[0]);
-        RingDual ring;
+    // U queue entries per thread and step, as separate load / arithmetic / store sections, so that their dependency
+    // chains interleave (the test warps are few; a single chain leaves them waiting on shared-memory latency)
+    for (uint32_t ib = (uint32_t)(tid - l); ib < qn; ib += (uint32_t)(U * nthreads)) {  // (warp-uniform trip count)
+        RingDual ring[U];
+        uint32_t pos[U];
+        bool valid[U];
 #pragma unroll
-        for (int k = 0; k < 16; k++) ring.w[k] = dual_word((uint32_t)pc[FDF_RING_DY(k) * kTileW + FDF_RING_DX(k)], bias);
-        const uint32_t best = best_of_lanes(best_window(ring, n));
-        const bool kp = valid && best > (uint32_t)(256 + t);
-        uint32_t sc = 1u;  // Off mode: the plane only records "keypoint here" (used by the dense fallback)
-        if (MODE == NMS_MAX_THRESHOLD) sc = best - 256u;                  // (garbage unless kp)
-        if (MODE == NMS_SUM_ABSOLUTE) sc = score_sum_abs_dual(ring, t);  // <= 4080 < 2^12
-        const uint32_t pos = (uint32_t)((rr << 8) | j);
-        if (kp) plane[rr * kPlaneW + j - kPlaneLead] = (uint16_t)((tag << 12) | sc);
-#if defined(__CUDA_ARCH__)
-        if (klist != nullptr) {
-            const uint32_t b = __ballot_sync(0xffffffffu, kp);
-            if (b != 0u) {
-                uint32_t base = 0u;
-                if (lane == 0) base = atomicAdd(kcount, (uint32_t)__popc(b));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (kp) klist[base + (uint32_t)__popc(b & ((1u << lane) - 1u))] = (uint16_t)pos;
-            }
+        for (int u = 0; u < U; u++) {
+            const uint32_t i = ib + (uint32_t)(u * nthreads) + (uint32_t)l;
+            valid[u] = i < qn;
+            const uint32_t ent = queue[valid[u] ? i : ib];
+            const int rr = (int)(ent >> 9);
+            const int j = (int)((ent >> 5) & 15u) * 16 + mask_bit_to_px((int)(ent & 31u));
+            pos[u] = (uint32_t)((rr << 8) | j);
+            const uint8_t *pc = tile + (rr + 3) * kTileW + j;
+            const uint32_t bias = dual_bias((int)pc[0]);
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                ring[u].w[k] = dual_word((uint32_t)pc[FDF_RING_DY(k) * kTileW + FDF_RING_DX(k)], bias);
         }
+        bool kp[U];
+        uint32_t sc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t best = best_of_lanes(best_window(ring[u], n));
+            kp[u] = valid[u] && best > (uint32_t)(256 + t);
+            sc[u] = 1u;  // Off mode: the plane only records "keypoint here" (used by the dense fallback)
+            if (MODE == NMS_MAX_THRESHOLD) sc[u] = best - 256u;                     // (garbage unless kp)
+            if (MODE == NMS_SUM_ABSOLUTE) sc[u] = score_sum_abs_dual(ring[u], t);  // <= 4080 < 2^12
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (kp[u]) plane[(pos[u] >> 8) * kPlaneW + (pos[u] & 0xffu) - kPlaneLead] = (uint16_t)((tag << 12) | sc[u]);
+#if defined(__CUDA_ARCH__)
+            if (klist != nullptr) {
+                const uint32_t b = __ballot_sync(0xffffffffu, kp[u]);
+                if (b != 0u) {
+                    uint32_t base = 0u;
+                    if (lane == 0) base = atomicAdd(kcount, (uint32_t)__popc(b));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (kp[u]) klist[base + (uint32_t)__popc(b & ((1u << lane) - 1u))] = (uint16_t)pos[u];
+                }
+            }
 #else
-        if (klist != nullptr && kp) klist[(*kcount)++] = (uint16_t)pos;
+            if (klist != nullptr && kp[u]) klist[(*kcount)++] = (uint16_t)pos[u];
 #endif
+        }
     }
 }
 

@@ -54,7 +54,7 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
             const uint32_t *vt = vtab[vtab_variant(c, NC)];
             qcount = 0;
             for (int warp = 0; warp < kFilterWarps; warp++)
-                phase_a_warp<MODE, SR, kFilterWarps>(warp, -1, tile, wq.data(), vt, queue.data(), &qcount, g, kbias, 0, SR);
+                phase_a_warp<MODE, SR, kFilterWarps>(warp, -1, tile, wq.data(), vt, vtab_variant(c, NC), queue.data(), &qcount, g, kbias, 0, SR);
             const uint32_t qn = qcount;
             if (tag == 1u && gc != 0u) std::fill(plane.begin(), plane.end(), (uint16_t)0);
             if (qn <= (uint32_t)kQueueCap) {
@@ -73,7 +73,7 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
                 for (int lo = 0; lo < SR; lo += kGroupRows) {
                     qcount = 0;
                     for (int warp = 0; warp < kFallbackWarps; warp++)
-                        phase_a_warp<MODE, SR, kFallbackWarps>(warp, -1, tile, wq.data(), vt, queue.data(), &qcount, g, kbias, lo,
+                        phase_a_warp<MODE, SR, kFallbackWarps>(warp, -1, tile, wq.data(), vt, vtab_variant(c, NC), queue.data(), &qcount, g, kbias, lo,
                                                            lo + kGroupRows);
                     if (qcount > (uint32_t)kQueueCap) return -18;
                     for (int tid = 0; tid < kTestThreads; tid++)
