@@ -138,9 +138,15 @@ FDF_HD Stage1Masks stage1_band(const uint8_t *tile, int rr0, int q, uint32_t kbi
             for (int k = 0; k < 4; k++) d[i - 3].w[k] = absdiff4(row[i].w[k], row[i - 3].w[k]);
         }
         if (i >= 6) {  // centre = tile row i - 3: north difference d[i - 6], south difference d[i - 3]
-            uint32_t o = 0u, oh = 0u;
+            // "some centre of the group has a north or south difference > t" is only needed per group, and stage 2
+            // repeats the test per pixel: so OR the eight difference words first and threshold once.  A byte of the OR
+            // is >= every byte that went into it, so no exceeding difference is lost; the OR of two differences <= t
+            // can exceed t, which only sends a few more groups to stage 2 (18.8 % instead of 18.5 % at t = 20).
+            uint32_t x = d[i - 6].w[0] | d[i - 3].w[0];
 #pragma unroll
-            for (int k = 0; k < 4; k++) o |= exceeds4(d[i - 6].w[k] | d[i - 3].w[k], kbias);
+            for (int k = 1; k < 4; k++) x |= d[i - 6].w[k] | d[i - 3].w[k];
+            const uint32_t o = exceeds4(x, kbias);
+            uint32_t oh = 0u;
             if ((o & 0x80808080u) != 0u) m.v |= 1u << (i - 6);
 #if !defined(FDF_STAGE1_H)  // the horizontal group test below is a measured loss (1.077 vs 1.039 ms per 256 frames: its
                             // dense work costs more than the stage-2 entries it saves), so it is off by default
@@ -249,6 +255,7 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
     if (q == 0) hl = 0u;  // (tile columns 0 .. 15: the centres that count start at column 11, their x - 3 is in the group)
     const uint32_t need = s1.v & (s1.h | hl) & live_mask(g, rr0, BH, row_lo, row_hi);
     const uint32_t ent = (uint32_t)((rr0 << 4) | q);
+#if !defined(FDF_WQ_SCAN)  // one ballot per row (default)
 #pragma unroll
     for (int i = 0; i < BH; i++) {
         const bool mine = (need >> i) & 1u;
@@ -256,6 +263,30 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
         if (mine) wq[n + (uint32_t)__popc(b & lt)] = (uint16_t)(ent + (uint32_t)(i << 4));
         n += (uint32_t)__popc(b);
     }
+#else
+    {   // timing experiment: warp prefix sum of the lanes' row counts, then every lane writes its own rows.  Fewer
+        // instructions (~45 instead of ~80 per lane) but measured 16 % SLOWER (1.193 vs 1.029 ms per 256 frames): the
+        // five dependent shuffles sit on the filter warps' critical path and the lane-major entry order makes the
+        // stage-2 row loads of a quarter-warp hit the same banks.
+        (void)lt;
+        const uint32_t cnt = (uint32_t)__popc(need);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, dd);
+            if (lane >= dd) incl += v;
+        }
+        n = __shfl_sync(0xffffffffu, incl, 31);
+        uint16_t *out = wq + (incl - cnt);
+#pragma unroll
+        for (int i = 0; i < BH; i++) {
+            if ((need >> i) & 1u) {
+                *out = (uint16_t)(ent + (uint32_t)(i << 4));
+                out++;
+            }
+        }
+    }
+#endif
     __syncwarp();
 #if !(defined(FDF_ABLATE) && (FDF_ABLATE & 32))  // timing experiment: stage 1 only
     // stage 2, one lane per queued group.  When the queue is full the entries are dropped but still counted:
@@ -331,10 +362,54 @@ FDF_HD void phase_b(int tid, int lane, int nthreads, uint32_t qn, const uint8_t 
         }
         bool kp[U];
         uint32_t sc[U];
+#if defined(FDF_EXP_LOADS) || defined(FDF_EXP_ALU)  // sensitivity experiments: extra shared-memory loads / extra logic-pipe work
+        uint32_t dummy = 0u;
+#endif
+#if defined(FDF_EXP_LOADS)
+        {
+            const uint32_t ent = queue[valid[0] ? ib + (uint32_t)l : ib];
+            const uint8_t *pc = tile + ((int)(ent >> 9) + 3) * kTileW + (int)((ent >> 5) & 15u) * 16 + mask_bit_to_px((int)(ent & 31u));
+#pragma unroll
+            for (int k = 0; k < 16; k++) dummy += pc[FDF_RING_DY(k) * kTileW + FDF_RING_DX((k + 5) & 15)];
+        }
+#endif
+#if defined(FDF_EXP_ALU)
+        {
+#if FDF_EXP_ALU == 1   // one dependent chain of 48 logic-pipe instructions (+ 48 XORs)
+            uint32_t x = ring[0].w[0];
+#pragma unroll
+            for (int k = 0; k < 48; k++) x = min3_u16x2(x ^ ring[0].w[k & 15], ring[0].w[(k + 3) & 15], ring[0].w[(k + 7) & 15]);
+            dummy += x;
+#elif FDF_EXP_ALU == 2  // 96 logic-pipe instructions in 16 independent chains
+            uint32_t x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = ring[0].w[k];
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int k = 0; k < 16; k++) x[k] = min3_u16x2(x[k] ^ ring[0].w[(k + r) & 15], ring[0].w[(k + 3) & 15], ring[0].w[(k + 7 + r) & 15]);
+#pragma unroll
+            for (int k = 0; k < 16; k++) dummy ^= x[k];
+#else                   // 96 multiply-adds in 16 independent chains
+            uint32_t x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = ring[0].w[k];
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int k = 0; k < 16; k++) x[k] = x[k] * ring[0].w[(k + r + 1) & 15] + ring[0].w[(k + 7 + r) & 15];
+#pragma unroll
+            for (int k = 0; k < 16; k++) dummy ^= x[k];
+#endif
+        }
+#endif
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint32_t best = best_of_lanes(best_window(ring[u], n));
             kp[u] = valid[u] && best > (uint32_t)(256 + t);
+#if defined(FDF_EXP_LOADS) || defined(FDF_EXP_ALU)
+            if (dummy == 0x7654321u) kp[u] = !kp[u];
+#endif
             sc[u] = 1u;  // Off mode: the plane only records "keypoint here" (used by the dense fallback)
             if (MODE == NMS_MAX_THRESHOLD) sc[u] = best - 256u;                     // (garbage unless kp)
             if (MODE == NMS_SUM_ABSOLUTE) sc[u] = score_sum_abs_dual(ring[u], t);  // <= 4080 < 2^12
