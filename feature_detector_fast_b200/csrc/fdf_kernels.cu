@@ -164,7 +164,7 @@ struct Layout {
     static constexpr int klist_off = queue_off + queue_bytes;           // keypoint list of the chunk being tested
     static constexpr int klist_bytes = kQueueCap * 2;
     static constexpr int wq_off = klist_off + klist_bytes;              // filter warps' stage-1 -> stage-2 queues
-    static constexpr int wq_bytes = kFilterWarps * kWarpQueueCap * 2;
+    static constexpr int wq_bytes = 4 * kWarpQueueCap * 2;  // (a filter warp looks at 32 * SR / (2 kFilterWarps) <= 1024 / kFilterWarps groups)
     static constexpr int vtab_off = wq_off + wq_bytes;                  // validity tables: first / middle / last chunk
     static constexpr int vtab_bytes = 3 * kVtabWords * 4;
     static constexpr int misc_off = vtab_off + vtab_bytes;
@@ -395,7 +395,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
 
     if (is_filter) {
         // ================================ filter warps =================================================
-        uint16_t *wq = wqs + warp * kWarpQueueCap;
+        uint16_t *wq = wqs + warp * (4 * kWarpQueueCap / kFilterWarps);
         FDF_CLK_BEGIN
         for (uint32_t it = 0; cur < total_items; it++) {
             const uint32_t frame = cur / p.strips_per_frame;
@@ -799,7 +799,7 @@ size_t detect_smem_bytes(int mode, int sr) {
     const size_t tile = (size_t)tile_rows(sr) * kTileW;
     (void)mode;
     const size_t plane = (size_t)sr * kPlaneW * 2;
-    const size_t queues = (size_t)(kQueueBufs + 1) * kQueueCap * 2, wq = (size_t)kFilterWarps * kWarpQueueCap * 2;
+    const size_t queues = (size_t)(kQueueBufs + 1) * kQueueCap * 2, wq = (size_t)4 * kWarpQueueCap * 2;
     return (size_t)kTileStages * tile + plane + queues + wq + (size_t)3 * kVtabWords * 4 + 192;
 }
 

@@ -12,7 +12,10 @@ namespace fdf {
 #ifndef FDF_TEST_WARPS
 #define FDF_TEST_WARPS 6
 #endif
-constexpr int kFilterWarps = 4;     // warps 0 .. 3 run phase A (dense filter), the others everything per candidate
+#ifndef FDF_FILTER_WARPS
+#define FDF_FILTER_WARPS 4
+#endif
+constexpr int kFilterWarps = FDF_FILTER_WARPS;  // warps 0 .. 3 run phase A (dense filter), the others everything per candidate
 constexpr int kTestWarps = FDF_TEST_WARPS;
 constexpr int kComputeWarps = kFilterWarps + kTestWarps;
 constexpr int kThreads = kComputeWarps * 32;           // threads per CTA of the detection kernel

@@ -242,7 +242,7 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
                          int variant, uint16_t *queue, uint32_t *qcount, const ChunkGeo &g, uint32_t kbias, int row_lo,
                          int row_hi) {
     constexpr int BH = SR / (2 * NW);
-    static_assert(BH * 32 <= kWarpQueueCap, "a warp queue must hold every group stage 1 looks at");
+    static_assert(BH * 32 * NW <= 4 * kWarpQueueCap, "a warp queue must hold every group stage 1 looks at");
     uint32_t n = 0u;  // entries in wq (warp-uniform)
     // groups 2 .. 14 of a chunk are all-valid unless it is the last chunk of its row (variant 2)
     const uint32_t inside = variant == 2 ? 0u : 1u;

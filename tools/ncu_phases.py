@@ -30,9 +30,9 @@ def func_of(fn, ln):
     return None
 
 HELPERS = {"max3u", "mad32", "absdiff4", "byte_perm", "popc32", "highest_set_bit", "swap16", "min_u16x2", "max_u16x2",
-           "min3_u16x2", "max3_u16x2", "addrelu_s16x2", "exceeds4", "load16", "atomic_add_u32", "atomic_or_u32",
+           "min3_u16x2", "max3_u16x2", "addrelu_s16x2", "exceeds4", "dual_word", "dual_bias", "best_of_lanes", "load16", "atomic_add_u32", "atomic_or_u32",
            "lowest_set_bit", "live_score", "filter_kbias", "mask_bit_to_px", "smem_u32"}
-PHASE = {"vertical_any": "A1 stage1", "stage1_lane": "A1 stage1", "candidate_mask16": "A2 stage2", "stage2_entry": "A2 stage2",
+PHASE = {"vertical_any": "A1 stage1", "stage1_lane": "A1 stage1", "candidate_mask16": "A2 stage2", "stage2_entry": "A2 stage2", "stage2_mask": "A2 stage2", "push_candidates": "A2 push", "best_window": "B test", "best_window_k": "B test", "score_sum_abs_dual": "B score",
          "phase_a_warp": "A1 stage1", "ring_masks": "B test", "has_arc": "B test", "phase_b": "B test",
          "score_max_threshold": "B score", "max_of_extended": "B score", "score_sum_abs": "B score",
          "nms_emits": "NMS+stage", "nms_is_max": "NMS+stage", "emit_list": "NMS+stage", "nms_dense": "NMS+stage",
