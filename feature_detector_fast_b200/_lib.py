@@ -56,6 +56,10 @@ def load_library() -> C.CDLL:
     lib.fdf_detect_batch.argtypes = [vp, vp, u32, u32, u32, u32, u64, u8, u8, u8, vp, sz, vp]
     lib.fdf_detect_device.restype = C.c_int
     lib.fdf_detect_device.argtypes = [vp, vp, u32, u32, u32, u32, u64, u8, u8, u8, vp, sz, vp, vp]
+    lib.fdf_rgb8_to_luma8_device.restype = C.c_int
+    lib.fdf_rgb8_to_luma8_device.argtypes = [vp, vp, u32, u32, u32, u32, u64, vp, u32, u64, vp]
+    lib.fdf_detect_rgb8.restype = C.c_int
+    lib.fdf_detect_rgb8.argtypes = [vp, vp, u32, u32, u32, u8, u8, u8, vp, sz, C.POINTER(sz)]
     lib.fdf_synth_frames_device.restype = C.c_int
     lib.fdf_synth_frames_device.argtypes = [vp, vp, u32, u32, u32, u32, u64, u64, u32, u32, u32, vp]
     lib.fdf_kernel_launches.restype = u64

@@ -119,6 +119,23 @@ class Detector:
             _raise(self._lib, self._ctx, st)
         return buf[: n.value].copy()
 
+    def detect_rgb8_array(self, rgb, config: Config, cap: Optional[int] = None) -> np.ndarray:
+        """fdf_detect_rgb8 (main.rs:53-67: to_rgb8 -> to_luma8 -> detect) on an (H, W, 3) uint8 array."""
+        a = np.ascontiguousarray(np.asarray(rgb))
+        if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+            raise TypeError("rgb must be an (H, W, 3) uint8 array")
+        h, w, _ = a.shape
+        worst = max(0, w - 6) * max(0, h - 6)
+        cap = worst if cap is None else int(cap)
+        buf = self._scratch(max(cap, 1))
+        n = C.c_size_t(0)
+        st = self._lib.fdf_detect_rgb8(self._ctx, a.ctypes.data, w, h, a.strides[0], int(config.threshold),
+                                       int(config.count), int(config.non_maximal_supression), buf.ctypes.data, cap,
+                                       C.byref(n))
+        if st != 0:
+            _raise(self._lib, self._ctx, st)
+        return buf[: n.value].copy()
+
     def detect_batch(self, frames: np.ndarray, config: Config, cap: Optional[int] = None,
                      out: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
         """fdf_detect_batch over a C-contiguous (F, H, W) uint8 array: (points (K, 2), offsets (F+1,))."""
@@ -171,6 +188,23 @@ class Detector:
         if st != 0:
             _raise(self._lib, self._ctx, st)
         return points, offsets
+
+    def rgb8_to_luma8_device(self, rgb, out=None, stream=None):
+        """fdf_rgb8_to_luma8_device: CUDA uint8 (F, H, W, 3) -> (F, H, Wp) luma view of width W, row stride a multiple
+        of 16 bytes (ready for detect_device)."""
+        import torch
+
+        if rgb.dtype != torch.uint8 or rgb.dim() != 4 or rgb.shape[3] != 3 or not rgb.is_cuda or not rgb.is_contiguous():
+            raise TypeError("rgb must be a contiguous CUDA uint8 tensor of shape (F, H, W, 3)")
+        f, h, w, _ = rgb.shape
+        if out is None:
+            out = torch.empty((f, h, (w + 15) // 16 * 16), dtype=torch.uint8, device=rgb.device)[:, :, :w]
+        s = stream if stream is not None else torch.cuda.current_stream(rgb.device)
+        st = self._lib.fdf_rgb8_to_luma8_device(self._ctx, rgb.data_ptr(), f, w, h, rgb.stride(1), rgb.stride(0),
+                                                out.data_ptr(), out.stride(1), out.stride(0), s.cuda_stream)
+        if st != 0:
+            _raise(self._lib, self._ctx, st)
+        return out
 
     def synth_frames(self, n_frames: int, w: int, h: int, seed: int, first_frame: int = 0, kind: int = 0,
                      amp: int = 4, out=None, device=None):

@@ -58,6 +58,7 @@ struct fdf_ctx {
     DeviceBuffer<uint8_t> workspace;            // tickets | flags | cursor | scan status | per-strip count/dst | run records
     DeviceBuffer<uint32_t> staging;             // per-chunk unordered runs of (row << 16 | x) before the gather
     DeviceBuffer<uint8_t> staged_frames;        // host-path input staging (pitched to 16 bytes)
+    DeviceBuffer<uint8_t> staged_rgb;           // fdf_detect_rgb8: the RGB image before the luma conversion
     DeviceBuffer<fdf_point> staged_points;      // host-path output staging
     DeviceBuffer<unsigned long long> staged_offsets;
     unsigned long long *pinned_offsets = nullptr;
@@ -174,6 +175,7 @@ void fdf_destroy(fdf_ctx *ctx) {
     ctx->workspace.release();
     ctx->staging.release();
     ctx->staged_frames.release();
+    ctx->staged_rgb.release();
     ctx->staged_points.release();
     ctx->staged_offsets.release();
     if (ctx->pinned_offsets) cudaFreeHost(ctx->pinned_offsets);
@@ -428,6 +430,65 @@ fdf_status fdf_detect(fdf_ctx *ctx, const uint8_t *img, uint32_t w, uint32_t h, 
                                      offsets);
     if (st == FDF_OK || st == FDF_ERR_CAPACITY) *n_out = (size_t)offsets[1];
     return st;
+}
+
+fdf_status fdf_rgb8_to_luma8_device(fdf_ctx *ctx, const uint8_t *d_rgb, uint32_t n_frames, uint32_t w, uint32_t h,
+                                    uint32_t rgb_pitch, uint64_t rgb_frame_stride, uint8_t *d_luma,
+                                    uint32_t luma_pitch, uint64_t luma_frame_stride, void *stream_handle) {
+    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
+    if (n_frames == 0 || w == 0 || h == 0) return FDF_OK;
+    if (!d_rgb || !d_luma) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null image pointer");
+    if ((uint64_t)rgb_pitch < 3ull * w || luma_pitch < w)
+        return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "pitch smaller than one row (rgb %u, luma %u, width %u)", rgb_pitch,
+                    luma_pitch, w);
+    if (n_frames > 1 && (rgb_frame_stride < (uint64_t)rgb_pitch * h || luma_frame_stride < (uint64_t)luma_pitch * h))
+        return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "frame stride smaller than one frame");
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_handle);  // NULL = the default stream
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    FDF_CUDA(ctx, fdf::launch_luma(d_rgb, n_frames, w, h, rgb_pitch, rgb_frame_stride, d_luma, luma_pitch,
+                                   luma_frame_stride, stream));
+    ctx->launches += 1;
+    return FDF_OK;
+}
+
+fdf_status fdf_detect_rgb8(fdf_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, uint32_t rgb_pitch,
+                           uint8_t threshold, uint8_t count, uint8_t nms, fdf_point *out, size_t cap,
+                           size_t *n_out) {
+    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
+    if (!n_out) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null n_out");
+    *n_out = 0;
+    fdf_status st = check_config(ctx, count, nms);
+    if (st != FDF_OK) return st;
+    if (!out && cap > 0) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null output pointer");
+    if (w < 7 || h < 7) return FDF_OK;
+    if (!rgb) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null image pointer");
+    if ((uint64_t)rgb_pitch < 3ull * w) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "rgb_pitch %u < 3 * width", rgb_pitch);
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t dpitch = (w + 15u) & ~15u, rpitch = (3u * w + 3u) & ~3u;
+    const size_t worst = (size_t)(w - 6) * (size_t)(h - 6), dcap = cap < worst ? cap : worst;
+    FDF_CUDA(ctx, ctx->staged_rgb.reserve((size_t)rpitch * h));
+    FDF_CUDA(ctx, ctx->staged_frames.reserve((size_t)dpitch * h));
+    FDF_CUDA(ctx, ctx->staged_points.reserve(dcap ? dcap : 1));
+    FDF_CUDA(ctx, ctx->staged_offsets.reserve(4));
+    FDF_CUDA(ctx, cudaMemcpy2DAsync(ctx->staged_rgb.ptr, rpitch, rgb, rgb_pitch, 3u * (size_t)w, h, cudaMemcpyHostToDevice,
+                                    ctx->stream));
+    st = fdf_rgb8_to_luma8_device(ctx, ctx->staged_rgb.ptr, 1, w, h, rpitch, (uint64_t)rpitch * h, ctx->staged_frames.ptr,
+                                  dpitch, (uint64_t)dpitch * h, ctx->stream);
+    if (st != FDF_OK) return st;
+    st = fdf_detect_device(ctx, ctx->staged_frames.ptr, 1, w, h, dpitch, (uint64_t)dpitch * h, threshold, count, nms,
+                           ctx->staged_points.ptr, dcap, reinterpret_cast<uint64_t *>(ctx->staged_offsets.ptr), ctx->stream);
+    if (st != FDF_OK) return st;
+    unsigned long long offs[2] = {0, 0};
+    uint32_t flags = 0;
+    FDF_CUDA(ctx, cudaMemcpyAsync(offs, ctx->staged_offsets.ptr, sizeof(offs), cudaMemcpyDeviceToHost, ctx->stream));
+    FDF_CUDA(ctx, cudaMemcpyAsync(&flags, ctx->workspace.ptr + 4, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+    FDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = (size_t)offs[1];
+    if (flags) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x", flags);
+    const size_t ncopy = offs[1] < dcap ? (size_t)offs[1] : dcap;
+    if (ncopy) FDF_CUDA(ctx, cudaMemcpy(out, ctx->staged_points.ptr, ncopy * sizeof(fdf_point), cudaMemcpyDeviceToHost));
+    if (offs[1] > cap) return fail(ctx, FDF_ERR_CAPACITY, "%llu keypoints found, capacity %zu", offs[1], cap);
+    return FDF_OK;
 }
 
 #ifdef FDF_PHASE_CLOCKS

@@ -758,6 +758,45 @@ __global__ void fdf_synth_kernel(uint8_t *frames, uint32_t n_frames, uint32_t w,
     }
 }
 
+// ---- RGB8 -> luma8: the step in front of the path (main.rs:53-58 `image::open(..).to_rgb8()` then `.to_luma8()`) ----
+// image 0.24.6 (Cargo.lock:388-390, not vendored): luma = (2126 r + 7152 g + 722 b) / 10000 in u32, truncating
+// (color.rs: SRGB_LUMA = [2126, 7152, 722], SRGB_LUMA_DIV = 10000), which is the identity for r == g == b.
+// HBM-bound (3 bytes read, 1 written per pixel): one thread converts four pixels, 12 bytes in as three words when the
+// row is word-aligned, one word out.
+__device__ __forceinline__ uint32_t luma_of(uint32_t r, uint32_t g, uint32_t b) {
+    return (2126u * r + 7152u * g + 722u * b) / 10000u;
+}
+
+__global__ void fdf_luma_kernel(const uint8_t *rgb, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t rgb_pitch,
+                                unsigned long long rgb_stride, uint8_t *luma, uint32_t luma_pitch,
+                                unsigned long long luma_stride) {
+    const unsigned long long w4 = (w + 3u) / 4u;
+    const unsigned long long total = (unsigned long long)n_frames * h * w4;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(rgb) | rgb_pitch | rgb_stride) & 3u) == 0u &&
+                         ((reinterpret_cast<uintptr_t>(luma) | luma_pitch | luma_stride) & 3u) == 0u;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t x4 = (uint32_t)(i % w4);
+        const uint32_t y = (uint32_t)((i / w4) % h);
+        const uint32_t f = (uint32_t)(i / (w4 * h));
+        const uint8_t *src = rgb + (size_t)f * rgb_stride + (size_t)y * rgb_pitch + (size_t)x4 * 12u;
+        uint8_t *dst = luma + (size_t)f * luma_stride + (size_t)y * luma_pitch + (size_t)x4 * 4u;
+        if (aligned && x4 * 4u + 4u <= w) {
+            const uint32_t a = reinterpret_cast<const uint32_t *>(src)[0];  // r0 g0 b0 r1
+            const uint32_t b = reinterpret_cast<const uint32_t *>(src)[1];  // g1 b1 r2 g2
+            const uint32_t c = reinterpret_cast<const uint32_t *>(src)[2];  // b2 r3 g3 b3
+            const uint32_t l0 = luma_of(a & 0xffu, (a >> 8) & 0xffu, (a >> 16) & 0xffu);
+            const uint32_t l1 = luma_of(a >> 24, b & 0xffu, (b >> 8) & 0xffu);
+            const uint32_t l2 = luma_of((b >> 16) & 0xffu, b >> 24, c & 0xffu);
+            const uint32_t l3 = luma_of((c >> 8) & 0xffu, (c >> 16) & 0xffu, c >> 24);
+            *reinterpret_cast<uint32_t *>(dst) = l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
+        } else {
+            for (uint32_t k = 0; k < 4u && x4 * 4u + k < w; k++)
+                dst[k] = (uint8_t)luma_of(src[3 * k], src[3 * k + 1], src[3 * k + 2]);
+        }
+    }
+}
+
 #ifdef FDF_PHASE_CLOCKS
 }  // namespace
 cudaError_t read_phase_clocks(unsigned long long out[256]) {
@@ -845,6 +884,18 @@ cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream) {
     unsigned long long grid = (unsigned long long)sms * (unsigned)per_sm;
     if (grid > items) grid = items;
     fdf_gather_kernel<<<(unsigned)grid, kGatherThreads, smem, stream>>>(p, (uint32_t)items);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_luma(const uint8_t *d_rgb, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t rgb_pitch,
+                        unsigned long long rgb_stride, uint8_t *d_luma, uint32_t luma_pitch,
+                        unsigned long long luma_stride, cudaStream_t stream) {
+    const unsigned long long total = (unsigned long long)n_frames * h * ((w + 3u) / 4u);
+    if (total == 0) return cudaSuccess;
+    unsigned long long blocks = (total + 255ull) / 256ull;
+    if (blocks > 148ull * 32ull) blocks = 148ull * 32ull;  // grid-stride: a multiple of the SM count
+    fdf_luma_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_rgb, n_frames, w, h, rgb_pitch, rgb_stride, d_luma, luma_pitch,
+                                                          luma_stride);
     return cudaGetLastError();
 }
 

@@ -101,6 +101,11 @@ cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const Detec
 cudaError_t launch_scan(const DetectParams &p, cudaStream_t stream);
 cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream);
 
+// RGB8 (interleaved, 3 bytes per pixel) -> luma8 with the `image` crate's integer weights (main.rs:53-58).
+cudaError_t launch_luma(const uint8_t *d_rgb, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t rgb_pitch,
+                        unsigned long long rgb_stride, uint8_t *d_luma, uint32_t luma_pitch,
+                        unsigned long long luma_stride, cudaStream_t stream);
+
 cudaError_t launch_synth(uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t pitch,
                          unsigned long long frame_stride, unsigned long long seed, uint32_t first_frame,
                          uint32_t kind, uint32_t amp, cudaStream_t stream);

@@ -96,6 +96,27 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
                              uint8_t count, uint8_t nms, fdf_point *d_out, size_t cap,
                              uint64_t *d_offsets, void *stream);
 
+/*
+ * The step in front of the path in the reference's CLI: `image::open(path).to_rgb8()` followed by
+ * `DynamicImage::ImageRgb8(..).to_luma8()` (main.rs:53-58).  Interleaved RGB8 in DEVICE memory -> luma8 in
+ * DEVICE memory, enqueued on `stream`: luma = (2126 r + 7152 g + 722 b) / 10000, integer, truncating -- the
+ * weights of image 0.24.6 (Cargo.lock:388-390; the crate is not vendored in the reference checkout, so this
+ * conversion is pinned only by "identity for r == g == b", which the shipped grey PNG confirms).
+ * Give luma_pitch / luma_frame_stride as multiples of 16 to pass the result straight to fdf_detect_device.
+ */
+fdf_status fdf_rgb8_to_luma8_device(fdf_ctx *ctx, const uint8_t *d_rgb, uint32_t n_frames, uint32_t w, uint32_t h,
+                                    uint32_t rgb_pitch, uint64_t rgb_frame_stride, uint8_t *d_luma,
+                                    uint32_t luma_pitch, uint64_t luma_frame_stride, void *stream);
+
+/*
+ * main.rs:53-67 in one call: an interleaved RGB8 image in HOST memory (h rows of 3 w bytes, rgb_pitch bytes
+ * between rows) is copied to the device, converted to luma there and run through the detector.  Same output
+ * contract as fdf_detect.
+ */
+fdf_status fdf_detect_rgb8(fdf_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, uint32_t rgb_pitch,
+                           uint8_t threshold, uint8_t count, uint8_t nms, fdf_point *out, size_t cap,
+                           size_t *n_out);
+
 /* Fills device memory with the synthetic frames used by the tests and the benchmark (bit-identical
  * to oracle/fdf_oracle.c: fdf_oracle_synth_frame).  Frame f of the output is generator frame
  * first_frame + f.  kind 0 = scene, 1 = uniform noise; amp = noise amplitude of kind 0. */

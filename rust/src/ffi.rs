@@ -61,6 +61,34 @@ extern "C" {
         d_offsets: *mut u64,
         stream: *mut c_void,
     ) -> c_int;
+    /// main.rs:53-58 `to_rgb8()` + `to_luma8()` on device memory (include/fdf.h: fdf_rgb8_to_luma8_device)
+    pub fn fdf_rgb8_to_luma8_device(
+        ctx: *mut fdf_ctx,
+        d_rgb: *const u8,
+        n_frames: u32,
+        w: u32,
+        h: u32,
+        rgb_pitch: u32,
+        rgb_frame_stride: u64,
+        d_luma: *mut u8,
+        luma_pitch: u32,
+        luma_frame_stride: u64,
+        stream: *mut core::ffi::c_void,
+    ) -> c_int;
+    /// main.rs:53-67 in one call on a host RGB8 image (include/fdf.h: fdf_detect_rgb8)
+    pub fn fdf_detect_rgb8(
+        ctx: *mut fdf_ctx,
+        rgb: *const u8,
+        w: u32,
+        h: u32,
+        rgb_pitch: u32,
+        threshold: u8,
+        count: u8,
+        nms: u8,
+        out: *mut fdf_point,
+        cap: usize,
+        n_out: *mut usize,
+    ) -> c_int;
     pub fn fdf_last_error(ctx: *const fdf_ctx) -> *const c_char;
     pub fn fdf_status_string(status: c_int) -> *const c_char;
 }

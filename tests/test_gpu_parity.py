@@ -308,3 +308,49 @@ def test_host_batch_is_pipelined_in_sub_batches(detector, oracle_mod, monkeypatc
     with pytest.raises(fdf.FdfError) as ei:
         detector.detect_batch(frames, _cfg(16, 9, 1), out=small)
     assert ei.value.status == 4  # FDF_ERR_CAPACITY
+
+
+# ---- the step in front of the path: RGB8 -> luma8 (main.rs:53-58), fdf_rgb8_to_luma8_device / fdf_detect_rgb8 ----
+def _luma_restated(rgb: np.ndarray) -> np.ndarray:
+    """image 0.24.6 `to_luma8`: (2126 r + 7152 g + 722 b) / 10000 in u32, truncating (restated; the crate is not vendored)."""
+    r, g, b = (rgb[..., i].astype(np.uint32) for i in range(3))
+    return ((2126 * r + 7152 * g + 722 * b) // 10000).astype(np.uint8)
+
+
+def test_rgb8_to_luma8_device_matches_the_restated_weights(detector):
+    import torch
+
+    rng = np.random.default_rng(11)
+    for (f, h, w) in [(1, 9, 7), (2, 33, 61), (1, 40, 128), (3, 17, 250)]:
+        rgb = rng.integers(0, 256, (f, h, w, 3), dtype=np.uint8)
+        rgb[0, 0, 0] = (255, 255, 255)
+        rgb[0, 0, 1] = (0, 0, 0)
+        got = detector.rgb8_to_luma8_device(torch.from_numpy(rgb).cuda())
+        assert got.stride(1) % 16 == 0
+        assert np.array_equal(got.cpu().numpy(), _luma_restated(rgb)), (f, h, w)
+    # unaligned source rows (a view into a wider buffer): the byte path of the kernel
+    wide = torch.from_numpy(rng.integers(0, 256, (1, 20, 71, 3), dtype=np.uint8)).cuda()
+    view = wide[:, :, 1:66, :]
+    got = detector.rgb8_to_luma8_device(view.contiguous())
+    assert np.array_equal(got.cpu().numpy(), _luma_restated(view.cpu().numpy()))
+
+
+def test_detect_rgb8_is_detect_of_the_luma_image(detector, golden, oracle_mod):
+    import feature_detector_fast_b200 as fdf
+
+    grey = golden["grey"]
+    # r == g == b: the conversion is the identity (what the shipped PNG exercises), so the golden lists must come out
+    rgb = np.repeat(grey[:, :, None], 3, axis=2)
+    assert same_points(detector.detect_rgb8_array(rgb, fdf.Config(16, 9, fdf.NonMaximalSuppression.Off)), golden["rust_off"])
+    assert same_points(detector.detect_rgb8_array(rgb, fdf.Config(16, 9, fdf.NonMaximalSuppression.MaxThreshold)),
+                       golden["rust_nonmax"])
+    # a colour image: same as the oracle on the restated luma
+    rng = np.random.default_rng(5)
+    base = oracle_mod.synth_frame(333, 97, 3, 0, 0, 4).astype(np.int16)
+    col = np.stack([np.clip(base + rng.integers(-30, 30, base.shape), 0, 255) for _ in range(3)], axis=2).astype(np.uint8)
+    luma = _luma_restated(col)
+    for nms in (0, 1, 2):
+        cfg = fdf.Config(12, 9, fdf.NonMaximalSuppression(nms))
+        assert same_points(detector.detect_rgb8_array(col, cfg), oracle_mod.detect(luma, 12, 9, nms)), nms
+    with pytest.raises(fdf.FdfPanic):
+        detector.detect_rgb8_array(col, fdf.Config(12, 8, fdf.NonMaximalSuppression.Off))

@@ -30,6 +30,12 @@ __device__ __forceinline__ void op(uint32_t &a, uint32_t b, uint32_t c) {
     if (OP == 17) asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(a) : "r"(b), "r"(c));
     if (OP == 18) asm volatile("vmin2.s32.s32.s32 %0, %0, %1, %2;" : "+r"(a) : "r"(b), "r"(0u));
     if (OP == 19) asm volatile("{.reg .pred p; setp.ne.u32 p, %0, %1; @p add.u32 %0, %0, %2;}" : "+r"(a) : "r"(b), "r"(c));
+    if (OP == 20) a = __vimin3_u16x2(a, b, c);               // VIMNMX3.U16x2
+    if (OP == 21) a = __vminu2(a, b);                        // VIMNMX.U16x2
+    if (OP == 22) a = __viaddmax_s16x2_relu(a, b, c);        // VIADDMNMX.S16x2.RELU
+    if (OP == 23) a = __vimax3_u32(a, b, c);                 // VIMNMX3.U32
+    if (OP == 24) a = __dp4a(a, b, c);                       // IDP.4A
+    if (OP == 25) a = (uint32_t)__viaddmax_s32((int)a, (int)b, (int)c);  // VIADDMNMX
 }
 
 template <int OPA, int OPB>
@@ -88,6 +94,15 @@ int main() {
     run<10, -1>("SHR imm", out, cyc);
     run<6, -1>("VIMNMX3 (min3)", out, cyc);
     run<18, -1>("vmin2 (VIMNMX.S16x2)", out, cyc);
+    run<20, -1>("VIMNMX3.U16x2", out, cyc);
+    run<21, -1>("VIMNMX.U16x2", out, cyc);
+    run<22, -1>("VIADDMNMX.S16x2.RELU", out, cyc);
+    run<23, -1>("VIMNMX3.U32", out, cyc);
+    run<24, -1>("IDP.4A", out, cyc);
+    run<25, -1>("VIADDMNMX.S32", out, cyc);
+    run<20, 2>("VIMNMX3.U16x2 + IMAD", out, cyc);
+    run<24, 0>("IDP.4A + LOP3", out, cyc);
+    run<24, 2>("IDP.4A + IMAD", out, cyc);
     run<7, -1>("POPC", out, cyc);
     run<8, -1>("FLO (bfind)", out, cyc);
     run<11, -1>("IMAD.HI", out, cyc);
