@@ -336,10 +336,19 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
 // (dense fallback): no list.
 // On the device the 32 lanes of a warp call it together (lane >= 0); the host emulator calls it once per thread
 // with lane = -1.
-template <int MODE, int SR, int U = 1>
+// `tile_done()` is called exactly once per call, warp-uniformly, as soon as this thread has read everything it needs
+// from the tile and the candidate queue (after the loads of its last step): the kernel uses it to request the next
+// tile before the arithmetic of the last step instead of after it.
+struct NoTileDone {
+    FDF_HD void operator()() const {}
+};
+
+template <int MODE, int SR, int U = 1, class TileDone = NoTileDone>
 FDF_HD void phase_b(int tid, int lane, int nthreads, uint32_t qn, const uint8_t *tile, const uint16_t *queue,
-                    uint16_t *klist, uint32_t *kcount, uint16_t *plane, int t, int n, uint32_t tag) {
+                    uint16_t *klist, uint32_t *kcount, uint16_t *plane, int t, int n, uint32_t tag,
+                    TileDone tile_done = TileDone()) {
     const int l = lane < 0 ? 0 : lane;
+    bool told = false;
     // U queue entries per thread and step, as separate load / arithmetic / store sections, so that their dependency
     // chains interleave (the test warps are few; a single chain leaves them waiting on shared-memory latency)
     for (uint32_t ib = (uint32_t)(tid - l); ib < qn; ib += (uint32_t)(U * nthreads)) {  // (warp-uniform trip count)
@@ -359,6 +368,10 @@ FDF_HD void phase_b(int tid, int lane, int nthreads, uint32_t qn, const uint8_t 
 #pragma unroll
             for (int k = 0; k < 16; k++)
                 ring[u].w[k] = dual_word((uint32_t)pc[FDF_RING_DY(k) * kTileW + FDF_RING_DX(k)], bias);
+        }
+        if (ib + (uint32_t)(U * nthreads) >= qn) {  // (warp-uniform) the last step: the ring words are in registers
+            tile_done();
+            told = true;
         }
         bool kp[U];
         uint32_t sc[U];
@@ -432,6 +445,7 @@ FDF_HD void phase_b(int tid, int lane, int nthreads, uint32_t qn, const uint8_t 
 #endif
         }
     }
+    if (!told) tile_done();  // (no step at all)
 }
 
 // ---- NMS: strict maximum over the 8 neighbours (replaces fast_simd.rs:588-616) -------------------
