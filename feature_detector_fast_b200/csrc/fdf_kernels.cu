@@ -125,6 +125,14 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, 
         : "memory");
 }
 
+// TMA: prefetch a tile into L2 only (no shared memory, no completion): the later load of the same box then hits L2
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap *tmap, int x, int y, int z) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
@@ -146,6 +154,9 @@ __device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned l
 #endif
 #ifndef FDF_TILE_STAGES
 #define FDF_TILE_STAGES 2
+#endif
+#ifndef FDF_L2_PREFETCH
+#define FDF_L2_PREFETCH 1
 #endif
 constexpr int kTileStages = FDF_TILE_STAGES;  // tile buffers per CTA: the tile of chunk k + kTileStages is requested when
                                               // phase B of chunk k is done, so TMA latency (~1700 cycles under load)
@@ -358,6 +369,10 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
 #endif
         mbar_expect_tx(&full_bar[stage], (uint32_t)L::tile_bytes);
         tma_load_3d(tiles + stage * L::tile_bytes, &tmap, c * kChunkW - kTileLead, ty0, (int)frame, &full_bar[stage]);
+        // and pull the strip's next tile into L2 (cp.async.bulk.prefetch.tensor: no shared memory, no completion), so
+        // that its load, one chunk from now, is an L2 hit (+1 %; 2 or 4 chunks ahead measured no better)
+        if (FDF_L2_PREFETCH > 0 && c + FDF_L2_PREFETCH < NC)
+            tma_prefetch_l2_3d(&tmap, (c + FDF_L2_PREFETCH) * kChunkW - kTileLead, ty0, (int)frame);
     };
 
     if (t0) {
