@@ -207,8 +207,61 @@ def run_reference_arm(args, rank):
     return 0
 
 
+def run_criterion(args, rank):
+    """benches/benchmark.rs restated: the crate's three criterion functions -- simd_t16_c_9_off /
+    _max_threshold / _sum_abs, one 1920x1080 frame per iteration -- timed criterion-style (warm-up, then samples;
+    mean and a 95 % confidence interval of the mean) for one arm: `--impl b200` = one fdf_detect call per iteration
+    through the C ABI with HOST buffers (copies included), `--impl reference` = the CPU port on one thread.
+    Prints one JSON line per function.  The reference's published numbers (README.md:55-65, i7-4770TE, its private
+    1080p screenshot): 5.34 / 8.71 / 7.23 ms."""
+    if rank != 0:
+        return 0
+    import math
+
+    import numpy as np
+
+    import oracle  # (synthetic frame generator; the CPU arm also times the port -- bench.py's CPU-baseline role)
+
+    oracle.build()
+    w, h = 1920, 1080
+    frame = oracle.synth_frame(w, h, SEED, 0, 0, 4)
+    pad = np.zeros(frame.size + 64, np.uint8)
+    pad[: frame.size] = frame.reshape(-1)
+    frame = pad[: frame.size].reshape(h, w)
+    names = {0: "simd_t16_c_9_off", 1: "simd_t16_c_9_max_threshold", 2: "simd_t16_c_9_sum_abs"}
+    if args.impl == "b200":
+        import feature_detector_fast_b200 as fdf
+
+        det = fdf.Detector(0)
+        run = lambda nms: len(det.detect_array(frame, fdf.Config(16, 9, fdf.NonMaximalSuppression(nms))))
+    else:
+        run = lambda nms: len(oracle.port_detect(frame, 16, 9, nms))
+    for nms, name in names.items():
+        t_end = time.perf_counter() + 1.0  # warm-up
+        while time.perf_counter() < t_end:
+            found = run(nms)
+        samples = []
+        t_end = time.perf_counter() + 4.0
+        while len(samples) < 100 or (time.perf_counter() < t_end and len(samples) < 2000):
+            t0 = time.perf_counter()
+            run(nms)
+            samples.append((time.perf_counter() - t0) * 1e3)
+        mean = sum(samples) / len(samples)
+        sd = math.sqrt(sum((x - mean) ** 2 for x in samples) / (len(samples) - 1))
+        half = 1.96 * sd / math.sqrt(len(samples))
+        print(json.dumps({"criterion": name, "impl": args.impl, "unit": "ms per 1920x1080 frame",
+                          "ci95": [round(mean - half, 4), round(mean, 4), round(mean + half, 4)],
+                          "samples": len(samples), "keypoints": found, "mpix_per_s": round(w * h / mean / 1e3, 1),
+                          "data": "synthetic 1080p scene frame (the reference's screenshot is not shipped)",
+                          "api": "fdf_detect, host buffers" if args.impl == "b200" else "CPU port of fast_simd.rs, 1 thread"}),
+              flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--criterion", action="store_true",
+                    help="benches/benchmark.rs protocol (three 1080p single-frame functions) instead of the batch workload")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
@@ -222,6 +275,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.criterion:
+        return run_criterion(args, rank)
     if args.impl == "reference":
         return run_reference_arm(args, rank)
 
