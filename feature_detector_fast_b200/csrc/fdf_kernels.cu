@@ -263,6 +263,23 @@ __device__ unsigned long long g_phase_clocks[16 * 16];  // [warp][slot]
 //       the chunk's keypoint list, barrier, and the last warp copies the survivors to the staging buffer
 //       while the others already wait for chunk k + 1.
 // A landed tile k + 2 implies that chunk k - 1 is completely done, hence that queue (k + 2) % 3 is free again.
+// Timing experiment (-DFDF_QFULL_BAR): queue hand-off filter -> test warps on a hardware named barrier (ids 4 ..): the
+// filter warps only ARRIVE, the test warps SYNC, i.e. they block in hardware instead of polling an mbarrier (the q_full
+// polls are 15 % of all executed instructions).  Measured 1.9 % SLOWER (1.035 vs 1.015 ms per 256 frames): the polls
+// use issue slots nobody else wants, and a polled wait is left sooner than a named barrier.  Default: mbarrier.
+__device__ __forceinline__ void qfull_arrive(uint32_t qb) {  // (immediate barrier ids: a register id reserves all 16)
+    if (qb == 0u) asm volatile("bar.arrive 4, %0;" ::"n"(kThreads) : "memory");
+    else if (qb == 1u) asm volatile("bar.arrive 5, %0;" ::"n"(kThreads) : "memory");
+    else if (qb == 2u) asm volatile("bar.arrive 6, %0;" ::"n"(kThreads) : "memory");
+    else asm volatile("bar.arrive 7, %0;" ::"n"(kThreads) : "memory");
+}
+__device__ __forceinline__ void qfull_sync(uint32_t qb) {
+    if (qb == 0u) asm volatile("bar.sync 4, %0;" ::"n"(kThreads) : "memory");
+    else if (qb == 1u) asm volatile("bar.sync 5, %0;" ::"n"(kThreads) : "memory");
+    else if (qb == 2u) asm volatile("bar.sync 6, %0;" ::"n"(kThreads) : "memory");
+    else asm volatile("bar.sync 7, %0;" ::"n"(kThreads) : "memory");
+}
+
 __device__ __forceinline__ void bar_test_group() {
     asm volatile("bar.sync 1, %0;" ::"n"(kTestThreads) : "memory");
 }
@@ -439,7 +456,11 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                                                      &qcount[qb], g, kbias, 0, SR);
 #endif
                 __syncwarp();
+#ifndef FDF_QFULL_BAR
                 if (lane == 0) mbar_arrive(&q_full[qb]);
+#else
+                qfull_arrive(qb);
+#endif
                 FDF_CLK(1)
                 if (++qb == (uint32_t)kQueueBufs) {
                     qb = 0;
@@ -483,7 +504,11 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                 clear_plane(ttid, kTestThreads);
                 bar_test_group();
             }
+#ifndef FDF_QFULL_BAR
             mbar_wait(&q_full[qb], qpar, p.flags, s_abort);
+#else
+            qfull_sync(qb);
+#endif
             mbar_wait(&full_bar[stage], qpar, p.flags, s_abort);  // (completed long ago: makes the tile visible here too)
             FDF_CLK(4)
             const uint32_t qn = qcount[qb];
