@@ -354,3 +354,45 @@ def test_detect_rgb8_is_detect_of_the_luma_image(detector, golden, oracle_mod):
         assert same_points(detector.detect_rgb8_array(col, cfg), oracle_mod.detect(luma, 12, 9, nms)), nms
     with pytest.raises(fdf.FdfPanic):
         detector.detect_rgb8_array(col, fdf.Config(12, 8, fdf.NonMaximalSuppression.Off))
+
+
+def test_config5_full_size_properties(detector):
+    """BASELINE config 5 at its FULL size (512 resident 3840x2160 frames, t=20, n=9, MaxThreshold; 4.2 GB of pixels,
+    ~9.5 M keypoints): too big for the oracle, so size-independent properties are checked on the device --
+    (1) CSR offsets are non-decreasing and end at the number of points written; (2) every frame's list is strictly
+    increasing in (y, x), i.e. row-major and duplicate-free, with centres inside the NMS emit range; (3) detection is
+    a pure function of the frame: the 256 frames that a second batch (generator frames 256..767) shares with the
+    first one (0..511) give identical lists at different positions of the batch; (4) a second run is bit-identical."""
+    import torch
+
+    F, W, H = 512, 3840, 2160
+    cfg = _cfg(20, 9, 1)
+    a = detector.synth_frames(F, W, H, seed=99, first_frame=0, kind=0, amp=4)
+    pts_a, offs_a = detector.detect_device(a, cfg, points=torch.empty((F * 60000, 2), dtype=torch.int32, device="cuda"))
+    torch.cuda.synchronize()
+    assert detector.device_flags() == 0
+    offs_a = offs_a.clone()
+    total = int(offs_a[-1])
+    assert 0 < total <= pts_a.shape[0]
+    assert int(offs_a[0]) == 0 and bool((offs_a[1:] >= offs_a[:-1]).all())
+    p = pts_a[:total].to(torch.int64)
+    frame_of = torch.searchsorted(offs_a[1:].contiguous(), torch.arange(total, device="cuda"), right=True)
+    key = (frame_of * H + p[:, 1]) * W + p[:, 0]
+    assert bool((key[1:] > key[:-1]).all())  # row-major inside each frame, frames in order, no duplicates
+    assert int(p[:, 0].min()) >= 3 and int(p[:, 0].max()) < W - 3 and int(p[:, 1].min()) >= 4 and int(p[:, 1].max()) <= H - 5
+    first = pts_a[:total].clone()
+    del a, p, key, frame_of
+    # (3) the same frames at other batch positions
+    b = detector.synth_frames(F, W, H, seed=99, first_frame=256, kind=0, amp=4)
+    pts_b, offs_b = detector.detect_device(b, cfg, points=torch.empty((F * 60000, 2), dtype=torch.int32, device="cuda"))
+    torch.cuda.synchronize()
+    assert detector.device_flags() == 0
+    lo_a, hi_a = int(offs_a[256]), int(offs_a[512])
+    hi_b = int(offs_b[256])
+    assert hi_a - lo_a == hi_b
+    assert bool((offs_a[256:] - offs_a[256] == offs_b[:257]).all())
+    assert torch.equal(first[lo_a:hi_a], pts_b[:hi_b])
+    # (4) idempotence
+    pts_c, offs_c = detector.detect_device(b, cfg, points=torch.empty((F * 60000, 2), dtype=torch.int32, device="cuda"))
+    torch.cuda.synchronize()
+    assert torch.equal(offs_b, offs_c) and torch.equal(pts_b[: int(offs_b[-1])], pts_c[: int(offs_c[-1])])
