@@ -539,7 +539,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
 #endif
                 FDF_CLK(5)
                 bar_test_group();  // every score of this chunk is in the plane and its keypoint list is complete
-#ifndef FDF_EARLY_TILE_REQUEST
+#if !defined(FDF_EARLY_TILE_REQUEST) && !defined(FDF_LATE_TILE_REQUEST)
                 if (t0) {
                     qcount[qb] = 0u;
                     request_tile(c + ahead, gc + (uint32_t)ahead, it);
@@ -551,6 +551,12 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
 #endif
                 FDF_CLK(7)
                 bar_test_group();  // the run is complete; the keypoint list is free
+#ifdef FDF_LATE_TILE_REQUEST  // timing experiment: the filter group gets its next tile only after the NMS pass
+                if (t0) {
+                    qcount[qb] = 0u;
+                    request_tile(c + ahead, gc + (uint32_t)ahead, it);
+                }
+#endif
                 if (t0) {
                     const uint32_t count = *scount;
                     *scount = 0u;
