@@ -209,6 +209,9 @@ FDF_HD uint32_t candidate_mask16(const Px16 &c, const Px16 &n, const Px16 &s, ui
 FDF_HD int mask_bit_to_px(int p) { return 4 * (7 - (p & 7)) + (p >> 3); }
 
 // ---- exact segment test on 2 x 16-bit lanes ----------------------------------------------------------
+// (ring_masks / has_arc / score_max_threshold / score_sum_abs below are the first-generation forms: the kernel now uses
+// the dual-word forms at the end of this file; these stay as an independent second implementation that
+// tests/host/strip_emulator.cpp::fdf_core_check compares against the oracle AND against the dual-word forms.)
 // The 16 ring pixels are held as 8 words  P[i] = ring[i] | ring[i + 8] << 16  (opposite pixels share a word).
 struct Ring2 {
     uint32_t p[8];

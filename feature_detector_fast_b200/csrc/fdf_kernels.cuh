@@ -43,10 +43,6 @@ constexpr unsigned long long kStageSlack = 1024ull * kStageBlock;  // what partl
 #ifndef FDF_TEST_UNROLL
 #define FDF_TEST_UNROLL 1
 #endif
-#ifndef FDF_EMIT_UNROLL
-#define FDF_EMIT_UNROLL 1
-#endif
-constexpr int kEmitUnroll = FDF_EMIT_UNROLL;  // same for the (short) NMS pass
 constexpr int kTestUnroll = FDF_TEST_UNROLL;  // queue entries a test thread works on at once (measured: 1 is best;
                                               // 2 / 3 interleave the dependency chains but cost registers and issue slots)
 constexpr int kWarpQueueCap = 256;  // 16-pixel groups one warp can pass from filter stage 1 to stage 2 per chunk
