@@ -396,3 +396,12 @@ def test_config5_full_size_properties(detector):
     pts_c, offs_c = detector.detect_device(b, cfg, points=torch.empty((F * 60000, 2), dtype=torch.int32, device="cuda"))
     torch.cuda.synchronize()
     assert torch.equal(offs_b, offs_c) and torch.equal(pts_b[: int(offs_b[-1])], pts_c[: int(offs_c[-1])])
+
+
+def test_very_wide_images_take_the_multi_round_gather(detector, oracle_mod):
+    """Widths beyond ~8000 pixels: more level-2 bitmap words than gather threads (several rounds of the block prefix
+    sum in fdf_gather_kernel), many chunks per strip (tag wrap, > 32 run records per strip)."""
+    for (w, h, kind, t) in [(9000, 41, 0, 16), (16001, 23, 0, 16), (12345, 70, 1, 60)]:
+        img = oracle_mod.synth_frame(w, h, seed=w, frame=0, kind=kind, amp=5)
+        for nms in (0, 1, 2):
+            assert same_points(detector.detect_array(img, _cfg(t, 9, nms)), oracle_mod.port_detect(img, t, 9, nms)), (w, h, nms)
