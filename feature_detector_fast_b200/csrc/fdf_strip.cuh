@@ -291,6 +291,23 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
 #if !(defined(FDF_ABLATE) && (FDF_ABLATE & 32))  // timing experiment: stage 1 only
     // stage 2, one lane per queued group.  When the queue is full the entries are dropped but still counted:
     // *qcount > kQueueCap tells the test warps to redo the chunk in row groups.
+#if defined(FDF_STAGE2_X2)  // timing experiment: two queued groups per lane and step (interleaved dependency chains)
+    for (uint32_t i = (uint32_t)lane; i < n; i += 64u) {
+        const bool two = i + 32u < n;
+        const uint32_t e0 = wq[i], e1 = wq[two ? i + 32u : i];
+        const uint32_t m0 = stage2_mask(e0, tile, vtab, inside, kbias);
+        uint32_t m1 = stage2_mask(e1, tile, vtab, inside, kbias);
+        if (!two) m1 = 0u;
+        const uint32_t c0 = (uint32_t)__popc(m0), c1 = (uint32_t)__popc(m1);
+        if (c0 + c1 != 0u) {
+            const uint32_t slot = atomicAdd(qcount, c0 + c1);
+            if (slot + c0 + c1 <= (uint32_t)kQueueCap) {
+                push_candidates(e0, m0, queue, slot);
+                push_candidates(e1, m1, queue, slot + c0);
+            }
+        }
+    }
+#else
     for (uint32_t i = (uint32_t)lane; i < n; i += 32u) {
         const uint32_t e = wq[i];
         const uint32_t m = stage2_mask(e, tile, vtab, inside, kbias);
@@ -304,6 +321,7 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
             if (slot + cnt <= (uint32_t)kQueueCap) push_candidates(e, m, queue, slot);
         }
     }
+#endif
 #endif
 #else
     (void)lane_or_minus1;
