@@ -145,6 +145,28 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-GPU runs: pin this rank to the CPUs that are local to its GPU (sysfs local_cpulist of the GPU's PCI
+    function) BEFORE the pinned host buffers are allocated, so that their pages sit on the GPU's NUMA node and the
+    end-to-end copies do not cross the socket interconnect.  Returns the cpu list it bound to, or None."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "%d cpus local to GPU %d" % (len(cpus), local_rank)
+    except Exception:
+        return None
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -295,6 +317,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     det = fdf.Detector(local_rank)
     cfg = fdf.Config(THRESHOLD, COUNT, fdf.NonMaximalSuppression.MaxThreshold)
     F = args.frames
@@ -397,7 +420,7 @@ def main():
         e2e = {"value": round(n_total * W * H * e2e_steps / dt / 1e6, 1), "unit": "Mpix/s",
                "h2d_bytes_per_step": F * W * H, "d2h_bytes_per_step": 8 * (F + 1) + 8 * found + 4,
                "steps": e2e_steps, "ms_per_step": round(dt / e2e_steps * 1e3, 3),
-               "api": "fdf_detect_batch (C ABI, pinned host buffers)"}
+               "api": "fdf_detect_batch (C ABI, pinned host buffers)", "host_placement": numa or "default"}
         del h_frames, h_points
 
     # ---- CPU baseline beside it (rank 0, N = 1 only), which also re-checks the GPU counts ---------------
