@@ -405,3 +405,30 @@ def test_very_wide_images_take_the_multi_round_gather(detector, oracle_mod):
         img = oracle_mod.synth_frame(w, h, seed=w, frame=0, kind=kind, amp=5)
         for nms in (0, 1, 2):
             assert same_points(detector.detect_array(img, _cfg(t, 9, nms)), oracle_mod.port_detect(img, t, 9, nms)), (w, h, nms)
+
+
+def test_randomised_shapes_contents_and_configs(detector, oracle_mod):
+    """Seeded fuzz: 500 random (width, height, content, threshold, count, mode) cases against the oracle's AVX2 port
+    (itself pinned to the scalar restatement in the CPU tier); every 10th case also against the scalar oracle."""
+    rng = np.random.default_rng(20261018)
+    for case in range(500):
+        w, h = int(rng.integers(7, 900)), int(rng.integers(7, 260))
+        style = case % 5
+        if style == 0:
+            img = rng.integers(0, 256, (h, w), dtype=np.uint8)                       # uniform noise (dense fallback)
+        elif style == 1:
+            img = oracle_mod.synth_frame(w, h, case, 0, 0, int(rng.integers(0, 12)))  # scene
+        elif style == 2:
+            img = (rng.integers(0, 2, (h, w)) * rng.integers(1, 256)).astype(np.uint8)  # two levels: exact score ties
+        elif style == 3:
+            img = np.clip(rng.normal(128, rng.integers(1, 60), (h, w)), 0, 255).astype(np.uint8)  # gaussian noise
+        else:
+            img = oracle_mod.synth_frame(w, h, case, 1, 0, 4)
+            img[:: int(rng.integers(2, 9)), :] = int(rng.integers(0, 256))            # scene with flat rows
+        t = int(rng.choice([0, 1, 2, 5, 10, 16, 20, 31, 64, 100, 127, 128, 129, 200, 254, 255]))
+        n, nms = int(rng.integers(9, 17)), int(rng.integers(0, 3))
+        got = detector.detect_array(img, _cfg(t, n, nms))
+        assert same_points(got, oracle_mod.port_detect(img, t, n, nms)), (case, w, h, style, t, n, nms)
+        if case % 10 == 0:
+            assert same_points(got, oracle_mod.detect(img, t, n, nms)), (case, w, h, style, t, n, nms)
+    assert detector.device_flags() == 0
