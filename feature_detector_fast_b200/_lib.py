@@ -58,6 +58,8 @@ def load_library() -> C.CDLL:
     lib.fdf_detect_device.argtypes = [vp, vp, u32, u32, u32, u32, u64, u8, u8, u8, vp, sz, vp, vp]
     lib.fdf_rgb8_to_luma8_device.restype = C.c_int
     lib.fdf_rgb8_to_luma8_device.argtypes = [vp, vp, u32, u32, u32, u32, u64, vp, u32, u64, vp]
+    lib.fdf_rgb8_to_grey_sum3_device.restype = C.c_int
+    lib.fdf_rgb8_to_grey_sum3_device.argtypes = [vp, vp, u32, u32, u32, u32, u64, vp, u32, u64, vp]
     lib.fdf_detect_rgb8.restype = C.c_int
     lib.fdf_detect_rgb8.argtypes = [vp, vp, u32, u32, u32, u8, u8, u8, vp, sz, C.POINTER(sz)]
     lib.fdf_synth_frames_device.restype = C.c_int

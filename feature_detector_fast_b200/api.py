@@ -189,9 +189,9 @@ class Detector:
             _raise(self._lib, self._ctx, st)
         return points, offsets
 
-    def rgb8_to_luma8_device(self, rgb, out=None, stream=None):
+    def rgb8_to_luma8_device(self, rgb, out=None, stream=None, sum3: bool = False):
         """fdf_rgb8_to_luma8_device: CUDA uint8 (F, H, W, 3) -> (F, H, Wp) luma view of width W, row stride a multiple
-        of 16 bytes (ready for detect_device)."""
+        of 16 bytes (ready for detect_device).  sum3=True: fdf_rgb8_to_grey_sum3_device, util.rs's (r + g + b) / 3."""
         import torch
 
         if rgb.dtype != torch.uint8 or rgb.dim() != 4 or rgb.shape[3] != 3 or not rgb.is_cuda or not rgb.is_contiguous():
@@ -200,8 +200,9 @@ class Detector:
         if out is None:
             out = torch.empty((f, h, (w + 15) // 16 * 16), dtype=torch.uint8, device=rgb.device)[:, :, :w]
         s = stream if stream is not None else torch.cuda.current_stream(rgb.device)
-        st = self._lib.fdf_rgb8_to_luma8_device(self._ctx, rgb.data_ptr(), f, w, h, rgb.stride(1), rgb.stride(0),
-                                                out.data_ptr(), out.stride(1), out.stride(0), s.cuda_stream)
+        fn = self._lib.fdf_rgb8_to_grey_sum3_device if sum3 else self._lib.fdf_rgb8_to_luma8_device
+        st = fn(self._ctx, rgb.data_ptr(), f, w, h, rgb.stride(1), rgb.stride(0), out.data_ptr(), out.stride(1),
+                out.stride(0), s.cuda_stream)
         if st != 0:
             _raise(self._lib, self._ctx, st)
         return out

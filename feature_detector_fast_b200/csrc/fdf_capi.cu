@@ -432,9 +432,10 @@ fdf_status fdf_detect(fdf_ctx *ctx, const uint8_t *img, uint32_t w, uint32_t h, 
     return st;
 }
 
-fdf_status fdf_rgb8_to_luma8_device(fdf_ctx *ctx, const uint8_t *d_rgb, uint32_t n_frames, uint32_t w, uint32_t h,
-                                    uint32_t rgb_pitch, uint64_t rgb_frame_stride, uint8_t *d_luma,
-                                    uint32_t luma_pitch, uint64_t luma_frame_stride, void *stream_handle) {
+namespace {
+fdf_status rgb_to_grey(fdf_ctx *ctx, const uint8_t *d_rgb, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t rgb_pitch,
+                       uint64_t rgb_frame_stride, uint8_t *d_luma, uint32_t luma_pitch, uint64_t luma_frame_stride,
+                       int kind, void *stream_handle) {
     if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
     if (n_frames == 0 || w == 0 || h == 0) return FDF_OK;
     if (!d_rgb || !d_luma) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null image pointer");
@@ -446,9 +447,24 @@ fdf_status fdf_rgb8_to_luma8_device(fdf_ctx *ctx, const uint8_t *d_rgb, uint32_t
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_handle);  // NULL = the default stream
     FDF_CUDA(ctx, cudaSetDevice(ctx->device));
     FDF_CUDA(ctx, fdf::launch_luma(d_rgb, n_frames, w, h, rgb_pitch, rgb_frame_stride, d_luma, luma_pitch,
-                                   luma_frame_stride, stream));
+                                   luma_frame_stride, kind, stream));
     ctx->launches += 1;
     return FDF_OK;
+}
+}  // namespace
+
+fdf_status fdf_rgb8_to_luma8_device(fdf_ctx *ctx, const uint8_t *d_rgb, uint32_t n_frames, uint32_t w, uint32_t h,
+                                    uint32_t rgb_pitch, uint64_t rgb_frame_stride, uint8_t *d_luma,
+                                    uint32_t luma_pitch, uint64_t luma_frame_stride, void *stream_handle) {
+    return rgb_to_grey(ctx, d_rgb, n_frames, w, h, rgb_pitch, rgb_frame_stride, d_luma, luma_pitch, luma_frame_stride, 0,
+                       stream_handle);
+}
+
+fdf_status fdf_rgb8_to_grey_sum3_device(fdf_ctx *ctx, const uint8_t *d_rgb, uint32_t n_frames, uint32_t w, uint32_t h,
+                                        uint32_t rgb_pitch, uint64_t rgb_frame_stride, uint8_t *d_grey,
+                                        uint32_t grey_pitch, uint64_t grey_frame_stride, void *stream_handle) {
+    return rgb_to_grey(ctx, d_rgb, n_frames, w, h, rgb_pitch, rgb_frame_stride, d_grey, grey_pitch, grey_frame_stride, 1,
+                       stream_handle);
 }
 
 fdf_status fdf_detect_rgb8(fdf_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_t h, uint32_t rgb_pitch,

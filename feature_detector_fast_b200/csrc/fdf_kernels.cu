@@ -831,10 +831,14 @@ __global__ void fdf_synth_kernel(uint8_t *frames, uint32_t n_frames, uint32_t w,
 // (color.rs: SRGB_LUMA = [2126, 7152, 722], SRGB_LUMA_DIV = 10000), which is the identity for r == g == b.
 // HBM-bound (3 bytes read, 1 written per pixel): one thread converts four pixels, 12 bytes in as three words when the
 // row is word-aligned, one word out.
+// kind 0: image 0.24.6 to_luma8 (above); kind 1: the crate's own util.rs:5-41 `Rgb8ToLuma16View` + `to_grey`:
+// the view's pixel is r + g + b as u16, to_grey stores (that / 3) as u8.
+template <int KIND>
 __device__ __forceinline__ uint32_t luma_of(uint32_t r, uint32_t g, uint32_t b) {
-    return (2126u * r + 7152u * g + 722u * b) / 10000u;
+    return KIND == 0 ? (2126u * r + 7152u * g + 722u * b) / 10000u : (r + g + b) / 3u;
 }
 
+template <int KIND>
 __global__ void fdf_luma_kernel(const uint8_t *rgb, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t rgb_pitch,
                                 unsigned long long rgb_stride, uint8_t *luma, uint32_t luma_pitch,
                                 unsigned long long luma_stride) {
@@ -853,14 +857,14 @@ __global__ void fdf_luma_kernel(const uint8_t *rgb, uint32_t n_frames, uint32_t 
             const uint32_t a = reinterpret_cast<const uint32_t *>(src)[0];  // r0 g0 b0 r1
             const uint32_t b = reinterpret_cast<const uint32_t *>(src)[1];  // g1 b1 r2 g2
             const uint32_t c = reinterpret_cast<const uint32_t *>(src)[2];  // b2 r3 g3 b3
-            const uint32_t l0 = luma_of(a & 0xffu, (a >> 8) & 0xffu, (a >> 16) & 0xffu);
-            const uint32_t l1 = luma_of(a >> 24, b & 0xffu, (b >> 8) & 0xffu);
-            const uint32_t l2 = luma_of((b >> 16) & 0xffu, b >> 24, c & 0xffu);
-            const uint32_t l3 = luma_of((c >> 8) & 0xffu, (c >> 16) & 0xffu, c >> 24);
+            const uint32_t l0 = luma_of<KIND>(a & 0xffu, (a >> 8) & 0xffu, (a >> 16) & 0xffu);
+            const uint32_t l1 = luma_of<KIND>(a >> 24, b & 0xffu, (b >> 8) & 0xffu);
+            const uint32_t l2 = luma_of<KIND>((b >> 16) & 0xffu, b >> 24, c & 0xffu);
+            const uint32_t l3 = luma_of<KIND>((c >> 8) & 0xffu, (c >> 16) & 0xffu, c >> 24);
             *reinterpret_cast<uint32_t *>(dst) = l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
         } else {
             for (uint32_t k = 0; k < 4u && x4 * 4u + k < w; k++)
-                dst[k] = (uint8_t)luma_of(src[3 * k], src[3 * k + 1], src[3 * k + 2]);
+                dst[k] = (uint8_t)luma_of<KIND>(src[3 * k], src[3 * k + 1], src[3 * k + 2]);
         }
     }
 }
@@ -957,13 +961,17 @@ cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream) {
 
 cudaError_t launch_luma(const uint8_t *d_rgb, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t rgb_pitch,
                         unsigned long long rgb_stride, uint8_t *d_luma, uint32_t luma_pitch,
-                        unsigned long long luma_stride, cudaStream_t stream) {
+                        unsigned long long luma_stride, int kind, cudaStream_t stream) {
     const unsigned long long total = (unsigned long long)n_frames * h * ((w + 3u) / 4u);
     if (total == 0) return cudaSuccess;
     unsigned long long blocks = (total + 255ull) / 256ull;
     if (blocks > 148ull * 32ull) blocks = 148ull * 32ull;  // grid-stride: a multiple of the SM count
-    fdf_luma_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_rgb, n_frames, w, h, rgb_pitch, rgb_stride, d_luma, luma_pitch,
-                                                          luma_stride);
+    if (kind == 0)
+        fdf_luma_kernel<0><<<(unsigned)blocks, 256, 0, stream>>>(d_rgb, n_frames, w, h, rgb_pitch, rgb_stride, d_luma,
+                                                                 luma_pitch, luma_stride);
+    else
+        fdf_luma_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(d_rgb, n_frames, w, h, rgb_pitch, rgb_stride, d_luma,
+                                                                 luma_pitch, luma_stride);
     return cudaGetLastError();
 }
 

@@ -97,10 +97,11 @@ cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const Detec
 cudaError_t launch_scan(const DetectParams &p, cudaStream_t stream);
 cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream);
 
-// RGB8 (interleaved, 3 bytes per pixel) -> luma8 with the `image` crate's integer weights (main.rs:53-58).
+// RGB8 (interleaved, 3 bytes per pixel) -> luma8: kind 0 = the `image` crate's integer weights (main.rs:53-58),
+// kind 1 = (r + g + b) / 3 as util.rs:5-41 (`Rgb8ToLuma16View::to_grey`) does.
 cudaError_t launch_luma(const uint8_t *d_rgb, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t rgb_pitch,
                         unsigned long long rgb_stride, uint8_t *d_luma, uint32_t luma_pitch,
-                        unsigned long long luma_stride, cudaStream_t stream);
+                        unsigned long long luma_stride, int kind, cudaStream_t stream);
 
 cudaError_t launch_synth(uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t pitch,
                          unsigned long long frame_stride, unsigned long long seed, uint32_t first_frame,

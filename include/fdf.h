@@ -109,6 +109,16 @@ fdf_status fdf_rgb8_to_luma8_device(fdf_ctx *ctx, const uint8_t *d_rgb, uint32_t
                                     uint32_t luma_pitch, uint64_t luma_frame_stride, void *stream);
 
 /*
+ * The crate's OWN grey conversion, util.rs:5-41 (`Rgb8ToLuma16View` + `to_grey`; main.rs:57 has it commented out):
+ * the view's pixel is r + g + b as u16 (util.rs:38-40) and to_grey stores that / 3 as u8 (util.rs:21-23).  Same
+ * layout contract as fdf_rgb8_to_luma8_device.  Unlike the image crate's weights this one is pinned by the
+ * reference's source.
+ */
+fdf_status fdf_rgb8_to_grey_sum3_device(fdf_ctx *ctx, const uint8_t *d_rgb, uint32_t n_frames, uint32_t w, uint32_t h,
+                                        uint32_t rgb_pitch, uint64_t rgb_frame_stride, uint8_t *d_grey,
+                                        uint32_t grey_pitch, uint64_t grey_frame_stride, void *stream);
+
+/*
  * main.rs:53-67 in one call: an interleaved RGB8 image in HOST memory (h rows of 3 w bytes, rgb_pitch bytes
  * between rows) is copied to the device, converted to luma there and run through the detector.  Same output
  * contract as fdf_detect.

@@ -75,6 +75,20 @@ extern "C" {
         luma_frame_stride: u64,
         stream: *mut core::ffi::c_void,
     ) -> c_int;
+    /// util.rs:5-41 `Rgb8ToLuma16View` + `to_grey`: (r + g + b) / 3 (include/fdf.h: fdf_rgb8_to_grey_sum3_device)
+    pub fn fdf_rgb8_to_grey_sum3_device(
+        ctx: *mut fdf_ctx,
+        d_rgb: *const u8,
+        n_frames: u32,
+        w: u32,
+        h: u32,
+        rgb_pitch: u32,
+        rgb_frame_stride: u64,
+        d_grey: *mut u8,
+        grey_pitch: u32,
+        grey_frame_stride: u64,
+        stream: *mut core::ffi::c_void,
+    ) -> c_int;
     /// main.rs:53-67 in one call on a host RGB8 image (include/fdf.h: fdf_detect_rgb8)
     pub fn fdf_detect_rgb8(
         ctx: *mut fdf_ctx,

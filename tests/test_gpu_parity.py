@@ -328,6 +328,10 @@ def test_rgb8_to_luma8_device_matches_the_restated_weights(detector):
         got = detector.rgb8_to_luma8_device(torch.from_numpy(rgb).cuda())
         assert got.stride(1) % 16 == 0
         assert np.array_equal(got.cpu().numpy(), _luma_restated(rgb)), (f, h, w)
+        # util.rs:5-41: Rgb8ToLuma16View pixel = r + g + b (u16), to_grey = that / 3 as u8
+        got3 = detector.rgb8_to_luma8_device(torch.from_numpy(rgb).cuda(), sum3=True)
+        want3 = (rgb.astype(np.uint16).sum(axis=3) // 3).astype(np.uint8)
+        assert np.array_equal(got3.cpu().numpy(), want3), (f, h, w)
     # unaligned source rows (a view into a wider buffer): the byte path of the kernel
     wide = torch.from_numpy(rng.integers(0, 256, (1, 20, 71, 3), dtype=np.uint8)).cuda()
     view = wide[:, :, 1:66, :]
