@@ -47,6 +47,11 @@ namespace fdf {
 cudaError_t read_phase_clocks(unsigned long long out[256]);
 }
 #endif
+#ifdef FDF_TRACE
+namespace fdf {
+cudaError_t read_trace(long long *out, size_t bytes);
+}
+#endif
 
 struct fdf_ctx {
     int device = 0;
@@ -148,15 +153,14 @@ fdf_status fdf_create(int device, fdf_ctx **out_ctx) {
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->back_stream, cudaStreamNonBlocking) != cudaSuccess) {
-        delete ctx;
+        fdf_destroy(ctx);  // (frees whichever streams were created)
         return FDF_ERR_CUDA;
     }
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
         qres != cudaDriverEntryPointSuccess) {
-        cudaStreamDestroy(ctx->stream);
-        delete ctx;
+        fdf_destroy(ctx);
         return FDF_ERR_CUDA;
     }
     ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
@@ -513,6 +517,16 @@ fdf_status fdf_debug_phase_clocks(fdf_ctx *ctx, uint64_t out[256]) {
     if (!ctx || !out) return FDF_ERR_INVALID_ARGUMENT;
     FDF_CUDA(ctx, cudaDeviceSynchronize());
     FDF_CUDA(ctx, fdf::read_phase_clocks(reinterpret_cast<unsigned long long *>(out)));
+    return FDF_OK;
+}
+#endif
+
+#ifdef FDF_TRACE
+// (debug builds only) the timeline table of the last launch: [cta 4][warp 16][chunk 200][slot 12] clock64 values
+fdf_status fdf_debug_trace(fdf_ctx *ctx, int64_t *out, size_t bytes) {
+    if (!ctx || !out) return FDF_ERR_INVALID_ARGUMENT;
+    FDF_CUDA(ctx, cudaDeviceSynchronize());
+    FDF_CUDA(ctx, fdf::read_trace(reinterpret_cast<long long *>(out), bytes));
     return FDF_OK;
 }
 #endif

@@ -45,9 +45,6 @@ constexpr unsigned long long kStatusAggregate = 1ull << 62;
 constexpr unsigned long long kStatusPrefix = 2ull << 62;
 constexpr unsigned long long kStatusValueMask = (1ull << 62) - 1ull;
 constexpr uint32_t kSpinLimit = 1u << 22;
-#ifndef FDF_WAIT_SLEEP_NS
-#define FDF_WAIT_SLEEP_NS 0
-#endif
 constexpr uint32_t kWaitHintNs = 100000u;  // mbarrier.try_wait suspend-time hint
 constexpr unsigned long long kWaitLimitNs = 4000000000ull;  // 4 s
 
@@ -71,48 +68,54 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// try_wait suspends the thread (no issue slots used) until the phase completes or the time hint (ns) runs out
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(kWaitHintNs)
-        : "memory");
-    return ok != 0;
-}
-
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 
+// Spins on mbarrier.try_wait (each probe suspends the thread in hardware until the phase completes or the time hint
+// runs out) for at most `rounds` probes: the loop is three instructions -- probe, branch out, count-and-branch back --
+// because waiting warps re-issue it all the time and every extra instruction in it is an issue slot (and a logic-pipe
+// slot) taken from the warps that work.  Returns true when the phase has completed.
+__device__ __forceinline__ bool mbar_spin(uint64_t *bar, uint32_t parity, uint32_t rounds) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, %3;\n"
+        "FDF_SPIN:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %4;\n"
+        "@p bra FDF_SPIN_DONE;\n"
+        "add.u32 n, n, -1;\n"
+        "setp.ne.u32 p, n, 0;\n"
+        "@p bra FDF_SPIN;\n"
+        "setp.ne.u32 p, n, n;\n"  // (gave up: p = false)
+        "FDF_SPIN_DONE:\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(rounds), "r"(kWaitHintNs)
+        : "memory");
+    return done != 0;
+}
+
 // Waits for the phase; a wait that lasts longer than kWaitLimitNs can only be a bug in the pipeline: it is turned
-// into an error flag (the host reports FDF_ERR_INTERNAL) instead of a hung GPU.
+// into an error flag (the host reports FDF_ERR_INTERNAL) instead of a hung GPU.  The clock and the CTA's abort flag
+// are looked at once per kSpinRounds probes only.
 // (`abort` is a flag in shared memory: once one wait of the CTA has timed out, no other wait of the CTA blocks, so
 // that the kernel still ends quickly.)
+constexpr uint32_t kSpinRounds = 4096u;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *flags, volatile uint32_t *abort) {
-    if (mbar_try_wait(bar, parity)) return;
-    unsigned long long t0 = 0ull;
-    for (uint32_t spins = 1;; spins++) {
-        if (mbar_try_wait(bar, parity)) return;
-#if FDF_WAIT_SLEEP_NS > 0
-        __nanosleep(FDF_WAIT_SLEEP_NS);  // the other warp group is busy: leave it the issue slots
-#endif
-        if ((spins & 63u) == 0u) {  // (rarely reached: a wait normally ends within a few rounds)
-            if (*abort != 0u) return;
-            const unsigned long long now = global_timer_ns();
-            if (t0 == 0ull) t0 = now;
-            if (now - t0 > kWaitLimitNs) {
-                atomicOr(flags, kFlagTmaTimeout);
-                *abort = 1u;
-                return;
-            }
+    if (mbar_spin(bar, parity, kSpinRounds)) return;
+    const unsigned long long t0 = global_timer_ns();
+    while (!mbar_spin(bar, parity, kSpinRounds)) {
+        if (*abort != 0u) return;
+        if (global_timer_ns() - t0 > kWaitLimitNs) {
+            atomicOr(flags, kFlagTmaTimeout);
+            *abort = 1u;
+            return;
         }
     }
 }
@@ -248,10 +251,26 @@ __device__ unsigned long long g_phase_clocks[16 * 16];  // [warp][slot]
     if (lane == 0)                                                                                \
         for (int i = 0; i < 10; i++)                                                              \
             if (clk_acc[i]) atomicAdd(&g_phase_clocks[warp * 16 + i], (unsigned long long)clk_acc[i]);
+#elif defined(FDF_TRACE)
+// Timeline trace (tools/trace_timeline.py builds the library with -DFDF_TRACE): the CTAs resident on SM 0 write
+// clock64() at every phase boundary of their first kTraceChunks chunks, per warp (lane 0), into a global table.
+constexpr int kTraceCtas = 4, kTraceChunks = 200, kTraceSlots = 12;
+__device__ long long g_trace[kTraceCtas][16][kTraceChunks][kTraceSlots];
+__device__ unsigned int g_trace_n;
+#define FDF_CLK_BEGIN
+#define FDF_CLK(slot)                                                                                           \
+    if (trace_cta >= 0 && lane == 0 && gc < (uint32_t)kTraceChunks) g_trace[trace_cta][warp][gc][slot] = clock64();
+#define FDF_CLK_END
 #else
 #define FDF_CLK_BEGIN
 #define FDF_CLK(slot)
 #define FDF_CLK_END
+#endif
+#ifdef FDF_TRACE
+#define FDF_TRACE_ROW \
+    ((trace_cta >= 0 && lane == 0 && gc < (uint32_t)kTraceChunks) ? &g_trace[trace_cta][warp][gc][0] : nullptr)
+#else
+#define FDF_TRACE_ROW nullptr
 #endif
 
 // ---- the detection kernel ----------------------------------------------------------------------
@@ -415,7 +434,22 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         for (int i = i0; i < L::plane_bytes / 16; i += n) pz[i] = make_uint4(0u, 0u, 0u, 0u);
     };
     clear_plane(tid, kThreads);
+#ifdef FDF_TRACE
+    volatile int &s_trace_cta = *reinterpret_cast<volatile int *>(smem + L::misc_off + 176);
+    if (tid == 0) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_trace_cta = -1;
+        if (smid == 0u) {
+            const unsigned int k = atomicAdd(&g_trace_n, 1u);
+            if (k < (unsigned)kTraceCtas) s_trace_cta = (int)k;
+        }
+    }
+#endif
     __syncthreads();
+#ifdef FDF_TRACE
+    const int trace_cta = s_trace_cta;
+#endif
     cur = s_ticket[0];
     if (t0)
         for (int c = 0; c < ahead; c++) request_tile(c, (uint32_t)c, 0u);  // (ahead <= NC: all of the first strip)
@@ -453,7 +487,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                 phase_a_warp<MODE, SR, kFilterWarps>(warp, lane, tiles + stage * L::tile_bytes, wq,
                                                      vtabs + vtab_variant(c, NC) * kVtabWords, vtab_variant(c, NC),
                                                      queues + qb * kQueueCap,
-                                                     &qcount[qb], g, kbias, 0, SR);
+                                                     &qcount[qb], g, kbias, 0, SR, FDF_TRACE_ROW);
 #endif
                 __syncwarp();
 #ifndef FDF_QFULL_BAR
@@ -539,12 +573,14 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
 #endif
                 FDF_CLK(5)
                 bar_test_group();  // every score of this chunk is in the plane and its keypoint list is complete
+                FDF_CLK(3)
 #if !defined(FDF_EARLY_TILE_REQUEST) && !defined(FDF_LATE_TILE_REQUEST)
                 if (t0) {
                     qcount[qb] = 0u;
                     request_tile(c + ahead, gc + (uint32_t)ahead, it);
                 }
 #endif
+                FDF_CLK(6)
 #if !(FDF_ABLATE & 2)
                 emit_list<MODE, SR>(ttid, kTestThreads, kcount[gc & 1u], klist, plane, scount, *s_base, p.staging_cap,
                                     p.staging, g);
@@ -868,6 +904,18 @@ __global__ void fdf_luma_kernel(const uint8_t *rgb, uint32_t n_frames, uint32_t 
         }
     }
 }
+
+#ifdef FDF_TRACE
+}  // namespace
+cudaError_t read_trace(long long *out, size_t bytes) {  // and resets the CTA counter for the next launch
+    if (bytes > sizeof(g_trace)) bytes = sizeof(g_trace);
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_trace, bytes);
+    if (e != cudaSuccess) return e;
+    const unsigned int zero = 0u;
+    return cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero));
+}
+namespace {
+#endif
 
 #ifdef FDF_PHASE_CLOCKS
 }  // namespace

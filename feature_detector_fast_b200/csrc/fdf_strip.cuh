@@ -240,7 +240,7 @@ FDF_HD void push_candidates(uint32_t e, uint32_t m, uint16_t *queue, uint32_t sl
 template <int MODE, int SR, int NW>
 FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint16_t *wq, const uint32_t *vtab,
                          int variant, uint16_t *queue, uint32_t *qcount, const ChunkGeo &g, uint32_t kbias, int row_lo,
-                         int row_hi) {
+                         int row_hi, long long *trace = nullptr) {
     constexpr int BH = SR / (2 * NW);
     static_assert(BH * 32 * NW <= 4 * kWarpQueueCap, "a warp queue must hold every group stage 1 looks at");
     uint32_t n = 0u;  // entries in wq (warp-uniform)
@@ -288,6 +288,9 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
     }
 #endif
     __syncwarp();
+#if defined(FDF_TRACE)
+    if (trace != nullptr) trace[9] = clock64();  // stage 1 done
+#endif
 #if !(defined(FDF_ABLATE) && (FDF_ABLATE & 32))  // timing experiment: stage 1 only
     // stage 2, one lane per queued group.  When the queue is full the entries are dropped but still counted:
     // *qcount > kQueueCap tells the test warps to redo the chunk in row groups.
@@ -325,6 +328,7 @@ FDF_HD void phase_a_warp(int warp, int lane_or_minus1, const uint8_t *tile, uint
 #endif
 #else
     (void)lane_or_minus1;
+    (void)trace;
     uint32_t hprev = 0u;
     for (int lane = 0; lane < 32; lane++) {
         const int q = lane & 15, rr0 = (2 * warp + (lane >> 4)) * BH;

@@ -12,6 +12,25 @@
 */
 pub mod ffi;
 
+// The reference's scalar specification and its drawing helpers stay in the crate exactly as they are
+// (reference `src/lib.rs:9-10`): `tests/compare.rs:1,49`, `benches/benchmark.rs:2` and `src/main.rs:1` import them.
+// The two files are the maintainer's own `src/opencv_compat.rs` and `src/util.rs`, unchanged; they are not
+// duplicated in this repository (this directory is an overlay on the reference tree).
+pub mod opencv_compat;
+pub mod util;
+
+/// Stands where the AVX2 module stood (reference `src/lib.rs:12-13`, `src/fast_simd.rs:847-859`), so that
+/// `tests/compare.rs:45` and `benches/benchmark.rs:25,36,47`, which call `fast_simd::detector` directly, build and
+/// run against the CUDA path unchanged.  No `target_feature = "avx2"` gate any more: the path needs a B200, not AVX2.
+pub mod fast_simd {
+    use crate::{Config, Point};
+
+    /// Same signature and results as the reference's `fast_simd::detector` (`src/fast_simd.rs:847`).
+    pub fn detector(image: &image::GrayImage, config: &Config) -> Vec<Point> {
+        crate::detect(image, config)
+    }
+}
+
 use std::cell::RefCell;
 use std::ffi::CStr;
 

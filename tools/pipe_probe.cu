@@ -36,6 +36,12 @@ __device__ __forceinline__ void op(uint32_t &a, uint32_t b, uint32_t c) {
     if (OP == 23) a = __vimax3_u32(a, b, c);                 // VIMNMX3.U32
     if (OP == 24) a = __dp4a(a, b, c);                       // IDP.4A
     if (OP == 25) a = (uint32_t)__viaddmax_s32((int)a, (int)b, (int)c);  // VIADDMNMX
+    // round 2: could the 16-bit-lane min/max of phase B run on the floating-point pipes instead of the logic pipe?
+    if (OP == 26) asm volatile("min.f16x2 %0, %0, %1;" : "+r"(a) : "r"(b));                       // HMNMX2
+    if (OP == 27) asm volatile("fma.rn.relu.f16x2 %0, %0, %1, %2;" : "+r"(a) : "r"(b), "r"(c));   // HFMA2.RELU
+    if (OP == 28) asm volatile("add.f16x2 %0, %0, %1;" : "+r"(a) : "r"(b));                       // HADD2
+    if (OP == 29) asm volatile("min.bf16x2 %0, %0, %1;" : "+r"(a) : "r"(b));                      // HMNMX2.BF16
+    if (OP == 30) asm volatile("{.reg .f32 t; min.f32 t, %0, %1; mov.b32 %0, t;}" : "+r"(a) : "r"(b));  // FMNMX
 }
 
 template <int OPA, int OPB>
@@ -103,6 +109,17 @@ int main() {
     run<20, 2>("VIMNMX3.U16x2 + IMAD", out, cyc);
     run<24, 0>("IDP.4A + LOP3", out, cyc);
     run<24, 2>("IDP.4A + IMAD", out, cyc);
+    run<26, -1>("HMNMX2 (min.f16x2)", out, cyc);
+    run<29, -1>("HMNMX2.BF16", out, cyc);
+    run<30, -1>("FMNMX", out, cyc);
+    run<27, -1>("HFMA2.RELU", out, cyc);
+    run<28, -1>("HADD2", out, cyc);
+    run<26, 0>("HMNMX2 + LOP3", out, cyc);
+    run<26, 2>("HMNMX2 + IMAD", out, cyc);
+    run<26, 20>("HMNMX2 + VIMNMX3.U16x2", out, cyc);
+    run<27, 0>("HFMA2.RELU + LOP3", out, cyc);
+    run<27, 2>("HFMA2.RELU + IMAD", out, cyc);
+    run<27, 13>("HFMA2.RELU + FFMA", out, cyc);
     run<7, -1>("POPC", out, cyc);
     run<8, -1>("FLO (bfind)", out, cyc);
     run<11, -1>("IMAD.HI", out, cyc);

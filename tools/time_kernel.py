@@ -32,6 +32,12 @@ for _ in range(a.steps):
 torch.cuda.synchronize()
 ms = [det.get_timing(i) for i in range(a.steps)]
 k = sum(m[0] for m in ms) / a.steps
+n_found = int(offs[-1])
+pl = pts[:n_found].long()
+idx = torch.arange(n_found, device="cuda", dtype=torch.int64)
+chk = int(((pl[:, 0] * 7919 + pl[:, 1] * 104729 + 1) * (idx % 65521 + 1)).sum().item()) & 0xFFFFFFFFFFFF  # order-sensitive
+tag = os.environ.get("FDF_LIB", "default").split("/")[-1]
+print(f"[{tag}] checksum {chk:012x} ", end="")
 print(f"frames {a.frames} nms {a.nms}: detect {k:.4f} ms  scan {sum(m[1] for m in ms) / a.steps:.4f}  gather "
       f"{sum(m[2] for m in ms) / a.steps:.4f}  -> {a.frames * a.w * a.h / k / 1e6:.1f} Gpix/s  found {int(offs[-1])}"
       f"  flags {det.device_flags()}")
