@@ -56,6 +56,17 @@ def load_library() -> C.CDLL:
     lib.fdf_detect_batch.argtypes = [vp, vp, u32, u32, u32, u32, u64, u8, u8, u8, vp, sz, vp]
     lib.fdf_detect_device.restype = C.c_int
     lib.fdf_detect_device.argtypes = [vp, vp, u32, u32, u32, u32, u64, u8, u8, u8, vp, sz, vp, vp]
+    if hasattr(lib, "fdf_detect_shard_begin"):  # (what-if builds of older sources loaded through FDF_LIB lack these)
+        lib.fdf_detect_shard_begin.restype = C.c_int
+        lib.fdf_detect_shard_begin.argtypes = [vp, vp, u32, u32, u32, u32, u64, u8, u8, u8, sz, vp, vp]
+        lib.fdf_detect_shard_finish.restype = C.c_int
+        lib.fdf_detect_shard_finish.argtypes = [vp, vp, u32, u32, u32, u32, vp, sz, vp, vp]
+        lib.fdf_shared_alloc.restype = C.c_int
+        lib.fdf_shared_alloc.argtypes = [vp, sz, C.POINTER(vp), vp]
+        lib.fdf_shared_open.restype = C.c_int
+        lib.fdf_shared_open.argtypes = [vp, vp, C.POINTER(vp)]
+        lib.fdf_shared_close.restype = C.c_int
+        lib.fdf_shared_close.argtypes = [vp, vp]
     lib.fdf_rgb8_to_luma8_device.restype = C.c_int
     lib.fdf_rgb8_to_luma8_device.argtypes = [vp, vp, u32, u32, u32, u32, u64, vp, u32, u64, vp]
     lib.fdf_rgb8_to_grey_sum3_device.restype = C.c_int

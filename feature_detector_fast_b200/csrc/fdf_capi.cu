@@ -69,6 +69,9 @@ struct fdf_ctx {
     unsigned long long *pinned_offsets = nullptr;
     size_t pinned_offsets_count = 0;
     uint64_t launches = 0;
+    fdf::DetectParams shard_params;  // fdf_detect_shard_begin -> fdf_detect_shard_finish
+    bool shard_pending = false;
+    std::vector<void *> shared_owned, shared_opened;  // fdf_shared_alloc / fdf_shared_open
     std::vector<cudaEvent_t> timing_events;  // 4 per slot: before detection, after it, after scan, after gather
     uint64_t timing_calls = 0;
     char error[512] = {0};
@@ -176,6 +179,8 @@ void fdf_destroy(fdf_ctx *ctx) {
     for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->back_stream) cudaStreamDestroy(ctx->back_stream);
+    for (void *q : ctx->shared_opened) cudaIpcCloseMemHandle(q);
+    for (void *q : ctx->shared_owned) cudaFree(q);
     ctx->workspace.release();
     ctx->staging.release();
     ctx->staged_frames.release();
@@ -187,20 +192,17 @@ void fdf_destroy(fdf_ctx *ctx) {
     delete ctx;
 }
 
-fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h,
-                             uint32_t pitch, uint64_t frame_stride, uint8_t threshold, uint8_t count, uint8_t nms,
-                             fdf_point *d_out, size_t cap, uint64_t *d_offsets, void *stream_handle) {
-    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
-    fdf_status st = check_config(ctx, count, nms);
-    if (st != FDF_OK) return st;
-    if (!d_offsets || (!d_out && cap > 0)) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null output pointer");
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_handle);  // NULL = the default stream
-    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
-
+namespace {
+// Argument checks, workspace / staging sizing and the TMA tensor map of one detection call.  Returns FDF_OK with
+// *empty = true when nothing can be a keypoint (the caller then only zeroes its offsets).
+fdf_status prepare_detect(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h, uint32_t pitch,
+                          uint64_t frame_stride, uint8_t threshold, uint8_t count, uint8_t nms, size_t cap,
+                          cudaStream_t stream, fdf::DetectParams &p, CUtensorMap &tmap, bool *empty) {
+    *empty = false;
     const int mode = nms;
     const long long rows = (long long)h - 2 * fdf::first_out_row(mode);
     if (n_frames == 0 || w < 7 || h < 7 || rows <= 0) {  // nothing can be a keypoint
-        FDF_CUDA(ctx, cudaMemsetAsync(d_offsets, 0, ((size_t)n_frames + 1) * sizeof(uint64_t), stream));
+        *empty = true;
         return FDF_OK;
     }
     if (!d_frames) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null frame pointer");
@@ -213,7 +215,7 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
                     "device frames need a 16-byte aligned base, pitch and frame_stride (TMA tensor map)");
 
     const int sr = choose_scored_rows(n_frames, h, mode);
-    fdf::DetectParams p;
+    p = fdf::DetectParams();
     p.w = w;
     p.h = h;
     p.n_frames = n_frames;
@@ -225,8 +227,6 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     p.mode = (uint32_t)mode;
     p.sr = (uint32_t)sr;
     p.cap = cap;
-    p.out = reinterpret_cast<uint2 *>(d_out);
-    p.offsets = reinterpret_cast<unsigned long long *>(d_offsets);
 
     if (fdf::gather_smem_bytes(mode, sr, p.words_per_row) > 200 * 1024 || w > 65535u ||
         p.chunks_per_strip > (uint32_t)fdf::kGatherMaxChunks)
@@ -246,7 +246,10 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     const size_t rn_off = rcnt_off + runs * sizeof(uint32_t);
     const size_t ws_bytes = rn_off + chunks * sizeof(uint32_t);
     FDF_CUDA(ctx, ctx->workspace.reserve(ws_bytes));
-    p.staging_cap = cap + cap / 2 + fdf::kStageSlack;
+    // Staging holds one unordered run per chunk, cut from 4096-entry blocks that a CTA takes from a global cursor.  A
+    // block's unused tail is lost when a run does not fit it, so K keypoints can take up to 2 K entries plus one
+    // partly used block per CTA (the dense path reserves exact sizes and may leave up to a whole block behind).
+    p.staging_cap = 2ull * cap + fdf::kStageSlack;
     FDF_CUDA(ctx, ctx->staging.reserve((size_t)p.staging_cap));
     FDF_CUDA(ctx, cudaMemsetAsync(ctx->workspace.ptr, 0, zeroed_bytes, stream));
     p.ticket = reinterpret_cast<uint32_t *>(ctx->workspace.ptr);
@@ -262,7 +265,6 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     p.staging = ctx->staging.ptr;
 
     // frames as a 3-D u8 tensor (x, y, frame); box = one tile; out-of-bounds elements read as 0
-    CUtensorMap tmap;
     const cuuint64_t dims[3] = {w, h, n_frames};
     const cuuint64_t strides[2] = {pitch, frame_stride};
     const cuuint32_t box[3] = {(cuuint32_t)fdf::kTileW, (cuuint32_t)fdf::tile_rows(sr), 1u};
@@ -271,6 +273,31 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
                               box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(ctx, FDF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+    return FDF_OK;
+}
+}  // namespace
+
+fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h,
+                             uint32_t pitch, uint64_t frame_stride, uint8_t threshold, uint8_t count, uint8_t nms,
+                             fdf_point *d_out, size_t cap, uint64_t *d_offsets, void *stream_handle) {
+    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
+    fdf_status st = check_config(ctx, count, nms);
+    if (st != FDF_OK) return st;
+    if (!d_offsets || (!d_out && cap > 0)) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null output pointer");
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_handle);  // NULL = the default stream
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    fdf::DetectParams p;
+    CUtensorMap tmap;
+    bool empty = false;
+    st = prepare_detect(ctx, d_frames, n_frames, w, h, pitch, frame_stride, threshold, count, nms, cap, stream, p, tmap,
+                        &empty);
+    if (st != FDF_OK) return st;
+    if (empty) {
+        FDF_CUDA(ctx, cudaMemsetAsync(d_offsets, 0, ((size_t)n_frames + 1) * sizeof(uint64_t), stream));
+        return FDF_OK;
+    }
+    p.out = reinterpret_cast<uint2 *>(d_out);
+    p.offsets = reinterpret_cast<unsigned long long *>(d_offsets);
 
     cudaEvent_t *ev = nullptr;
     if (!ctx->timing_events.empty()) {
@@ -278,7 +305,7 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
         ev = &ctx->timing_events[4 * (size_t)(ctx->timing_calls++ % slots)];
         FDF_CUDA(ctx, cudaEventRecord(ev[0], stream));
     }
-    FDF_CUDA(ctx, fdf::launch_detect(mode, sr, tmap, p, stream));
+    FDF_CUDA(ctx, fdf::launch_detect((int)p.mode, (int)p.sr, tmap, p, stream));
     if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[1], stream));
     FDF_CUDA(ctx, fdf::launch_scan(p, stream));
     if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[2], stream));
@@ -286,6 +313,138 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[3], stream));
     ctx->launches += 3;  // detection, scan, gather
     return FDF_OK;
+}
+
+// ---- sharded batches: one process per GPU, one exchange step -------------------------------------------
+fdf_status fdf_detect_shard_begin(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h,
+                                  uint32_t pitch, uint64_t frame_stride, uint8_t threshold, uint8_t count, uint8_t nms,
+                                  size_t cap_local, uint64_t *d_local_offsets, void *stream_handle) {
+    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
+    ctx->shard_pending = false;
+    fdf_status st = check_config(ctx, count, nms);
+    if (st != FDF_OK) return st;
+    if (!d_local_offsets) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null output pointer");
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_handle);
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    fdf::DetectParams p;
+    CUtensorMap tmap;
+    bool empty = false;
+    st = prepare_detect(ctx, d_frames, n_frames, w, h, pitch, frame_stride, threshold, count, nms, cap_local, stream, p,
+                        tmap, &empty);
+    if (st != FDF_OK) return st;
+    if (empty) {  // (this rank has no frames, or no frame can hold a keypoint: it still takes part in the exchange)
+        FDF_CUDA(ctx, cudaMemsetAsync(d_local_offsets, 0, ((size_t)n_frames + 1) * sizeof(uint64_t), stream));
+        p = fdf::DetectParams();
+        p.n_frames = 0;
+        ctx->shard_params = p;
+        ctx->shard_pending = true;
+        return FDF_OK;
+    }
+    p.out = nullptr;
+    p.offsets = reinterpret_cast<unsigned long long *>(d_local_offsets);
+    cudaEvent_t *ev = nullptr;
+    if (!ctx->timing_events.empty()) {
+        const size_t slots = ctx->timing_events.size() / 4;
+        ev = &ctx->timing_events[4 * (size_t)(ctx->timing_calls++ % slots)];
+        FDF_CUDA(ctx, cudaEventRecord(ev[0], stream));
+    }
+    FDF_CUDA(ctx, fdf::launch_detect((int)p.mode, (int)p.sr, tmap, p, stream));
+    if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[1], stream));
+    FDF_CUDA(ctx, fdf::launch_scan(p, stream));
+    if (ev) {
+        FDF_CUDA(ctx, cudaEventRecord(ev[2], stream));
+        FDF_CUDA(ctx, cudaEventRecord(ev[3], stream));  // (the gather launch of a sharded call is not timed)
+    }
+    ctx->launches += 2;
+    ctx->shard_params = p;
+    ctx->shard_pending = true;
+    return FDF_OK;
+}
+
+fdf_status fdf_detect_shard_finish(fdf_ctx *ctx, const uint64_t *d_all_offsets, uint32_t block, uint32_t n_ranks,
+                                   uint32_t rank, uint32_t total_frames, fdf_point *d_result, size_t cap_total,
+                                   uint64_t *d_global_offsets, void *stream_handle) {
+    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
+    if (!ctx->shard_pending) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "fdf_detect_shard_finish without a begin");
+    ctx->shard_pending = false;
+    if (!d_all_offsets || !d_global_offsets || (!d_result && cap_total > 0))
+        return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null pointer");
+    if (n_ranks == 0 || rank >= n_ranks) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "bad rank %u of %u", rank, n_ranks);
+    const uint32_t mine = fdf::shard_lo(total_frames, rank + 1, n_ranks) - fdf::shard_lo(total_frames, rank, n_ranks);
+    uint32_t widest = 0;
+    for (uint32_t r = 0; r < n_ranks; r++) {
+        const uint32_t fr = fdf::shard_lo(total_frames, r + 1, n_ranks) - fdf::shard_lo(total_frames, r, n_ranks);
+        if (fr > widest) widest = fr;
+    }
+    if (block < widest + 1) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "block %u < largest shard + 1 (%u)", block, widest + 1);
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_handle);
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    fdf::DetectParams p = ctx->shard_params;
+    if (p.n_frames != mine && !(p.n_frames == 0))
+        return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "rank %u owns %u of %u frames but began with %u", rank, mine,
+                    total_frames, p.n_frames);
+    p.out = reinterpret_cast<uint2 *>(d_result);
+    p.cap = cap_total;
+    p.all_offsets = reinterpret_cast<const unsigned long long *>(d_all_offsets);
+    p.global_offsets = reinterpret_cast<unsigned long long *>(d_global_offsets);
+    p.shard_block = block;
+    p.shard_ranks = n_ranks;
+    p.shard_rank = rank;
+    p.total_frames = total_frames;
+    FDF_CUDA(ctx, fdf::launch_gather(p, stream));
+    ctx->launches += 1;
+    return FDF_OK;
+}
+
+// ---- device memory that the other ranks' processes can map (CUDA IPC): the assembled batch result on rank 0 ------
+fdf_status fdf_shared_alloc(fdf_ctx *ctx, size_t bytes, void **d_ptr, uint8_t handle[64]) {
+    if (!ctx || !d_ptr || !handle) return FDF_ERR_INVALID_ARGUMENT;
+    *d_ptr = nullptr;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "fdf.h promises a 64-byte handle");
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *ptr = nullptr;
+    FDF_CUDA(ctx, cudaMalloc(&ptr, bytes ? bytes : 1));
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, ptr);
+    if (e != cudaSuccess) {
+        cudaFree(ptr);
+        return fail(ctx, FDF_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &hd, 64);
+    ctx->shared_owned.push_back(ptr);
+    *d_ptr = ptr;
+    return FDF_OK;
+}
+
+fdf_status fdf_shared_open(fdf_ctx *ctx, const uint8_t handle[64], void **d_ptr) {
+    if (!ctx || !d_ptr || !handle) return FDF_ERR_INVALID_ARGUMENT;
+    *d_ptr = nullptr;
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, 64);
+    void *ptr = nullptr;
+    FDF_CUDA(ctx, cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    ctx->shared_opened.push_back(ptr);
+    *d_ptr = ptr;
+    return FDF_OK;
+}
+
+fdf_status fdf_shared_close(fdf_ctx *ctx, void *d_ptr) {
+    if (!ctx || !d_ptr) return FDF_ERR_INVALID_ARGUMENT;
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < ctx->shared_owned.size(); i++)
+        if (ctx->shared_owned[i] == d_ptr) {
+            ctx->shared_owned.erase(ctx->shared_owned.begin() + (long)i);
+            FDF_CUDA(ctx, cudaFree(d_ptr));
+            return FDF_OK;
+        }
+    for (size_t i = 0; i < ctx->shared_opened.size(); i++)
+        if (ctx->shared_opened[i] == d_ptr) {
+            ctx->shared_opened.erase(ctx->shared_opened.begin() + (long)i);
+            FDF_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+            return FDF_OK;
+        }
+    return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "pointer was not obtained from fdf_shared_alloc / fdf_shared_open");
 }
 
 fdf_status fdf_set_timing(fdf_ctx *ctx, uint32_t slots) {

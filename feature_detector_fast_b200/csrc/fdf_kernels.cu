@@ -758,6 +758,25 @@ __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const Detect
         }
     };
     fetch(blockIdx.x);
+    // sharded batch: where this rank's points start in the batch result, and (first CTA) the global CSR offsets
+    unsigned long long shard_base = 0ull;
+    if (p.all_offsets != nullptr) {
+        for (uint32_t r = 0; r < p.shard_rank; r++) {
+            const uint32_t fr = shard_lo(p.total_frames, r + 1u, p.shard_ranks) - shard_lo(p.total_frames, r, p.shard_ranks);
+            shard_base += p.all_offsets[(size_t)r * p.shard_block + fr];
+        }
+        if (blockIdx.x == 0) {
+            unsigned long long rb = 0ull;
+            for (uint32_t r = 0; r < p.shard_ranks; r++) {
+                const uint32_t lo = shard_lo(p.total_frames, r, p.shard_ranks);
+                const uint32_t fr = shard_lo(p.total_frames, r + 1u, p.shard_ranks) - lo;
+                const unsigned long long *blk = p.all_offsets + (size_t)r * p.shard_block;
+                for (uint32_t f = (uint32_t)tid; f < fr; f += kGatherThreads) p.global_offsets[lo + f] = rb + blk[f];
+                rb += blk[fr];
+            }
+            if (tid == 0) p.global_offsets[p.total_frames] = rb;
+        }
+    }
     // (row, column) of the first level-1 word of each round of this thread: fixed for the whole kernel
     const int row_first = (32 * tid) / WW, col_first = 32 * tid - row_first * WW;
     const int row_step = (32 * kGatherThreads) / WW, col_step = 32 * kGatherThreads - row_step * WW;
@@ -788,7 +807,7 @@ __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const Detect
             }
         }
         __syncthreads();
-        const unsigned long long o = s_rec.dst;
+        const unsigned long long o = s_rec.dst + shard_base;
         uint32_t block_off = 0u;
         int row0 = row_first, col0 = col_first;  // of level-1 word 32 * ts
         for (int t0 = 0; t0 < nsum; t0 += kGatherThreads) {  // (one round unless the image is wider than ~8000 pixels)
@@ -992,7 +1011,8 @@ cudaError_t launch_scan(const DetectParams &p, cudaStream_t stream) {
 
 cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream) {
     const unsigned long long items = (unsigned long long)p.n_frames * p.strips_per_frame;
-    if (items == 0 || items > 0x7fffffffull) return cudaErrorInvalidValue;
+    // (a rank without frames still launches one CTA in a sharded call: it writes the batch's global offsets)
+    if ((items == 0 && p.all_offsets == nullptr) || items > 0x7fffffffull) return cudaErrorInvalidValue;
     const size_t smem = gather_smem_bytes((int)p.mode, (int)p.sr, p.words_per_row);
     cudaError_t e = cudaFuncSetAttribute(fdf_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1003,6 +1023,7 @@ cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream) {
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     unsigned long long grid = (unsigned long long)sms * (unsigned)per_sm;
     if (grid > items) grid = items;
+    if (grid == 0) grid = 1;
     fdf_gather_kernel<<<(unsigned)grid, kGatherThreads, smem, stream>>>(p, (uint32_t)items);
     return cudaGetLastError();
 }

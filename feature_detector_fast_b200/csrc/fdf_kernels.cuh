@@ -77,8 +77,22 @@ struct DetectParams {
     unsigned long long *scan_status;  // look-back words of the scan kernel's tiles (zeroed per launch)
     uint32_t *ticket;                 // strip tickets of the detection kernel (zeroed per launch)
     uint32_t *scan_ticket;            // tile tickets of the scan kernel (zeroed per launch)
-    uint32_t *flags;                  // zeroed per launch; bit 0 look-back timeout, bit 1 TMA wait timeout
+    uint32_t *flags;                  // zeroed per launch; bit 0 look-back timeout, bit 1 TMA wait timeout,
+                                      // bit 2 staging buffer overflow (entries dropped)
+    // Sharded batches (multi-GPU, one process per GPU; null / zero otherwise).  all_offsets holds every rank's LOCAL
+    // CSR offsets after the all-gather: rank r's block starts at r * shard_block and has frames(r) + 1 entries, where
+    // rank r owns frames [r * total / ranks, (r + 1) * total / ranks).  The gather kernel then writes this rank's
+    // points at out[(sum of the lower ranks' totals) + local position] -- `out` may be a peer-mapped buffer of
+    // another GPU -- and the batch's global CSR offsets to global_offsets[total_frames + 1].
+    const unsigned long long *all_offsets;
+    unsigned long long *global_offsets;
+    uint32_t shard_block, shard_ranks, shard_rank, total_frames;
 };
+
+// frames [lo, hi) of a batch of `total` frames owned by rank r of n (contiguous blocks; sharding.frame_shard)
+__host__ __device__ inline uint32_t shard_lo(uint32_t total, uint32_t r, uint32_t n) {
+    return (uint32_t)(((unsigned long long)r * total) / n);
+}
 
 constexpr int kScanThreads = 256;
 constexpr int kScanItemsPerThread = 8;

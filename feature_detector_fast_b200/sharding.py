@@ -1,56 +1,177 @@
 """Frame-level data parallelism: one process per GPU, frames sharded contiguously, one collective.
 
 The detection path has no cross-frame dependency (a frame is never split across GPUs), so the only
-exchange step is the all-gather of per-frame keypoint counts from which every rank derives the global
-CSR offsets of the batch result.  `torch.distributed` is plumbing: NCCL over
-NVLink on the GPUs, gloo in the CPU tests.
+exchange step is ONE all-gather of the ranks' local CSR offsets, from which every rank derives the
+global offsets of the batch result and each rank learns where its points start in it.
+The points themselves are not sent by a second collective: the emitting kernel of every rank writes them
+straight to their final position in rank 0's result buffer, which the other ranks map over NVLink (CUDA IPC,
+`fdf_shared_alloc` / `fdf_shared_open`).  `torch.distributed` is plumbing: NCCL on the GPUs (the all-gather,
+the 64-byte handle broadcast, the closing barrier), gloo in the CPU tests of the index arithmetic.
 """
 from __future__ import annotations
 
-from typing import Tuple
+import ctypes as C
+from typing import Optional, Tuple
 
 
 def frame_shard(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
-    """Contiguous block of frames owned by `rank`: [rank*F/G, (rank+1)*F/G)."""
+    """Contiguous block of frames owned by `rank`: [rank*F/G, (rank+1)*F/G)  (csrc/fdf_kernels.cuh: shard_lo)."""
     if world <= 0 or not (0 <= rank < world):
         raise ValueError("bad rank / world size")
     return (rank * n_frames) // world, ((rank + 1) * n_frames) // world
 
 
+def shard_block(n_frames: int, world: int) -> int:
+    """Entries per rank in the all-gather buffer: the largest shard's frames + 1 (its local CSR offsets)."""
+    return max(frame_shard(n_frames, r, world)[1] - frame_shard(n_frames, r, world)[0] for r in range(world)) + 1
+
+
 def counts_from_offsets(offsets):
-    """Per-frame keypoint counts from a rank-local CSR offsets tensor (F_local + 1,)."""
+    """Per-frame keypoint counts from a CSR offsets tensor (F + 1,)."""
     return offsets[1:] - offsets[:-1]
 
 
-def gather_frame_counts(local_counts, n_frames: int, group=None):
-    """All-gathers per-frame counts (int64 tensor, this rank's frames in order) into the global (F,) tensor.
+def global_offsets_from_blocks(all_offsets, n_frames: int, world: int):
+    """What `fdf_detect_shard_finish` computes on the device, restated on tensors (any device; the CPU tests and the
+    GPU checks compare against it): all_offsets is (world * block,) = every rank's local offsets block after the
+    all-gather.  Returns (global CSR offsets (F + 1,), per-rank base positions (world,))."""
+    import torch
 
-    Shards may differ by one frame, so each rank contributes a block padded to the largest shard.
-    """
+    block = all_offsets.numel() // world
+    out = torch.zeros(n_frames + 1, dtype=torch.int64, device=all_offsets.device)
+    bases = torch.zeros(world, dtype=torch.int64, device=all_offsets.device)
+    base = 0
+    for r in range(world):
+        lo, hi = frame_shard(n_frames, r, world)
+        blk = all_offsets[r * block: r * block + (hi - lo) + 1].to(torch.int64)
+        out[lo:hi] = blk[: hi - lo] + base
+        bases[r] = base
+        base = base + int(blk[hi - lo])
+    out[n_frames] = base
+    return out, bases
+
+
+def gather_offset_blocks(local_offsets, n_frames: int, group=None):
+    """The path's one collective, stand-alone (used by the gloo tests; ShardedDetector keeps its buffers resident):
+    all-gathers every rank's local offsets, each padded to shard_block entries, into a (world * block,) tensor."""
     import torch
     import torch.distributed as dist
 
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = frame_shard(n_frames, rank, world)
-    if local_counts.numel() != hi - lo:
-        raise ValueError(f"rank {rank} owns {hi - lo} frames but passed {local_counts.numel()} counts")
-    width = max(frame_shard(n_frames, r, world)[1] - frame_shard(n_frames, r, world)[0] for r in range(world))
-    send = torch.zeros(width, dtype=torch.int64, device=local_counts.device)
-    send[: hi - lo] = local_counts.to(torch.int64)
-    recv = torch.empty(world * width, dtype=torch.int64, device=local_counts.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    parts = []
-    for r in range(world):
-        a, b = frame_shard(n_frames, r, world)
-        parts.append(recv[r * width: r * width + (b - a)])
-    return torch.cat(parts)
+    if local_offsets.numel() != hi - lo + 1:
+        raise ValueError(f"rank {rank} owns {hi - lo} frames but passed {local_offsets.numel()} offsets")
+    block = shard_block(n_frames, world)
+    recv = torch.zeros(world * block, dtype=torch.int64, device=local_offsets.device)
+    send = recv[rank * block: (rank + 1) * block]
+    send[: hi - lo + 1] = local_offsets.to(torch.int64)
+    dist.all_gather_into_tensor(recv, send.clone(), group=group)
+    return recv
 
 
-def global_offsets(global_counts):
-    """Exclusive scan: CSR offsets (F + 1,) of the batch result assembled from all ranks."""
+class ShardedDetector:
+    """One batch, all GPUs of the box, one result (north star: "NCCL is used only to gather per-GPU keypoint counts and
+    offsets into one batch result over NVLink").
+
+    Every rank constructs it with the same arguments (collective).  Rank 0 owns the result buffer of `cap_total` points;
+    the other ranks map it.  `detect(local_frames, config)` enqueues, on torch's current stream:
+        detection + offset scan of the local frames   (2 launches, writes the local offsets into the all-gather buffer)
+        all_gather_into_tensor of the offset blocks    (1 NCCL launch: the exchange step)
+        ordered emission                               (1 launch: every rank's points land at their final position in
+                                                        rank 0's buffer; also writes the global CSR offsets)
+    and returns (points, global_offsets): `points` is the (cap_total, 2) int32 view of the result on rank 0 and None
+    elsewhere; global_offsets is an int64 (F + 1,) device tensor on every rank.  Call `fence()` (an all-reduce on the
+    same stream) before rank 0 reads points that other ranks wrote.
+    """
+
+    def __init__(self, detector, n_frames: int, cap_total: int, cap_local: Optional[int] = None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.det, self.group = detector, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_frames, self.cap_total = int(n_frames), int(cap_total)
+        self.lo, self.hi = frame_shard(self.n_frames, self.rank, self.world)
+        self.cap_local = int(cap_local) if cap_local is not None else self.cap_total
+        self.block = shard_block(self.n_frames, self.world)
+        self.device = torch.device("cuda", detector.device)
+        lib, ctx = detector._lib, detector._ctx
+        self._all = torch.zeros(self.world * self.block, dtype=torch.int64, device=self.device)
+        self._mine = self._all[self.rank * self.block: (self.rank + 1) * self.block]
+        self.global_offsets = torch.zeros(self.n_frames + 1, dtype=torch.int64, device=self.device)
+        self._fence = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # rank 0 allocates the result and broadcasts its IPC handle; the others map it (peer access over NVLink)
+        handle = torch.zeros(64, dtype=torch.uint8, device=self.device)
+        self._ptr = C.c_void_p()
+        if self.rank == 0:
+            hbuf = (C.c_uint8 * 64)()
+            st = lib.fdf_shared_alloc(ctx, max(1, self.cap_total) * 8, C.byref(self._ptr), hbuf)
+            if st != 0:
+                raise RuntimeError("fdf_shared_alloc: " + lib.fdf_last_error(ctx).decode())
+            handle.copy_(torch.tensor(list(hbuf), dtype=torch.uint8))
+        dist.broadcast(handle, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        if self.rank != 0:
+            hbuf = (C.c_uint8 * 64)(*handle.cpu().tolist())
+            st = lib.fdf_shared_open(ctx, hbuf, C.byref(self._ptr))
+            if st != 0:
+                raise RuntimeError("fdf_shared_open: " + lib.fdf_last_error(ctx).decode())
+        self.points = None
+        if self.rank == 0:
+            self.points = _tensor_from_pointer(self._ptr.value, (max(1, self.cap_total), 2), self.device)
+        dist.barrier(group=group)
+
+    def detect(self, local_frames, config):
+        import torch
+        import torch.distributed as dist
+
+        det, lib = self.det, self.det._lib
+        f, h, w = local_frames.shape
+        if f != self.hi - self.lo:
+            raise ValueError(f"rank {self.rank} owns frames [{self.lo}, {self.hi}) but got {f} frames")
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        st = lib.fdf_detect_shard_begin(det._ctx, local_frames.data_ptr() if f else None, f, w, h,
+                                        local_frames.stride(1) if f else w, local_frames.stride(0) if f else w * h,
+                                        int(config.threshold), int(config.count), int(config.non_maximal_supression),
+                                        self.cap_local, self._mine.data_ptr(), s)
+        if st != 0:
+            from .api import _raise
+            _raise(lib, det._ctx, st)
+        dist.all_gather_into_tensor(self._all, self._mine, group=self.group)  # in place: rank r's block is its input
+        st = lib.fdf_detect_shard_finish(det._ctx, self._all.data_ptr(), self.block, self.world, self.rank,
+                                         self.n_frames, self._ptr, self.cap_total, self.global_offsets.data_ptr(), s)
+        if st != 0:
+            from .api import _raise
+            _raise(lib, det._ctx, st)
+        return self.points, self.global_offsets
+
+    def fence(self) -> None:
+        """Orders every rank's emission before whatever rank 0 enqueues next on this stream."""
+        import torch.distributed as dist
+
+        dist.all_reduce(self._fence, group=self.group)
+
+    def close(self) -> None:
+        import torch.distributed as dist
+
+        if getattr(self, "_ptr", None) is not None and self._ptr.value:
+            if self.rank != 0:
+                self.det._lib.fdf_shared_close(self.det._ctx, self._ptr)
+            dist.barrier(group=self.group)  # nobody has the buffer mapped any more
+            if self.rank == 0:
+                self.points = None
+                self.det._lib.fdf_shared_close(self.det._ctx, self._ptr)
+            self._ptr = C.c_void_p()
+
+
+class _RawCudaBuffer:
+    """Minimal __cuda_array_interface__ carrier so that torch can view library-owned device memory."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _tensor_from_pointer(ptr: int, shape, device):
     import torch
 
-    out = torch.zeros(global_counts.numel() + 1, dtype=torch.int64, device=global_counts.device)
-    torch.cumsum(global_counts, 0, out=out[1:])
-    return out
+    with torch.cuda.device(device):
+        return torch.as_tensor(_RawCudaBuffer(ptr, shape, "<i4"), device=device)

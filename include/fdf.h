@@ -43,7 +43,7 @@ typedef enum fdf_status {
     FDF_ERR_CAPACITY = 4,        /* output buffer too small; *n_out / offsets[n_frames] hold the needed size */
     FDF_ERR_CUDA = 5,            /* a CUDA call failed; see fdf_last_error() */
     FDF_ERR_NO_DEVICE = 6,       /* no usable sm_100 device */
-    FDF_ERR_INTERNAL = 7         /* device-side consistency check failed (look-back timeout) */
+    FDF_ERR_INTERNAL = 7         /* device-side consistency check failed (a pipeline wait timed out, staging overflow) */
 } fdf_status;
 
 /* One context per host thread and device: owns a stream, the scan workspace and the staging
@@ -97,6 +97,40 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
                              uint64_t *d_offsets, void *stream);
 
 /*
+ * Multi-GPU (north star / SURVEY 8e): frames are independent units, so a batch of total_frames frames is sharded by
+ * contiguous blocks over n_ranks processes, one per GPU -- rank r owns frames [r*total/n, (r+1)*total/n) -- and the
+ * path's only exchange step is one all-gather of the ranks' local CSR offsets (NCCL over NVLink; the caller's
+ * communication library does it, this library has no networking code).  The reference has no counterpart: its
+ * `detect` (lib.rs:62-64) handles one image on one thread.
+ *
+ *   fdf_detect_shard_begin   detection + offset scan of this rank's frames; writes the n_frames + 1 LOCAL offsets to
+ *                            d_local_offsets (typically this rank's block of the all-gather send/receive buffer).
+ *                            cap_local sizes the rank's internal staging buffer (>= its keypoint count).
+ *   <all-gather>             every rank's block of `block` >= (largest shard + 1) uint64 entries into
+ *                            d_all_offsets[n_ranks * block].
+ *   fdf_detect_shard_finish  ordered emission of this rank's points DIRECTLY at their place in the batch result:
+ *                            d_result[(keypoints of all lower ranks) + local position].  d_result may be memory of
+ *                            another GPU mapped with fdf_shared_open (rank 0's buffer: the result is then assembled
+ *                            over NVLink by the emitting kernel itself, no extra copy); also writes the batch's global
+ *                            CSR offsets (total_frames + 1 entries) to this rank's d_global_offsets.
+ * All work is enqueued on `stream`.  A reader of d_result on another rank needs a later collective or barrier
+ * on that stream before it looks at the points.
+ */
+fdf_status fdf_detect_shard_begin(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h,
+                                  uint32_t pitch, uint64_t frame_stride, uint8_t threshold, uint8_t count, uint8_t nms,
+                                  size_t cap_local, uint64_t *d_local_offsets, void *stream);
+fdf_status fdf_detect_shard_finish(fdf_ctx *ctx, const uint64_t *d_all_offsets, uint32_t block, uint32_t n_ranks,
+                                   uint32_t rank, uint32_t total_frames, fdf_point *d_result, size_t cap_total,
+                                   uint64_t *d_global_offsets, void *stream);
+
+/* Device memory that other processes on the same node can map (CUDA IPC): fdf_shared_alloc returns the pointer and a
+ * 64-byte handle to send to the peers, fdf_shared_open maps a peer's allocation into this process (peer access over
+ * NVLink), fdf_shared_close unmaps / frees.  Everything still open is released by fdf_destroy. */
+fdf_status fdf_shared_alloc(fdf_ctx *ctx, size_t bytes, void **d_ptr, uint8_t handle[64]);
+fdf_status fdf_shared_open(fdf_ctx *ctx, const uint8_t handle[64], void **d_ptr);
+fdf_status fdf_shared_close(fdf_ctx *ctx, void *d_ptr);
+
+/*
  * The step in front of the path in the reference's CLI: `image::open(path).to_rgb8()` followed by
  * `DynamicImage::ImageRgb8(..).to_luma8()` (main.rs:53-58).  Interleaved RGB8 in DEVICE memory -> luma8 in
  * DEVICE memory, enqueued on `stream`: luma = (2126 r + 7152 g + 722 b) / 10000, integer, truncating -- the
@@ -146,7 +180,8 @@ fdf_status fdf_set_timing(fdf_ctx *ctx, uint32_t slots);
 fdf_status fdf_get_timing(fdf_ctx *ctx, uint32_t slot, float ms[3]);
 
 /* Device-side flags of the last fdf_detect_device-family call on this context, read back with a
- * synchronising copy: 0 = clean, bit 0 = look-back wait timed out (result invalid). */
+ * synchronising copy: 0 = clean, bit 0 = look-back wait timed out, bit 1 = a pipeline wait of the detection kernel
+ * timed out, bit 2 = the internal staging buffer overflowed (keypoints were dropped): the result is invalid. */
 fdf_status fdf_check_device_flags(fdf_ctx *ctx, uint32_t *flags);
 
 const char *fdf_last_error(const fdf_ctx *ctx);
