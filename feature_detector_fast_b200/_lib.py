@@ -77,6 +77,9 @@ def load_library() -> C.CDLL:
     lib.fdf_synth_frames_device.argtypes = [vp, vp, u32, u32, u32, u32, u64, u64, u32, u32, u32, vp]
     lib.fdf_kernel_launches.restype = u64
     lib.fdf_kernel_launches.argtypes = [vp]
+    if hasattr(lib, "fdf_set_tuning"):
+        lib.fdf_set_tuning.restype = C.c_int
+        lib.fdf_set_tuning.argtypes = [vp, C.c_int, u32]
     lib.fdf_set_timing.restype = C.c_int
     lib.fdf_set_timing.argtypes = [vp, u32]
     lib.fdf_get_timing.restype = C.c_int

@@ -222,6 +222,13 @@ class Detector:
             _raise(self._lib, self._ctx, st)
         return out
 
+    def set_tuning(self, strip_rows: int = 0, sub_batch_mb: int = 0) -> None:
+        """fdf_set_tuning: scored rows per strip (0 = automatic, 32, 48, 64) and the host path's sub-batch size in MB
+        (0 = default).  Results never depend on either."""
+        st = self._lib.fdf_set_tuning(self._ctx, int(strip_rows), int(sub_batch_mb))
+        if st != 0:
+            _raise(self._lib, self._ctx, st)
+
     def set_timing(self, slots: int) -> None:
         """Record CUDA events around the three launches of every following detect_device call (0 = off)."""
         st = self._lib.fdf_set_timing(self._ctx, int(slots))

@@ -42,11 +42,6 @@ struct DeviceBuffer {
 
 }  // namespace
 
-#ifdef FDF_PHASE_CLOCKS
-namespace fdf {
-cudaError_t read_phase_clocks(unsigned long long out[256]);
-}
-#endif
 #ifdef FDF_TRACE
 namespace fdf {
 cudaError_t read_trace(long long *out, size_t bytes);
@@ -69,6 +64,9 @@ struct fdf_ctx {
     unsigned long long *pinned_offsets = nullptr;
     size_t pinned_offsets_count = 0;
     uint64_t launches = 0;
+    fdf::DeviceInfo info;        // SM count, kernel occupancies, experiment knobs: looked up once in fdf_create
+    int force_sr = 0;            // FDF_FORCE_SR (experiments / tests): strip height override, read once in fdf_create
+    unsigned long long sub_batch_bytes = 128ull << 20;  // fdf_detect_batch sub-batch size (FDF_SUB_BATCH_MB, read once)
     fdf::DetectParams shard_params;  // fdf_detect_shard_begin -> fdf_detect_shard_finish
     bool shard_pending = false;
     std::vector<void *> shared_owned, shared_opened;  // fdf_shared_alloc / fdf_shared_open
@@ -107,12 +105,9 @@ fdf_status check_config(fdf_ctx *ctx, uint8_t count, uint8_t nms) {
 }
 
 // strip height: tall strips (less halo) when there is enough work to fill the GPU, short otherwise
-int choose_scored_rows(uint32_t n_frames, uint32_t h, int mode) {
+int choose_scored_rows(const fdf_ctx *ctx, uint32_t n_frames, uint32_t h, int mode) {
     const long long rows = (long long)h - 2 * fdf::first_out_row(mode);
-    if (const char *force = getenv("FDF_FORCE_SR")) {  // tuning knob for experiments: 32 or 64
-        const int v = atoi(force);
-        if (v == 32 || v == 48 || v == 64) return v;
-    }
+    if (ctx->force_sr == 32 || ctx->force_sr == 48 || ctx->force_sr == 64) return ctx->force_sr;
     const long long strips64 = (rows + fdf::out_rows(mode, 64) - 1) / fdf::out_rows(mode, 64);
     return (long long)n_frames * strips64 >= 2 * 148 ? 64 : 32;
 }
@@ -167,6 +162,16 @@ fdf_status fdf_create(int device, fdf_ctx **out_ctx) {
         return FDF_ERR_CUDA;
     }
     ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if (fdf::init_device_info(ctx->info) != cudaSuccess) {
+        fdf_destroy(ctx);
+        return FDF_ERR_CUDA;
+    }
+    // tuning / test knobs are read here, once: the environment cannot change the behaviour of a live context
+    if (const char *force = getenv("FDF_FORCE_SR")) ctx->force_sr = atoi(force);
+    if (const char *mb = getenv("FDF_SUB_BATCH_MB")) {
+        const long v = atol(mb);
+        if (v >= 1 && v <= 65536) ctx->sub_batch_bytes = (unsigned long long)v << 20;
+    }
     *out_ctx = ctx;
     return FDF_OK;
 }
@@ -214,7 +219,7 @@ fdf_status prepare_detect(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_fram
         return fail(ctx, FDF_ERR_INVALID_ARGUMENT,
                     "device frames need a 16-byte aligned base, pitch and frame_stride (TMA tensor map)");
 
-    const int sr = choose_scored_rows(n_frames, h, mode);
+    const int sr = choose_scored_rows(ctx, n_frames, h, mode);
     p = fdf::DetectParams();
     p.w = w;
     p.h = h;
@@ -229,26 +234,25 @@ fdf_status prepare_detect(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_fram
     p.cap = cap;
 
     if (fdf::gather_smem_bytes(mode, sr, p.words_per_row) > 200 * 1024 || w > 65535u ||
-        p.chunks_per_strip > (uint32_t)fdf::kGatherMaxChunks)
+        p.chunks_per_strip * (uint32_t)fdf::kRunsPerChunk > (uint32_t)fdf::kGatherMaxRuns)
         return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "image too wide (%u) for the strip bit plane", w);
     const unsigned long long items = (unsigned long long)n_frames * p.strips_per_frame;
     if (items > 0x7fffffffull) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "batch too large");
 
-    // workspace: [header 64 B: ticket, flags, scan ticket, cursor][scan status][zeroed up to here per launch]
-    //            [item_dst][run_base][item_count][run_count][run_n]
+    // workspace: [header 64 B: ticket, flags, scan ticket, cursor][scan status][item_count][zeroed up to here per launch]
+    //            [item_dst][run_base][run_count]
     const size_t scan_tiles = ((size_t)items + fdf::kScanTile - 1) / fdf::kScanTile;
-    const size_t zeroed_bytes = kWorkspaceHeader + scan_tiles * sizeof(unsigned long long);
-    const size_t chunks = (size_t)items * p.chunks_per_strip, runs = chunks * (size_t)fdf::run_stride(mode);
+    const size_t cnt_off = kWorkspaceHeader + scan_tiles * sizeof(unsigned long long);
+    const size_t zeroed_bytes = cnt_off + (size_t)items * sizeof(uint32_t);
+    const size_t runs = (size_t)items * p.chunks_per_strip * (size_t)fdf::kRunsPerChunk;
     const size_t dst_off = (zeroed_bytes + 15) & ~(size_t)15;
     const size_t rbase_off = dst_off + (size_t)items * sizeof(unsigned long long);
-    const size_t cnt_off = rbase_off + runs * sizeof(unsigned long long);
-    const size_t rcnt_off = cnt_off + (size_t)items * sizeof(uint32_t);
-    const size_t rn_off = rcnt_off + runs * sizeof(uint32_t);
-    const size_t ws_bytes = rn_off + chunks * sizeof(uint32_t);
+    const size_t rcnt_off = rbase_off + runs * sizeof(unsigned long long);
+    const size_t ws_bytes = rcnt_off + runs * sizeof(uint32_t);
     FDF_CUDA(ctx, ctx->workspace.reserve(ws_bytes));
-    // Staging holds one unordered run per chunk, cut from 4096-entry blocks that a CTA takes from a global cursor.  A
-    // block's unused tail is lost when a run does not fit it, so K keypoints can take up to 2 K entries plus one
-    // partly used block per CTA (the dense path reserves exact sizes and may leave up to a whole block behind).
+    // Staging holds the emit warps' unordered runs, cut from 4096-entry blocks that a warp takes from a global cursor.
+    // A block's unused tail is lost when the next run may not fit it, so K keypoints can take up to 2 K entries plus
+    // one partly used block per emit warp (kStageSlack).  Overflow is not silent: the kernels raise flag bit 2.
     p.staging_cap = 2ull * cap + fdf::kStageSlack;
     FDF_CUDA(ctx, ctx->staging.reserve((size_t)p.staging_cap));
     FDF_CUDA(ctx, cudaMemsetAsync(ctx->workspace.ptr, 0, zeroed_bytes, stream));
@@ -261,7 +265,6 @@ fdf_status prepare_detect(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_fram
     p.run_base = reinterpret_cast<unsigned long long *>(ctx->workspace.ptr + rbase_off);
     p.item_count = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + cnt_off);
     p.run_count = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + rcnt_off);
-    p.run_n = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + rn_off);
     p.staging = ctx->staging.ptr;
 
     // frames as a 3-D u8 tensor (x, y, frame); box = one tile; out-of-bounds elements read as 0
@@ -305,11 +308,11 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
         ev = &ctx->timing_events[4 * (size_t)(ctx->timing_calls++ % slots)];
         FDF_CUDA(ctx, cudaEventRecord(ev[0], stream));
     }
-    FDF_CUDA(ctx, fdf::launch_detect((int)p.mode, (int)p.sr, tmap, p, stream));
+    FDF_CUDA(ctx, fdf::launch_detect((int)p.mode, (int)p.sr, tmap, p, stream, ctx->info));
     if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[1], stream));
     FDF_CUDA(ctx, fdf::launch_scan(p, stream));
     if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[2], stream));
-    FDF_CUDA(ctx, fdf::launch_gather(p, stream));
+    FDF_CUDA(ctx, fdf::launch_gather(p, stream, ctx->info));
     if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[3], stream));
     ctx->launches += 3;  // detection, scan, gather
     return FDF_OK;
@@ -348,7 +351,7 @@ fdf_status fdf_detect_shard_begin(fdf_ctx *ctx, const uint8_t *d_frames, uint32_
         ev = &ctx->timing_events[4 * (size_t)(ctx->timing_calls++ % slots)];
         FDF_CUDA(ctx, cudaEventRecord(ev[0], stream));
     }
-    FDF_CUDA(ctx, fdf::launch_detect((int)p.mode, (int)p.sr, tmap, p, stream));
+    FDF_CUDA(ctx, fdf::launch_detect((int)p.mode, (int)p.sr, tmap, p, stream, ctx->info));
     if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[1], stream));
     FDF_CUDA(ctx, fdf::launch_scan(p, stream));
     if (ev) {
@@ -391,7 +394,7 @@ fdf_status fdf_detect_shard_finish(fdf_ctx *ctx, const uint64_t *d_all_offsets, 
     p.shard_ranks = n_ranks;
     p.shard_rank = rank;
     p.total_frames = total_frames;
-    FDF_CUDA(ctx, fdf::launch_gather(p, stream));
+    FDF_CUDA(ctx, fdf::launch_gather(p, stream, ctx->info));
     ctx->launches += 1;
     return FDF_OK;
 }
@@ -445,6 +448,16 @@ fdf_status fdf_shared_close(fdf_ctx *ctx, void *d_ptr) {
             return FDF_OK;
         }
     return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "pointer was not obtained from fdf_shared_alloc / fdf_shared_open");
+}
+
+fdf_status fdf_set_tuning(fdf_ctx *ctx, int strip_rows, uint32_t sub_batch_mb) {
+    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
+    if (strip_rows != 0 && strip_rows != 32 && strip_rows != 48 && strip_rows != 64)
+        return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "strip_rows must be 0 (automatic), 32, 48 or 64");
+    if (sub_batch_mb > 65536u) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "sub_batch_mb out of range");
+    ctx->force_sr = strip_rows;
+    ctx->sub_batch_bytes = (unsigned long long)(sub_batch_mb ? sub_batch_mb : 128u) << 20;
+    return FDF_OK;
 }
 
 fdf_status fdf_set_timing(fdf_ctx *ctx, uint32_t slots) {
@@ -517,11 +530,7 @@ fdf_status fdf_detect_batch(fdf_ctx *ctx, const uint8_t *frames, uint32_t n_fram
         ctx->pinned_offsets_count = (size_t)n_frames + 2;
     }
     // sub-batch size: about 128 MB of pixels, at least enough strips to fill the GPU several times over
-    unsigned long long sub_bytes = 128ull << 20;
-    if (const char *mb = getenv("FDF_SUB_BATCH_MB")) {  // tuning / test knob
-        const long v = atol(mb);
-        if (v >= 1 && v <= 65536) sub_bytes = (unsigned long long)v << 20;
-    }
+    const unsigned long long sub_bytes = ctx->sub_batch_bytes;
     uint32_t sub = (uint32_t)(sub_bytes / (dstride ? dstride : 1));
     if (sub < 1u) sub = 1u;
     if (sub > n_frames) sub = n_frames;
@@ -578,8 +587,9 @@ fdf_status fdf_detect_batch(fdf_ctx *ctx, const uint8_t *frames, uint32_t n_fram
         found += got;
     }
     FDF_CUDA(ctx, cudaStreamSynchronize(ctx->back_stream));
-    if (flags_all) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x (look-back or pipeline wait timed out)", flags_all);
+    if (flags_all & ~4u) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x (look-back or pipeline wait timed out)", flags_all);
     if (found > cap) return fail(ctx, FDF_ERR_CAPACITY, "%llu keypoints found, capacity %zu", (unsigned long long)found, cap);
+    if (flags_all) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x (staging buffer overflow)", flags_all);
     return FDF_OK;
 }
 
@@ -663,22 +673,13 @@ fdf_status fdf_detect_rgb8(fdf_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_
     FDF_CUDA(ctx, cudaMemcpyAsync(&flags, ctx->workspace.ptr + 4, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
     FDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *n_out = (size_t)offs[1];
-    if (flags) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x", flags);
+    if (flags & ~4u) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x", flags);
+    if (offs[1] > cap) return fail(ctx, FDF_ERR_CAPACITY, "%llu keypoints found, capacity %zu", offs[1], cap);
+    if (flags) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x (staging buffer overflow)", flags);
     const size_t ncopy = offs[1] < dcap ? (size_t)offs[1] : dcap;
     if (ncopy) FDF_CUDA(ctx, cudaMemcpy(out, ctx->staged_points.ptr, ncopy * sizeof(fdf_point), cudaMemcpyDeviceToHost));
-    if (offs[1] > cap) return fail(ctx, FDF_ERR_CAPACITY, "%llu keypoints found, capacity %zu", offs[1], cap);
     return FDF_OK;
 }
-
-#ifdef FDF_PHASE_CLOCKS
-// (debug builds only, not part of include/fdf.h) cycles per kernel phase since the last call
-fdf_status fdf_debug_phase_clocks(fdf_ctx *ctx, uint64_t out[256]) {
-    if (!ctx || !out) return FDF_ERR_INVALID_ARGUMENT;
-    FDF_CUDA(ctx, cudaDeviceSynchronize());
-    FDF_CUDA(ctx, fdf::read_phase_clocks(reinterpret_cast<unsigned long long *>(out)));
-    return FDF_OK;
-}
-#endif
 
 #ifdef FDF_TRACE
 // (debug builds only) the timeline table of the last launch: [cta 4][warp 16][chunk 200][slot 12] clock64 values

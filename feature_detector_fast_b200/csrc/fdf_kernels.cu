@@ -41,11 +41,18 @@ namespace {
 
 constexpr uint32_t kFlagLookbackTimeout = 1u;
 constexpr uint32_t kFlagTmaTimeout = 2u;
+constexpr uint32_t kFlagStagingOverflow = 4u;
 constexpr unsigned long long kStatusAggregate = 1ull << 62;
 constexpr unsigned long long kStatusPrefix = 2ull << 62;
 constexpr unsigned long long kStatusValueMask = (1ull << 62) - 1ull;
 constexpr uint32_t kSpinLimit = 1u << 22;
-constexpr uint32_t kWaitHintNs = 100000u;  // mbarrier.try_wait suspend-time hint
+#ifndef FDF_WAIT_MODE
+#define FDF_WAIT_MODE 0
+#endif
+#ifndef FDF_WAIT_HINT_NS
+#define FDF_WAIT_HINT_NS 100000
+#endif
+constexpr uint32_t kWaitHintNs = FDF_WAIT_HINT_NS;  // mbarrier.try_wait suspend-time hint
 constexpr unsigned long long kWaitLimitNs = 4000000000ull;  // 4 s
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -86,7 +93,13 @@ __device__ __forceinline__ bool mbar_spin(uint64_t *bar, uint32_t parity, uint32
         ".reg .u32 n;\n"
         "mov.u32 n, %3;\n"
         "FDF_SPIN:\n"
+#if FDF_WAIT_MODE == 1   // experiment: no suspend-time hint (the hardware's default time limit)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#elif FDF_WAIT_MODE == 2  // experiment: non-blocking test (busy polling)
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %4;\n"
+#endif
         "@p bra FDF_SPIN_DONE;\n"
         "add.u32 n, n, -1;\n"
         "setp.ne.u32 p, n, 0;\n"
@@ -151,10 +164,6 @@ __device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned l
 }
 
 // ---- shared-memory carve-up ------------------------------------------------------------------
-#ifndef FDF_ABLATE
-#define FDF_ABLATE 0  // (timing experiments only, results are wrong: skip phase B = 1, the NMS pass = 2, phase A = 4,
-                      //  B arithmetic = 8, B ring loads = 16, stage 2 = 32, the candidate push = 64)
-#endif
 #ifndef FDF_TILE_STAGES
 #define FDF_TILE_STAGES 2
 #endif
@@ -162,38 +171,51 @@ __device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned l
 #define FDF_L2_PREFETCH 1
 #endif
 constexpr int kTileStages = FDF_TILE_STAGES;  // tile buffers per CTA: the tile of chunk k + kTileStages is requested when
-                                              // phase B of chunk k is done, so TMA latency (~1700 cycles under load)
-                                              // is hidden behind kTileStages - 1 chunks of work
-constexpr int kQueueBufs = kTileStages;       // candidate queues: the filter may run kTileStages - 1 chunks ahead of the test
+                                              // the test warps are done with chunk k
+constexpr int kQueueBufs = kTileStages;       // candidate queues, one per tile buffer
+constexpr int kTicketSlots = 8;               // strips whose tickets can be in flight between the tile requests and the
+                                              // emit warps (a strip can be a single chunk)
+constexpr uint32_t kDenseMark = 0xffffffffu;  // keypoint count of a chunk that went through the dense path
 static_assert(kTileStages >= 2 && kTileStages <= 4, "misc layout holds up to 4 barriers of each kind");
 
-template <int MODE, int SR>
-struct Layout {
-    static constexpr int TR = tile_rows(SR);
-    static constexpr int tile_bytes = TR * kTileW;  // one TMA box
-    static constexpr int plane_off = kTileStages * tile_bytes;
-    static constexpr int plane_bytes = SR * kPlaneW * 2;  // u16: tag << 12 | score (Off mode: score 1)
-    static constexpr int queue_off = plane_off + plane_bytes;
-    static constexpr int queue_bytes = kQueueBufs * kQueueCap * 2;      // candidate queues, per chunk
-    static constexpr int klist_off = queue_off + queue_bytes;           // keypoint list of the chunk being tested
-    static constexpr int klist_bytes = kQueueCap * 2;
-    static constexpr int wq_off = klist_off + klist_bytes;              // filter warps' stage-1 -> stage-2 queues
-    static constexpr int wq_bytes = 4 * kWarpQueueCap * 2;  // (a filter warp looks at 32 * SR / (2 kFilterWarps) <= 1024 / kFilterWarps groups)
-    static constexpr int vtab_off = wq_off + wq_bytes;                  // validity tables: first / middle / last chunk
-    static constexpr int vtab_bytes = 3 * kVtabWords * 4;
-    static constexpr int misc_off = vtab_off + vtab_bytes;
-    static constexpr int misc_bytes = 192;
-    static constexpr int total = misc_off + misc_bytes;
-    static_assert(tile_bytes % 128 == 0, "TMA destination must stay 128-byte aligned");
-    static_assert(plane_bytes % 16 == 0 && plane_off % 16 == 0, "the plane is cleared with 128-bit stores");
-    static_assert(SR % (2 * kFilterWarps) == 0 && SR <= 64, "filter warps take row pairs; queue entries hold 6 row bits");
-    static_assert(kFallbackWarps * kWarpQueueCap * 2 <= kQueueCap * 2 && kFallbackWarps <= kTestWarps,
-                  "the dense fallback borrows the keypoint list buffer for its warp queues");
-    static_assert(SR % (2 * kFallbackWarps) == 0, "fallback filter warps take row pairs");
-    static_assert(vtab_off % 16 == 0, "the validity tables are read with 128-bit loads");
-    static_assert(kGroupRows * kTileW <= kQueueCap, "a row group must always fit the candidate queue");
-    static_assert(SR % kGroupRows == 0, "the dense fallback walks whole row groups");
+// score planes / keypoint lists per CTA: two one-byte planes let the test warps fill the plane of chunk k + 1 while
+// the emit warps still read the plane of chunk k; SumAbsolute needs two-byte cells, so it gets one plane and the two
+// groups take turns on it
+__host__ __device__ constexpr int plane_bufs(int mode) { return mode == NMS_SUM_ABSOLUTE ? 1 : 2; }
+__host__ __device__ constexpr int plane_cell_bytes(int mode) { return mode == NMS_SUM_ABSOLUTE ? 2 : 1; }
+
+struct LayoutSizes {
+    int tile_bytes, plane_off, plane_bytes, queue_off, klist_off, ent_off, vtab_off, misc_off, total;
 };
+__host__ __device__ constexpr LayoutSizes layout_sizes(int mode, int sr) {
+    LayoutSizes l = {};
+    l.tile_bytes = tile_rows(sr) * kTileW;                                  // one TMA box
+    l.plane_off = kTileStages * l.tile_bytes;
+    l.plane_bytes = sr * kPlaneW * plane_cell_bytes(mode);                  // one plane
+    l.queue_off = l.plane_off + plane_bufs(mode) * l.plane_bytes;           // candidate queues [kQueueBufs][kQueueCap] u16
+    l.klist_off = l.queue_off + kQueueBufs * kQueueCap * 2;                 // keypoint lists [planes][kKlistCap] u16
+    l.ent_off = l.klist_off + plane_bufs(mode) * kKlistCap * 2;             // stage-1 entry tables [2][warps][kWarpQueueCap] u8
+    l.vtab_off = l.ent_off + 2 * kFilterWarps * kWarpQueueCap;              // validity tables: first / middle / last chunk
+    l.misc_off = l.vtab_off + 3 * kVtabWords * 4;
+    l.total = l.misc_off + 256;
+    return l;
+}
+
+// misc block (byte offsets)
+constexpr int kMiscFullBar = 0;     // [4] u64 tile landed
+constexpr int kMiscQFull = 32;      // [4] u64 candidate queue complete (one arrival per filter warp)
+constexpr int kMiscKFull = 64;      // [2] u64 score plane + keypoint list complete (the last test warp arrives)
+constexpr int kMiscPFree = 80;      // [2] u64 score plane + keypoint list free again (the last emit warp arrives)
+constexpr int kMiscQCount = 96;     // [4] u32 candidate queue fill
+constexpr int kMiscKCount = 112;    // [2] u32 keypoints of the chunk
+constexpr int kMiscTDone = 120;     // [4] u32 test warps done with the chunk
+constexpr int kMiscEDone = 136;     // [2] u32 emit warps done with the chunk
+constexpr int kMiscTicket = 144;    // [8] u32 strip tickets
+constexpr int kMiscNEnt = 176;      // [2][4] u32 stage-1 entries per filter warp
+constexpr int kMiscReqDone = 208;   // u32 tile requests issued so far (they are issued in stream order)
+constexpr int kMiscAbort = 212;     // u32 a wait timed out
+constexpr int kMiscTrace = 216;     // i32 (trace builds) index of this CTA in the trace table
+static_assert(kFilterWarps <= 4 && kTicketSlots == 8, "misc layout");
 
 // ---- decoupled look-back (one warp) -------------------------------------------------------------
 // status[i]: bits 63:62 = 0 empty / 1 aggregate of item i / 2 inclusive prefix up to item i.
@@ -234,208 +256,154 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long *statu
     return excl;
 }
 
-// Optional phase clocks (tools/phase_clocks.py builds the library with -DFDF_PHASE_CLOCKS): cycles per phase, summed over
-// the warps of a group (lane 0 of each) and over all CTAs.
-#ifdef FDF_PHASE_CLOCKS
-__device__ unsigned long long g_phase_clocks[16 * 16];  // [warp][slot]
-#define FDF_CLK_BEGIN                 \
-    long long clk_prev = clock64();   \
-    long long clk_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-#define FDF_CLK(slot)                              \
-    {                                              \
-        const long long clk_now = clock64();       \
-        clk_acc[slot] += clk_now - clk_prev;       \
-        clk_prev = clk_now;                        \
-    }
-#define FDF_CLK_END                                                                               \
-    if (lane == 0)                                                                                \
-        for (int i = 0; i < 10; i++)                                                              \
-            if (clk_acc[i]) atomicAdd(&g_phase_clocks[warp * 16 + i], (unsigned long long)clk_acc[i]);
-#elif defined(FDF_TRACE)
 // Timeline trace (tools/trace_timeline.py builds the library with -DFDF_TRACE): the CTAs resident on SM 0 write
 // clock64() at every phase boundary of their first kTraceChunks chunks, per warp (lane 0), into a global table.
+#ifdef FDF_TRACE
 constexpr int kTraceCtas = 4, kTraceChunks = 200, kTraceSlots = 12;
 __device__ long long g_trace[kTraceCtas][16][kTraceChunks][kTraceSlots];
 __device__ unsigned int g_trace_n;
-#define FDF_CLK_BEGIN
 #define FDF_CLK(slot)                                                                                           \
     if (trace_cta >= 0 && lane == 0 && gc < (uint32_t)kTraceChunks) g_trace[trace_cta][warp][gc][slot] = clock64();
-#define FDF_CLK_END
 #else
-#define FDF_CLK_BEGIN
 #define FDF_CLK(slot)
-#define FDF_CLK_END
-#endif
-#ifdef FDF_TRACE
-#define FDF_TRACE_ROW \
-    ((trace_cta >= 0 && lane == 0 && gc < (uint32_t)kTraceChunks) ? &g_trace[trace_cta][warp][gc][0] : nullptr)
-#else
-#define FDF_TRACE_ROW nullptr
 #endif
 
 // ---- the detection kernel ----------------------------------------------------------------------
-// Two groups of warps per CTA, coupled only through mbarriers (no CTA-wide barrier inside the chunk loop):
-//   filter warps (0 .. kFilterWarps-1): wait for chunk k's tile, run phase A into candidate queue k % 3,
-//       arrive on q_full[k % 3], go on to chunk k + 1;
-//   test warps (the others): wait on q_full[k % 3], run phase B, barrier among themselves, then one thread
-//       requests the tile of chunk k + 2 (the tile buffer of chunk k is free now), all run the NMS pass over
-//       the chunk's keypoint list, barrier, and the last warp copies the survivors to the staging buffer
-//       while the others already wait for chunk k + 1.
-// A landed tile k + 2 implies that chunk k - 1 is completely done, hence that queue (k + 2) % 3 is free again.
-// Timing experiment (-DFDF_QFULL_BAR): queue hand-off filter -> test warps on a hardware named barrier (ids 4 ..): the
-// filter warps only ARRIVE, the test warps SYNC, i.e. they block in hardware instead of polling an mbarrier (the q_full
-// polls are 15 % of all executed instructions).  Measured 1.9 % SLOWER (1.035 vs 1.015 ms per 256 frames): the polls
-// use issue slots nobody else wants, and a polled wait is left sooner than a named barrier.  Default: mbarrier.
-__device__ __forceinline__ void qfull_arrive(uint32_t qb) {  // (immediate barrier ids: a register id reserves all 16)
-    if (qb == 0u) asm volatile("bar.arrive 4, %0;" ::"n"(kThreads) : "memory");
-    else if (qb == 1u) asm volatile("bar.arrive 5, %0;" ::"n"(kThreads) : "memory");
-    else if (qb == 2u) asm volatile("bar.arrive 6, %0;" ::"n"(kThreads) : "memory");
-    else asm volatile("bar.arrive 7, %0;" ::"n"(kThreads) : "memory");
-}
-__device__ __forceinline__ void qfull_sync(uint32_t qb) {
-    if (qb == 0u) asm volatile("bar.sync 4, %0;" ::"n"(kThreads) : "memory");
-    else if (qb == 1u) asm volatile("bar.sync 5, %0;" ::"n"(kThreads) : "memory");
-    else if (qb == 2u) asm volatile("bar.sync 6, %0;" ::"n"(kThreads) : "memory");
-    else asm volatile("bar.sync 7, %0;" ::"n"(kThreads) : "memory");
-}
-
-__device__ __forceinline__ void bar_test_group() {
-    asm volatile("bar.sync 1, %0;" ::"n"(kTestThreads) : "memory");
+// Persistent CTAs; a CTA draws strips (frame, rows) from an atomic ticket and walks each strip chunk by chunk.  Its
+// warps form a three-stage pipeline over the stream of chunks, coupled ONLY through mbarriers and a few shared
+// counters -- no CTA-wide barrier, and no barrier at all inside the test and emit groups, whose warps drift freely:
+//
+//   filter warps (kFilterWarps)   wait for the chunk's tile (TMA, full_bar) -> stage 1 over their own rows -> one
+//                                 barrier among the filter warps -> stage 2 over ALL warps' entries, dealt evenly ->
+//                                 candidate queue (one per tile buffer) -> arrive on q_full.
+//   test warps (kTestWarps)       wait q_full and p_free (the plane and keypoint list of chunk k - planes are free) ->
+//                                 exact test + score per candidate -> score plane, keypoint list.  The LAST test warp
+//                                 to finish a chunk (shared counter) arrives on k_full and requests the tile of chunk
+//                                 k + kTileStages: the tile and the candidate queue of chunk k are free now.
+//   emit warps (kEmitWarps)       wait k_full -> strict 3x3 maximum per listed keypoint on the plane -> survivors into
+//                                 the warp's own run of the staging buffer (ballot-ranked, no atomics), run record.  The
+//                                 LAST emit warp wipes the chunk's cells from the plane and arrives on p_free.
+//
+// Why this shape (profiles/r02_v15_timeline_3ctas.txt): with per-warp stage-2 queues one filter warp regularly took
+// 3-4 times as long as the others (a horizontal edge puts most of a chunk's 16-pixel groups into one warp's rows),
+// the test group waited for it, the filter group then waited for the test group's tile request, and the test group's
+// own chain (test -> barrier -> tile request -> NMS -> barrier -> bookkeeping by one thread) was the longest stage.
+// Stream bookkeeping: a chunk is (strip sequence number `it` of this CTA, chunk c of the strip); every warp walks the
+// same sequence on its own.  The ticket of strip `it` sits in s_ticket[it % kTicketSlots]; it is drawn by the thread
+// that requests the strip's first tile.  Tile requests are issued in stream order (s_req_done), so tickets are drawn in
+// order and the first ticket beyond the last strip ends the stream for everybody.
+__device__ __forceinline__ void bar_filter_group() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kFilterThreads) : "memory");
 }
 
-// Staging space is handed out in two levels: a CTA takes blocks of kStageBlock entries from the global cursor
-// (one contended atomic every few dozen chunks instead of one per chunk, which sat on the test warps' critical
-// path) and cuts its runs from the current block.  s_block[0] = next free entry, s_block[1] = end of the block.
-// Only thread t0 calls these, between barriers of the test group.
-// A chunk's run is opened before its size is known (room for a full keypoint list), written by the NMS pass, and
-// closed at its real size: the unused tail goes back to the block.
-__device__ __forceinline__ unsigned long long reserve_staging(uint32_t count, unsigned long long *s_block,
-                                                              const DetectParams &p) {
-    unsigned long long next = s_block[0];
-    if (next + count > s_block[1]) {
-        const unsigned long long n = count > (uint32_t)kStageBlock ? count : (unsigned long long)kStageBlock;
-        next = atomicAdd(p.cursor, n);
-        s_block[1] = next + n;
-    }
-    s_block[0] = next + count;
-    return next;
-}
-
-__device__ __forceinline__ unsigned long long open_run(unsigned long long *s_block, const DetectParams &p) {
-    if (s_block[0] + (unsigned long long)kQueueCap > s_block[1]) {
-        s_block[0] = atomicAdd(p.cursor, (unsigned long long)kStageBlock);
-        s_block[1] = s_block[0] + (unsigned long long)kStageBlock;
-    }
-    return s_block[0];
+__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
+    return *reinterpret_cast<const volatile uint32_t *>(p);
 }
 
 template <int MODE, int SR>
-#ifndef FDF_SMALL_SR_CTAS
-#define FDF_SMALL_SR_CTAS 4
-#endif
-__global__ void __launch_bounds__(kThreads, SR >= 48 ? 3 : FDF_SMALL_SR_CTAS)
+__global__ void __launch_bounds__(kThreads, SR >= 48 ? 3 : 4)
 fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p) {
-    using L = Layout<MODE, SR>;
+    typedef typename PlaneCell<MODE>::type cell_t;
+    constexpr LayoutSizes L = layout_sizes(MODE, SR);
+    constexpr int PL = plane_bufs(MODE);
     constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;  // score halo (rows and columns) needed by the 3x3 NMS
     constexpr int OUT_R = out_rows(MODE, SR);
+    static_assert(L.tile_bytes % 128 == 0, "TMA destination must stay 128-byte aligned");
+    static_assert(L.plane_bytes % 16 == 0 && L.plane_off % 16 == 0, "the plane is cleared with 128-bit stores");
+    static_assert(SR % (2 * kFilterWarps) == 0 && SR <= 64, "filter warps take row pairs; queue entries hold 6 row bits");
+    static_assert(L.vtab_off % 16 == 0 && L.misc_off % 8 == 0, "alignment of the validity tables / mbarriers");
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *tiles = smem;
-    uint16_t *plane = reinterpret_cast<uint16_t *>(smem + L::plane_off);
-    uint16_t *queues = reinterpret_cast<uint16_t *>(smem + L::queue_off);              // [kQueueBufs][kQueueCap]
-    uint16_t *klist = reinterpret_cast<uint16_t *>(smem + L::klist_off);               // [kQueueCap]
-    uint16_t *wqs = reinterpret_cast<uint16_t *>(smem + L::wq_off);                    // [kFilterWarps][kWarpQueueCap]
-    uint32_t *vtabs = reinterpret_cast<uint32_t *>(smem + L::vtab_off);                 // [3][kVtabWords]
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::misc_off);             // [kTileStages] tile landed
-    uint64_t *q_full = reinterpret_cast<uint64_t *>(smem + L::misc_off + 32);          // [kQueueBufs] candidate queue complete
-    uint32_t *qcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 64);          // [kQueueBufs] queue fill
-    uint32_t *s_ticket = reinterpret_cast<uint32_t *>(smem + L::misc_off + 80);        // [2] strip tickets (strip parity)
-    uint32_t *scount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 88);          // keypoints staged by the chunk so far
-    uint32_t *s_total = reinterpret_cast<uint32_t *>(smem + L::misc_off + 92);         // keypoints of the strip so far
-    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 96);
-    unsigned long long *s_block = reinterpret_cast<unsigned long long *>(smem + L::misc_off + 104);  // [2] staging block
-    volatile uint32_t *s_abort = reinterpret_cast<volatile uint32_t *>(smem + L::misc_off + 120);    // a wait timed out
-    uint32_t *kcount = reinterpret_cast<uint32_t *>(smem + L::misc_off + 124);         // [2] keypoint list fill (chunk parity)
-    [[maybe_unused]] volatile long long *clk_req =
-        reinterpret_cast<volatile long long *>(smem + L::misc_off + 136);              // [kTileStages] (phase clocks only)
+    cell_t *planes = reinterpret_cast<cell_t *>(smem + L.plane_off);                     // [PL][SR * kPlaneW]
+    uint16_t *queues = reinterpret_cast<uint16_t *>(smem + L.queue_off);                 // [kQueueBufs][kQueueCap]
+    uint16_t *klists = reinterpret_cast<uint16_t *>(smem + L.klist_off);                 // [PL][kKlistCap]
+    uint8_t *ents = smem + L.ent_off;                                                    // [2][kFilterWarps][kWarpQueueCap]
+    uint32_t *vtabs = reinterpret_cast<uint32_t *>(smem + L.vtab_off);                   // [3][kVtabWords]
+    uint8_t *misc = smem + L.misc_off;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(misc + kMiscFullBar);
+    uint64_t *q_full = reinterpret_cast<uint64_t *>(misc + kMiscQFull);
+    uint64_t *k_full = reinterpret_cast<uint64_t *>(misc + kMiscKFull);
+    uint64_t *p_free = reinterpret_cast<uint64_t *>(misc + kMiscPFree);
+    uint32_t *qcount = reinterpret_cast<uint32_t *>(misc + kMiscQCount);
+    uint32_t *kcount = reinterpret_cast<uint32_t *>(misc + kMiscKCount);
+    uint32_t *t_done = reinterpret_cast<uint32_t *>(misc + kMiscTDone);
+    uint32_t *e_done = reinterpret_cast<uint32_t *>(misc + kMiscEDone);
+    uint32_t *s_ticket = reinterpret_cast<uint32_t *>(misc + kMiscTicket);
+    uint32_t *s_nent = reinterpret_cast<uint32_t *>(misc + kMiscNEnt);
+    uint32_t *s_req_done = reinterpret_cast<uint32_t *>(misc + kMiscReqDone);
+    volatile uint32_t *s_abort = reinterpret_cast<volatile uint32_t *>(misc + kMiscAbort);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = (int)p.w, H = (int)p.h;
     const int NC = (int)p.chunks_per_strip;
     const uint32_t total_items = p.n_frames * p.strips_per_frame;
-    const bool is_filter = warp < kFilterWarps;
-    const int ttid = tid - kFilterWarps * 32;  // thread index inside the test group
-#ifndef FDF_T0_WARP
-#define FDF_T0_WARP (kTestWarps - 1)
-#endif
-    // the thread that draws tickets, requests tiles and keeps the run records: lane 0 of the LAST test warp, which gets
-    // the smallest share of every candidate / keypoint list -- its serial work between the group's barriers then
-    // overlaps the other warps' list work instead of extending the critical path
-    const bool t0 = ttid == 32 * FDF_T0_WARP;
 
-    uint32_t cur = 0u, nxt = 0xffffffffu;
-    bool have_nxt = false;
-    const int ahead = NC >= kTileStages ? kTileStages : NC;  // tiles requested this many chunks ahead (never beyond the next strip)
-
-    // request the tile of chunk c of the current strip (c < NC) or of chunk c - NC of the next strip; `it` is the
-    // current strip's sequence number in this CTA.  When the work is exhausted the barrier is completed without
-    // a tile, so that the filter warps wake up and see the end ticket.
-    auto request_tile = [&](int c, uint32_t stream_index, uint32_t it) {
-        uint32_t item = cur;
-        if (c >= NC) {
-            if (c - NC >= NC) return;
-            if (!have_nxt) {
-                nxt = atomicAdd(p.ticket, 1u);
-                have_nxt = true;
-                s_ticket[(it + 1u) & 1u] = nxt;
+    // Requests the tile of stream position r = chunk cr of strip sequence number itr (one thread).  Requests are issued
+    // in stream order: the caller for position r waits until the requests 0 .. r-1 have been issued, which also makes
+    // the ticket of a strip, drawn with its first tile, visible to the requests of its other tiles.  When the tickets
+    // are exhausted the barrier is completed without a tile, so that the filter warps wake up and see the end ticket.
+    auto request_tile = [&](uint32_t r, uint32_t itr, int cr) {
+        const unsigned long long t_begin = global_timer_ns();
+        while (ld_volatile_shared(s_req_done) != r) {
+            if (*s_abort != 0u) return;
+            if (global_timer_ns() - t_begin > kWaitLimitNs) {
+                atomicOr(p.flags, kFlagTmaTimeout);
+                *s_abort = 1u;
+                return;
             }
-            item = nxt;
-            c -= NC;
         }
-        const uint32_t stage = stream_index % (uint32_t)kTileStages;
+        __threadfence_block();
+        uint32_t item;
+        if (cr == 0) {
+            item = atomicAdd(p.ticket, 1u);
+            s_ticket[itr % (uint32_t)kTicketSlots] = item;
+        } else {
+            item = s_ticket[itr % (uint32_t)kTicketSlots];
+        }
+        const uint32_t stage = r % (uint32_t)kTileStages;
         if (item >= total_items) {
             mbar_arrive(&full_bar[stage]);
-            return;
+        } else {
+            const uint32_t frame = item / p.strips_per_frame;
+            const uint32_t strip = item - frame * p.strips_per_frame;
+            const int ty0 = first_out_row(MODE) + (int)strip * OUT_R - HS - 3;  // image row of tile row 0
+            mbar_expect_tx(&full_bar[stage], (uint32_t)L.tile_bytes);
+            tma_load_3d(tiles + stage * L.tile_bytes, &tmap, cr * kChunkW - kTileLead, ty0, (int)frame, &full_bar[stage]);
+            // and pull the strip's next tile into L2 (cp.async.bulk.prefetch.tensor: no shared memory, no completion), so
+            // that its load, one chunk from now, is an L2 hit
+            if (FDF_L2_PREFETCH > 0 && cr + FDF_L2_PREFETCH < NC)
+                tma_prefetch_l2_3d(&tmap, (cr + FDF_L2_PREFETCH) * kChunkW - kTileLead, ty0, (int)frame);
         }
-        const uint32_t frame = item / p.strips_per_frame;
-        const uint32_t strip = item - frame * p.strips_per_frame;
-        const int ty0 = first_out_row(MODE) + (int)strip * OUT_R - HS - 3;  // image row of tile row 0
-#ifdef FDF_PHASE_CLOCKS
-        clk_req[stage] = clock64();
-#endif
-        mbar_expect_tx(&full_bar[stage], (uint32_t)L::tile_bytes);
-        tma_load_3d(tiles + stage * L::tile_bytes, &tmap, c * kChunkW - kTileLead, ty0, (int)frame, &full_bar[stage]);
-        // and pull the strip's next tile into L2 (cp.async.bulk.prefetch.tensor: no shared memory, no completion), so
-        // that its load, one chunk from now, is an L2 hit (+1 %; 2 or 4 chunks ahead measured no better)
-        if (FDF_L2_PREFETCH > 0 && c + FDF_L2_PREFETCH < NC)
-            tma_prefetch_l2_3d(&tmap, (c + FDF_L2_PREFETCH) * kChunkW - kTileLead, ty0, (int)frame);
+        __threadfence_block();
+        *reinterpret_cast<volatile uint32_t *>(s_req_done) = r + 1u;
     };
 
-    if (t0) {
+    if (tid == 0) {
         tma_prefetch_desc(&tmap);
-        for (int i = 0; i < kTileStages; i++) mbar_init(&full_bar[i], 1);
-        for (int i = 0; i < kQueueBufs; i++) {
+        for (int i = 0; i < kTileStages; i++) {
+            mbar_init(&full_bar[i], 1);
             mbar_init(&q_full[i], kFilterWarps);
             qcount[i] = 0u;
+            t_done[i] = 0u;
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&p_free[i], 1);
+            kcount[i] = 0u;
+            e_done[i] = 0u;
         }
         fence_mbar_init();
-        *scount = 0u;
-        *s_total = 0u;
+        *s_req_done = 0u;
         *s_abort = 0u;
-        kcount[0] = kcount[1] = 0u;
-        s_block[0] = s_block[1] = 0ull;
-        *s_base = open_run(s_block, p);
-        cur = atomicAdd(p.ticket, 1u);
-        s_ticket[0] = cur;
     }
     if (tid < 3 * kVtabWords) vtabs[tid] = valid_word<MODE>(W, vtab_chunk(tid / kVtabWords, NC), tid % kVtabWords);
-    auto clear_plane = [&](int i0, int n) {  // by n threads, i0 = index of this one
-        uint4 *pz = reinterpret_cast<uint4 *>(plane);
-        for (int i = i0; i < L::plane_bytes / 16; i += n) pz[i] = make_uint4(0u, 0u, 0u, 0u);
-    };
-    clear_plane(tid, kThreads);
+    {
+        uint4 *pz = reinterpret_cast<uint4 *>(planes);
+        for (int i = tid; i < PL * L.plane_bytes / 16; i += kThreads) pz[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
 #ifdef FDF_TRACE
-    volatile int &s_trace_cta = *reinterpret_cast<volatile int *>(smem + L::misc_off + 176);
+    volatile int &s_trace_cta = *reinterpret_cast<volatile int *>(misc + kMiscTrace);
     if (tid == 0) {
         unsigned int smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -450,213 +418,246 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
 #ifdef FDF_TRACE
     const int trace_cta = s_trace_cta;
 #endif
-    cur = s_ticket[0];
-    if (t0)
-        for (int c = 0; c < ahead; c++) request_tile(c, (uint32_t)c, 0u);  // (ahead <= NC: all of the first strip)
+    if (tid == 0) {  // the first kTileStages tiles of the stream
+        uint32_t itr = 0u;
+        int cr = 0;
+        for (uint32_t r = 0; r < (uint32_t)kTileStages; r++) {
+            request_tile(r, itr, cr);
+            if (++cr == NC) {
+                cr = 0;
+                itr++;
+            }
+        }
+    }
 
     const int t = (int)p.threshold, n = (int)p.count;
-    const uint32_t kbias = filter_kbias(p.threshold);
-    uint32_t gc = 0;   // chunks processed by this CTA so far
+    uint32_t gc = 0;            // stream position of the chunk this warp works on
     uint32_t qb = 0, qpar = 0;  // tile stage = queue buffer = gc % kTileStages, and the parity of their mbarrier phases
-
-    if (is_filter) {
-        // ================================ filter warps =================================================
-        uint16_t *wq = wqs + warp * (4 * kWarpQueueCap / kFilterWarps);
-        FDF_CLK_BEGIN
-        for (uint32_t it = 0; cur < total_items; it++) {
-            const uint32_t frame = cur / p.strips_per_frame;
-            const uint32_t strip = cur - frame * p.strips_per_frame;
-            for (int c = 0; c < NC; c++, gc++) {
-                const uint32_t stage = qb;
-                const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
-#ifdef FDF_PHASE_CLOCKS
-                uint32_t landed;
-                asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                             : "=r"(landed) : "r"(smem_u32(&full_bar[stage])), "r"(qpar) : "memory");
-                const bool had_to_wait = landed == 0u;
-#endif
-                mbar_wait(&full_bar[stage], qpar, p.flags, s_abort);  // (also: queue qb is free again)
-#ifdef FDF_PHASE_CLOCKS
-                if (had_to_wait) {
-                    clk_acc[8] += clock64() - clk_req[stage];
-                    clk_acc[9] += 1;
-                }
-#endif
-                FDF_CLK(0)
-#if !(FDF_ABLATE & 4)
-                phase_a_warp<MODE, SR, kFilterWarps>(warp, lane, tiles + stage * L::tile_bytes, wq,
-                                                     vtabs + vtab_variant(c, NC) * kVtabWords, vtab_variant(c, NC),
-                                                     queues + qb * kQueueCap,
-                                                     &qcount[qb], g, kbias, 0, SR, FDF_TRACE_ROW);
-#endif
-                __syncwarp();
-#ifndef FDF_QFULL_BAR
-                if (lane == 0) mbar_arrive(&q_full[qb]);
-#else
-                qfull_arrive(qb);
-#endif
-                FDF_CLK(1)
-                if (++qb == (uint32_t)kQueueBufs) {
-                    qb = 0;
-                    qpar ^= 1u;
-                }
-            }
-            // the next strip's ticket is published before its first tile is requested (or the end is signalled)
-            mbar_wait(&full_bar[qb], qpar, p.flags, s_abort);
-            FDF_CLK(2)
-            cur = s_ticket[(it + 1u) & 1u];
+    uint32_t pi = 0, ppar = 0;  // plane / keypoint list = gc % PL, and the parity of their mbarrier phases
+    uint32_t cur = 0;           // ticket (frame, strip) of the current strip
+    auto next_chunk = [&]() {
+        gc++;
+        if (++qb == (uint32_t)kQueueBufs) {
+            qb = 0;
+            qpar ^= 1u;
         }
-        FDF_CLK_END
-        return;
-    }
-
-    // ==================================== test warps ===================================================
-    uint32_t tag = 1u;  // (gc % kTagPeriod) + 1
-    const int twarp = warp - kFilterWarps;
-    // t0, between the group's barriers: the chunk's run record and the strip's running total
-    auto close_run = [&](uint32_t slot, uint32_t count, bool last) {
-        if (count != 0u) {
-            p.run_base[slot] = *s_base;
-            p.run_count[slot] = count;
+        if (++pi == (uint32_t)PL) {
+            pi = 0;
+            ppar ^= 1u;
         }
-        p.run_n[slot] = count != 0u ? 1u : 0u;
-        const uint32_t tot = *s_total + count;
-        if (last) p.item_count[cur] = tot;
-        *s_total = last ? 0u : tot;
     };
-    FDF_CLK_BEGIN
-    for (uint32_t it = 0; cur < total_items; it++) {
-        const uint32_t frame = cur / p.strips_per_frame;
-        const uint32_t strip = cur - frame * p.strips_per_frame;
-        for (int c = 0; c < NC; c++, gc++) {
-            const uint32_t stage = qb;
-            const uint8_t *tile = tiles + stage * L::tile_bytes;
-            uint16_t *queue = queues + qb * kQueueCap;
-            const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
-            const uint32_t slot = cur * (uint32_t)NC + (uint32_t)c;
-            if (tag == 1u && gc != 0u) {  // every 15 chunks: restart the tags on a cleared plane
-                clear_plane(ttid, kTestThreads);
-                bar_test_group();
-            }
-#ifndef FDF_QFULL_BAR
-            mbar_wait(&q_full[qb], qpar, p.flags, s_abort);
-#else
-            qfull_sync(qb);
-#endif
-            mbar_wait(&full_bar[stage], qpar, p.flags, s_abort);  // (completed long ago: makes the tile visible here too)
-            FDF_CLK(4)
-            const uint32_t qn = qcount[qb];
-            if (qn <= (uint32_t)kQueueCap) {
-                // Timing experiment (-DFDF_EARLY_TILE_REQUEST, measured 4.5 % SLOWER: 1.069 vs 1.022 ms per 256 frames):
-                // the tile and the candidate queue of this chunk are free as soon as every test thread has loaded
-                // the ring bytes of its last candidate, so the other warps only ARRIVE on named barrier 2 there and
-                // the housekeeping warp waits on it and requests the tile of chunk k + 2 before the arithmetic of
-                // the last step.  Default: the request follows the group barrier after phase B.
-                auto tile_done = [&]() {
-#ifdef FDF_EARLY_TILE_REQUEST
-                    if (twarp == FDF_T0_WARP) {
-                        asm volatile("bar.sync 2, %0;" ::"n"(kTestThreads) : "memory");
-                        if (t0) {
-                            qcount[qb] = 0u;
-                            request_tile(c + ahead, gc + (uint32_t)ahead, it);
-                        }
-                    } else {
-                        asm volatile("bar.arrive 2, %0;" ::"n"(kTestThreads) : "memory");
+
+    if (warp < kFilterWarps) {
+        // ================================ filter warps =================================================
+        const uint32_t kbias = filter_kbias(p.threshold);
+        for (uint32_t it = 0;; it++) {
+            for (int c = 0; c < NC; c++) {
+                mbar_wait(&full_bar[qb], qpar, p.flags, s_abort);  // the tile has landed (also: queue qb is free again)
+                if (c == 0) {
+                    cur = s_ticket[it % (uint32_t)kTicketSlots];
+                    if (cur >= total_items || *s_abort != 0u) {  // the stream has ended: pass the news on and leave
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&q_full[qb]);
+                        return;
                     }
-#endif
-                };
-#if !(FDF_ABLATE & 1)
-                phase_b<MODE, SR, kTestUnroll>(ttid, lane, kTestThreads, qn, tile, queue, klist, &kcount[gc & 1u], plane, t, n, tag,
-                                               tile_done);
-#else
-                tile_done();
-#endif
+                }
+                FDF_CLK(0)
+                const uint32_t frame = cur / p.strips_per_frame;
+                const uint32_t strip = cur - frame * p.strips_per_frame;
+                const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
+                const uint8_t *tile = tiles + qb * L.tile_bytes;
+                uint8_t *eb = ents + (gc & 1u) * (kFilterWarps * kWarpQueueCap);
+                uint32_t *nent = s_nent + (gc & 1u) * 4u;
+                const uint32_t ne = phase_a_stage1<MODE, SR, kFilterWarps>(warp, lane, tile, eb + warp * kWarpQueueCap, g, kbias);
+                if (lane == 0) nent[warp] = ne;
+                FDF_CLK(9)
+                bar_filter_group();  // every warp's entries of this chunk are in the table
+                FDF_CLK(10)
+                phase_a_stage2<MODE, SR, kFilterWarps>(tid, kFilterThreads, tile, eb, nent,
+                                                       vtabs + vtab_variant(c, NC) * kVtabWords, queues + qb * kQueueCap,
+                                                       &qcount[qb], kbias);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&q_full[qb]);
+                FDF_CLK(1)
+                next_chunk();
+            }
+        }
+    } else if (warp < kFilterWarps + kTestWarps) {
+        // ==================================== test warps ===================================================
+        const int twarp = warp - kFilterWarps, ttid = tid - kFilterThreads;
+        for (uint32_t it = 0;; it++) {
+            for (int c = 0; c < NC; c++) {
+                mbar_wait(&q_full[qb], qpar, p.flags, s_abort);
+                mbar_wait(&full_bar[qb], qpar, p.flags, s_abort);  // (completed long ago: makes the tile visible here too)
+                if (c == 0) cur = s_ticket[it % (uint32_t)kTicketSlots];
+                const bool ended = cur >= total_items || *s_abort != 0u;
+                mbar_wait(&p_free[pi], ppar ^ 1u, p.flags, s_abort);  // plane pi and its keypoint list are free
+                FDF_CLK(4)
+                uint32_t qn = 0u;
+                if (!ended) {
+                    const uint32_t frame = cur / p.strips_per_frame;
+                    const uint32_t strip = cur - frame * p.strips_per_frame;
+                    const uint8_t *tile = tiles + qb * L.tile_bytes;
+                    cell_t *plane = planes + pi * (SR * kPlaneW);
+                    qn = qcount[qb];
+                    if (qn <= (uint32_t)kQueueCap) {
+                        phase_b<MODE, SR>(ttid, lane, kTestThreads, qn, tile, queues + qb * kQueueCap, klists + pi * kKlistCap,
+                                          &kcount[pi], plane, t, n);
+                    } else {  // very dense content: every pixel, straight from the tile
+                        const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
+                        phase_b_dense<MODE, SR>(twarp, lane, kTestWarps, tile, plane, g, c, t, n);
+                    }
+                }
                 FDF_CLK(5)
-                bar_test_group();  // every score of this chunk is in the plane and its keypoint list is complete
-                FDF_CLK(3)
-#if !defined(FDF_EARLY_TILE_REQUEST) && !defined(FDF_LATE_TILE_REQUEST)
-                if (t0) {
-                    qcount[qb] = 0u;
-                    request_tile(c + ahead, gc + (uint32_t)ahead, it);
+                __syncwarp();
+                // the last test warp to get here hands the chunk on and recycles its tile and candidate queue
+                uint32_t last = 0u;
+                if (lane == 0) {
+                    __threadfence_block();
+                    last = atomicAdd(&t_done[qb], 1u) == (uint32_t)(kTestWarps - 1) ? 1u : 0u;
+                    if (last) {
+                        __threadfence_block();
+                        t_done[qb] = 0u;
+                        if (!ended) {
+                            if (qn > (uint32_t)kQueueCap) kcount[pi] = kDenseMark;
+                            qcount[qb] = 0u;
+                        }
+                        __threadfence_block();
+                        mbar_arrive(&k_full[pi]);
+                        if (!ended) {
+                            uint32_t itr = it;
+                            int cr = c + kTileStages;
+                            while (cr >= NC) {
+                                cr -= NC;
+                                itr++;
+                            }
+                            request_tile(gc + (uint32_t)kTileStages, itr, cr);
+                        }
+                    }
                 }
-#endif
                 FDF_CLK(6)
-#if !(FDF_ABLATE & 2)
-                emit_list<MODE, SR>(ttid, kTestThreads, kcount[gc & 1u], klist, plane, scount, *s_base, p.staging_cap,
-                                    p.staging, g);
-#endif
-                FDF_CLK(7)
-                bar_test_group();  // the run is complete; the keypoint list is free
-#ifdef FDF_LATE_TILE_REQUEST  // timing experiment: the filter group gets its next tile only after the NMS pass
-                if (t0) {
-                    qcount[qb] = 0u;
-                    request_tile(c + ahead, gc + (uint32_t)ahead, it);
+                if (ended) return;
+                next_chunk();
+            }
+        }
+    } else {
+        // ==================================== emit warps ===================================================
+        const int ewarp = warp - kFilterWarps - kTestWarps;
+        constexpr int kEmitThreads = kEmitWarps * 32;
+        const uint32_t lt = (1u << lane) - 1u;
+        unsigned long long blk_next = 0ull, blk_end = 0ull;  // this warp's staging block (warp-uniform)
+        uint32_t strip_total = 0u;                           // keypoints this warp staged for the current strip
+        bool overflow = false;
+        // room for `need` entries in the warp's block, or a new block from the global cursor
+        auto ensure_room = [&](uint32_t need) {
+            if (blk_next + need > blk_end) {
+                const unsigned long long nblk = need > (uint32_t)kStageBlock ? need : (unsigned long long)kStageBlock;
+                unsigned long long b = 0ull;
+                if (lane == 0) b = atomicAdd(p.cursor, nblk);
+                blk_next = __shfl_sync(0xffffffffu, b, 0);
+                blk_end = blk_next + nblk;
+            }
+        };
+        for (uint32_t it = 0;; it++) {
+            for (int c = 0; c < NC; c++) {
+                mbar_wait(&k_full[pi], ppar, p.flags, s_abort);
+                if (c == 0) cur = s_ticket[it % (uint32_t)kTicketSlots];
+                if (cur >= total_items || *s_abort != 0u) {
+                    if (overflow && lane == 0) atomicOr(p.flags, kFlagStagingOverflow);
+                    return;
                 }
-#endif
-                if (t0) {
-                    const uint32_t count = *scount;
-                    *scount = 0u;
-                    kcount[gc & 1u] = 0u;  // (next used two chunks from now)
-                    close_run(slot, count, c == NC - 1);
-                    s_block[0] = *s_base + count;  // give the unused tail back
-                    *s_base = open_run(s_block, p);
+                FDF_CLK(7)
+                const uint32_t frame = cur / p.strips_per_frame;
+                const uint32_t strip = cur - frame * p.strips_per_frame;
+                const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
+                const cell_t *plane = planes + pi * (SR * kPlaneW);
+                const uint16_t *klist = klists + pi * kKlistCap;
+                const uint32_t kn = kcount[pi];
+                uint32_t count = 0u;
+                if (kn <= (uint32_t)kKlistCap) {
+                    // this warp's share of the keypoint list: entries ewarp * 32 + lane, + kEmitThreads, ...
+                    ensure_room(kn);
+                    for (uint32_t ib = (uint32_t)(ewarp * 32); ib < kn; ib += (uint32_t)kEmitThreads) {
+                        const uint32_t i = ib + (uint32_t)lane;
+                        const uint32_t ent = klist[i < kn ? i : ib];
+                        const bool keep = i < kn && list_entry_survives<MODE, SR>(ent, plane, g);
+                        const uint32_t b = __ballot_sync(0xffffffffu, keep);
+                        if (keep) {
+                            const unsigned long long o = blk_next + count + (uint32_t)__popc(b & lt);
+                            if (o < p.staging_cap) p.staging[o] = staged_entry<MODE>((int)(ent >> 8), (int)(ent & 0xffu), g);
+                            else overflow = true;
+                        }
+                        count += (uint32_t)__popc(b);
+                    }
+                } else {
+                    // the list overflowed or the chunk went through the dense path: scan this warp's rows of the plane,
+                    // count first (the run is reserved at its exact size), then write
+                    constexpr int kCells = SR * kPlaneW, kPer = (kCells + kEmitWarps - 1) / kEmitWarps;
+                    const int i0 = ewarp * kPer, i1 = min(kCells, i0 + kPer);
+                    for (int ib = i0; ib < i1; ib += 32) {
+                        const int i = ib + lane;
+                        const bool keep = i < i1 && plane_cell_survives<MODE, SR>(i, plane, g);
+                        count += (uint32_t)__popc(__ballot_sync(0xffffffffu, keep));
+                    }
+                    ensure_room(count);
+                    uint32_t at = 0u;
+                    for (int ib = i0; ib < i1; ib += 32) {
+                        const int i = ib + lane;
+                        const bool keep = i < i1 && plane_cell_survives<MODE, SR>(i, plane, g);
+                        const uint32_t b = __ballot_sync(0xffffffffu, keep);
+                        if (keep) {
+                            const unsigned long long o = blk_next + at + (uint32_t)__popc(b & lt);
+                            if (o < p.staging_cap) p.staging[o] = staged_entry<MODE>(i / kPlaneW, i % kPlaneW + kPlaneLead, g);
+                            else overflow = true;
+                        }
+                        at += (uint32_t)__popc(b);
+                    }
                 }
                 FDF_CLK(8)
-            } else {
-                // very dense content: redo the chunk kGroupRows rows at a time (the test warps filter for themselves;
-                // their warp queues live in the keypoint list buffer, which this path does not use), then
-                // emit from the score plane: count, reserve, write
-                uint16_t *wq = klist + twarp * kWarpQueueCap;
-                const uint32_t *vtab = vtabs + vtab_variant(c, NC) * kVtabWords;
-                for (int lo = 0; lo < SR; lo += kGroupRows) {
-                    bar_test_group();
-                    if (t0) qcount[qb] = 0u;
-                    bar_test_group();
-                    if (twarp < kFallbackWarps)
-                        phase_a_warp<MODE, SR, kFallbackWarps>(twarp, lane, tile, wq, vtab, vtab_variant(c, NC), queue,
-                                                               &qcount[qb], g, kbias,
-                                                               lo, lo + kGroupRows);
-                    bar_test_group();
-                    phase_b<MODE, SR>(ttid, lane, kTestThreads, qcount[qb], tile, queue, nullptr, nullptr, plane, t, n, tag);
+                if (lane == 0) {  // the warp's run record of this chunk
+                    const size_t slot = ((size_t)cur * (size_t)NC + (size_t)c) * kRunsPerChunk + (size_t)ewarp;
+                    p.run_base[slot] = blk_next;
+                    p.run_count[slot] = count;
                 }
-                bar_test_group();  // every score of this chunk is in the plane; tile[stage] is free again
-                if (t0) {
-                    qcount[qb] = 0u;
-                    request_tile(c + ahead, gc + (uint32_t)ahead, it);
+                blk_next += count;
+                strip_total += count;
+                if (c == NC - 1) {
+                    if (lane == 0 && strip_total != 0u) atomicAdd(&p.item_count[cur], strip_total);
+                    strip_total = 0u;
                 }
-                nms_dense<MODE, SR>(ttid, kTestThreads, 0, plane, scount, 0ull, p.staging_cap, p.staging, g, tag);
-                bar_test_group();
-                const uint32_t kn = *scount;
-                bar_test_group();
-                if (t0) {
-                    *scount = 0u;
-                    s_block[0] = *s_base;  // the run opened for this chunk is not used: the exact size is known now
-                    *s_base = reserve_staging(kn, s_block, p);
+                __syncwarp();
+                // the last emit warp to get here wipes the chunk's cells and gives plane and list back
+                uint32_t last = 0u;
+                if (lane == 0) {
+                    __threadfence_block();
+                    last = atomicAdd(&e_done[pi], 1u) == (uint32_t)(kEmitWarps - 1) ? 1u : 0u;
                 }
-                bar_test_group();
-                if (kn != 0u) nms_dense<MODE, SR>(ttid, kTestThreads, 1, plane, scount, *s_base, p.staging_cap, p.staging, g, tag);
-                bar_test_group();
-                if (t0) {
-                    *scount = 0u;
-                    close_run(slot, kn, c == NC - 1);
-                    *s_base = open_run(s_block, p);
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    __threadfence_block();
+                    cell_t *wplane = planes + pi * (SR * kPlaneW);
+                    if (kn <= (uint32_t)kKlistCap) {
+                        for (uint32_t i = (uint32_t)lane; i < kn; i += 32u) {
+                            const uint32_t ent = klist[i];
+                            wplane[(ent >> 8) * kPlaneW + (ent & 0xffu) - kPlaneLead] = (cell_t)0;
+                        }
+                    } else {
+                        uint4 *pz = reinterpret_cast<uint4 *>(wplane);
+                        for (int i = lane; i < L.plane_bytes / 16; i += 32) pz[i] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        kcount[pi] = 0u;
+                        e_done[pi] = 0u;
+                        __threadfence_block();
+                        mbar_arrive(&p_free[pi]);
+                    }
                 }
-            }
-            tag = tag == (uint32_t)kTagPeriod ? 1u : tag + 1u;
-            if (++qb == (uint32_t)kQueueBufs) {
-                qb = 0;
-                qpar ^= 1u;
+                FDF_CLK(11)
+                next_chunk();
             }
         }
-        if (t0 && !have_nxt) {  // (only when the look-ahead never reached the next strip: cannot happen with ahead >= 1)
-            nxt = atomicAdd(p.ticket, 1u);
-            s_ticket[(it + 1u) & 1u] = nxt;
-        }
-        have_nxt = false;
-        bar_test_group();  // the next ticket and the next run's base are visible to the whole group
-        cur = s_ticket[(it + 1u) & 1u];
     }
-    FDF_CLK_END
 }
 
 // ---- ordered compaction, step 2: exclusive scan of the per-strip counts -------------------------------
@@ -730,29 +731,29 @@ struct StripRecord {
 __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const DetectParams p, uint32_t n_items) {
     extern __shared__ __align__(16) uint32_t gsm[];
     __shared__ uint32_t warp_sums[kGatherThreads / 32];
-    __shared__ unsigned long long s_run_base[kGatherMaxChunks];
-    __shared__ uint32_t s_run_count[kGatherMaxChunks];
+    __shared__ unsigned long long s_run_base[kGatherMaxRuns];
+    __shared__ uint32_t s_run_count[kGatherMaxRuns];
     __shared__ StripRecord s_rec;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mode = (int)p.mode, sr = (int)p.sr;
-    const int WW = (int)p.words_per_row, NC = (int)p.chunks_per_strip;
+    const int WW = (int)p.words_per_row, NR = (int)p.chunks_per_strip * kRunsPerChunk;  // run records per strip
     const int nwords = out_rows(mode, sr) * WW;
     const int nsum = (nwords + 31) / 32;  // level-2 words
     uint32_t *bits = gsm, *summary = gsm + nsum * 32;
     for (int i = tid; i < nsum * 33; i += kGatherThreads) gsm[i] = 0u;
 
-    // records of a strip: thread c < NC holds chunk c's run, thread NC the strip's total and destination
+    // records of a strip: thread r < NR holds run r, thread NR the strip's total and destination
     unsigned long long r_base = 0ull;
     uint32_t r_count = 0u;
     auto fetch = [&](uint32_t item) {
         r_base = 0ull;
         r_count = 0u;
         if (item >= n_items) return;
-        if (tid < NC) {
-            const size_t slot = (size_t)item * NC + tid;
-            r_count = p.run_n[slot] != 0u ? p.run_count[slot] : 0u;
+        if (tid < NR) {
+            const size_t slot = (size_t)item * NR + tid;
+            r_count = p.run_count[slot];
             r_base = r_count != 0u ? p.run_base[slot] : 0ull;
-        } else if (tid == NC) {
+        } else if (tid == NR) {
             r_count = p.item_count[item];
             r_base = p.item_dst[item];
         }
@@ -782,10 +783,10 @@ __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const Detect
     const int row_step = (32 * kGatherThreads) / WW, col_step = 32 * kGatherThreads - row_step * WW;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         __syncthreads();  // the previous strip is finished with the records (and, the first time, the bitmap is zero)
-        if (tid < NC) {
+        if (tid < NR) {
             s_run_base[tid] = r_base;
             s_run_count[tid] = r_count;
-        } else if (tid == NC) {
+        } else if (tid == NR) {
             s_rec.dst = r_base;
             s_rec.total = r_count;
         }
@@ -794,12 +795,15 @@ __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const Detect
         if (s_rec.total == 0u) continue;  // (block-uniform)
         const uint32_t strip = item % p.strips_per_frame;
         const uint32_t y0 = (uint32_t)(first_out_row(mode) + (int)strip * out_rows(mode, sr));
-        // one warp per chunk: its run -> bits
-        for (int c = warp; c < NC; c += kGatherThreads / 32) {
+        // one warp per run: its entries -> bits
+        for (int c = warp; c < NR; c += kGatherThreads / 32) {
             const unsigned long long base = s_run_base[c];
             const uint32_t cnt = s_run_count[c];
             for (uint32_t i = (uint32_t)lane; i < cnt; i += 32u) {
-                if (base + i >= p.staging_cap) break;
+                if (base + i >= p.staging_cap) {  // (the emit warp that dropped these entries has raised the flag too)
+                    atomicOr(p.flags, kFlagStagingOverflow);
+                    break;
+                }
                 const uint32_t e = p.staging[base + i];
                 const uint32_t x = e & 0xffffu, w1 = (e >> 16) * (uint32_t)WW + (x >> 5);
                 atomicOr(&bits[w1], 1u << (x & 31u));
@@ -936,58 +940,69 @@ cudaError_t read_trace(long long *out, size_t bytes) {  // and resets the CTA co
 namespace {
 #endif
 
-#ifdef FDF_PHASE_CLOCKS
-}  // namespace
-cudaError_t read_phase_clocks(unsigned long long out[256]) {
-    cudaError_t e = cudaMemcpyFromSymbol(out, g_phase_clocks, 256 * sizeof(unsigned long long));
-    if (e != cudaSuccess) return e;
-    unsigned long long zero[256] = {0};
-    return cudaMemcpyToSymbol(g_phase_clocks, zero, sizeof(zero));
-}
-namespace {
-#endif
-
 template <int MODE, int SR>
-cudaError_t launch_t(const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream) {
+cudaError_t prepare_t(int *per_sm) {
     auto kern = fdf_detect_kernel<MODE, SR>;
     const size_t smem = detect_smem_bytes(MODE, SR);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const unsigned long long items = (unsigned long long)p.n_frames * p.strips_per_frame;
-    if (items == 0 || items > 0x7fffffffull) return cudaErrorInvalidValue;
-    // persistent grid: as many CTAs as can be resident at once (each loops over tickets)
-    int dev = 0, sms = 0, per_sm = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem)) != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorInvalidConfiguration;
-    if (const char *lim = getenv("FDF_CTAS_PER_SM")) {  // tuning knob for experiments
-        const int v = atoi(lim);
-        if (v >= 1 && v < per_sm) per_sm = v;
-    }
-    unsigned long long grid = (unsigned long long)sms * (unsigned)per_sm;
-    if (grid > items) grid = items;
-    kern<<<(unsigned)grid, kThreads, smem, stream>>>(tmap, p);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, kThreads, smem);
+}
+
+template <int MODE, int SR>
+cudaError_t launch_t(const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream, unsigned grid) {
+    fdf_detect_kernel<MODE, SR><<<grid, kThreads, detect_smem_bytes(MODE, SR), stream>>>(tmap, p);
     return cudaGetLastError();
 }
 
+constexpr size_t kGatherSmemLimit = 200 * 1024;
+
 }  // namespace
 
-size_t detect_smem_bytes(int mode, int sr) {
-    const size_t tile = (size_t)tile_rows(sr) * kTileW;
-    (void)mode;
-    const size_t plane = (size_t)sr * kPlaneW * 2;
-    const size_t queues = (size_t)(kQueueBufs + 1) * kQueueCap * 2, wq = (size_t)4 * kWarpQueueCap * 2;
-    return (size_t)kTileStages * tile + plane + queues + wq + (size_t)3 * kVtabWords * 4 + 192;
-}
+size_t detect_smem_bytes(int mode, int sr) { return (size_t)layout_sizes(mode, sr).total; }
 
 size_t gather_smem_bytes(int mode, int sr, uint32_t words_per_row) {
     const size_t nsum = ((size_t)out_rows(mode, sr) * words_per_row + 31) / 32;  // level-2 words
     return nsum * 33 * 4;
 }
-cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream) {
+
+// Everything a launch needs to know about the device and the kernels is looked up ONCE per context (fdf_create):
+// function attributes, occupancy per (mode, strip height), SM count, the experiment knob.  A detection call then
+// costs three launches and nothing else on the host.
+cudaError_t init_device_info(DeviceInfo &info) {
+    int dev = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&info.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+#define FDF_CASE(M, S, I) \
+    if ((e = prepare_t<M, S>(&info.detect_per_sm[M][I])) != cudaSuccess) return e;
+    FDF_CASE(0, 32, 0) FDF_CASE(0, 48, 1) FDF_CASE(0, 64, 2)
+    FDF_CASE(1, 32, 0) FDF_CASE(1, 48, 1) FDF_CASE(1, 64, 2)
+    FDF_CASE(2, 32, 0) FDF_CASE(2, 48, 1) FDF_CASE(2, 64, 2)
+#undef FDF_CASE
+    e = cudaFuncSetAttribute(fdf_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmemLimit);
+    if (e != cudaSuccess) return e;
+    info.gather_smem = ~(size_t)0;
+    info.gather_per_sm = 0;
+    info.ctas_limit = 0;
+    if (const char *lim = getenv("FDF_CTAS_PER_SM")) info.ctas_limit = atoi(lim);  // tuning knob for experiments
+    return cudaSuccess;
+}
+
+cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const DetectParams &p, cudaStream_t stream,
+                          const DeviceInfo &info) {
+    const unsigned long long items = (unsigned long long)p.n_frames * p.strips_per_frame;
+    if (items == 0 || items > 0x7fffffffull || mode < 0 || mode > 2) return cudaErrorInvalidValue;
+    const int si = sr == 32 ? 0 : (sr == 48 ? 1 : (sr == 64 ? 2 : -1));
+    if (si < 0) return cudaErrorInvalidValue;
+    int per_sm = info.detect_per_sm[mode][si];
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    if (info.ctas_limit >= 1 && info.ctas_limit < per_sm) per_sm = info.ctas_limit;
+    // persistent grid: as many CTAs as can be resident at once (each loops over tickets)
+    unsigned long long grid = (unsigned long long)info.sms * (unsigned)per_sm;
+    if (grid > items) grid = items;
 #define FDF_CASE(M, S) \
-    if (mode == M && sr == S) return launch_t<M, S>(tmap, p, stream);
+    if (mode == M && sr == S) return launch_t<M, S>(tmap, p, stream, (unsigned)grid);
     FDF_CASE(0, 32)
     FDF_CASE(0, 48)
     FDF_CASE(0, 64)
@@ -1009,19 +1024,21 @@ cudaError_t launch_scan(const DetectParams &p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream) {
+cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream, DeviceInfo &info) {
     const unsigned long long items = (unsigned long long)p.n_frames * p.strips_per_frame;
     // (a rank without frames still launches one CTA in a sharded call: it writes the batch's global offsets)
     if ((items == 0 && p.all_offsets == nullptr) || items > 0x7fffffffull) return cudaErrorInvalidValue;
     const size_t smem = gather_smem_bytes((int)p.mode, (int)p.sr, p.words_per_row);
-    cudaError_t e = cudaFuncSetAttribute(fdf_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int dev = 0, sms = 0, per_sm = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fdf_gather_kernel, kGatherThreads, smem)) != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorInvalidConfiguration;
-    unsigned long long grid = (unsigned long long)sms * (unsigned)per_sm;
+    if (smem > kGatherSmemLimit) return cudaErrorInvalidValue;
+    if (smem != info.gather_smem) {  // (occupancy depends on the image width only: looked up when the width changes)
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fdf_gather_kernel, kGatherThreads, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        info.gather_smem = smem;
+        info.gather_per_sm = per_sm;
+    }
+    unsigned long long grid = (unsigned long long)info.sms * (unsigned)info.gather_per_sm;
     if (grid > items) grid = items;
     if (grid == 0) grid = 1;
     fdf_gather_kernel<<<(unsigned)grid, kGatherThreads, smem, stream>>>(p, (uint32_t)items);

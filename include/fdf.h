@@ -172,6 +172,12 @@ fdf_status fdf_synth_frames_device(fdf_ctx *ctx, uint8_t *d_frames, uint32_t n_f
  * (detection, offset scan, gather) and one per synthetic-frame call. */
 uint64_t fdf_kernel_launches(const fdf_ctx *ctx);
 
+/* Tuning knobs of a context (tests and experiments; results never depend on them).  strip_rows: scored rows per
+ * strip, 0 = chosen from the batch size (default), or 32 / 48 / 64.  sub_batch_mb: how many MB of frames
+ * fdf_detect_batch copies and processes at a time, 0 = default (128).  The environment variables FDF_FORCE_SR and
+ * FDF_SUB_BATCH_MB give the initial values when the context is created; they are not read afterwards. */
+fdf_status fdf_set_tuning(fdf_ctx *ctx, int strip_rows, uint32_t sub_batch_mb);
+
 /* Per-kernel device timing for benchmarks.  fdf_set_timing(ctx, n) makes every following
  * fdf_detect_device-family call record CUDA events around its three launches into slot
  * (call index mod n); n = 0 switches it off.  fdf_get_timing synchronises on the slot's last event and

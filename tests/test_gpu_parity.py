@@ -242,9 +242,9 @@ def test_cpp_binding_and_cli_regenerate_the_shipped_renders(golden, tmp_path):
 
 
 @pytest.mark.parametrize("sr", [32, 48, 64])
-def test_forced_strip_heights(detector, oracle_mod, monkeypatch, sr):
+def test_forced_strip_heights(detector, oracle_mod, sr):
     """The launcher picks 32- or 64-row strips by batch size; every compiled strip height must give the same list."""
-    monkeypatch.setenv("FDF_FORCE_SR", str(sr))
+    detector.set_tuning(strip_rows=sr)
     img = oracle_mod.synth_frame(1920, 1080, seed=77, frame=sr, kind=0, amp=5)
     for nms in (0, 1, 2):
         assert same_points(detector.detect_array(img, _cfg(16, 9, nms)), oracle_mod.port_detect(img, 16, 9, nms)), nms
@@ -253,13 +253,14 @@ def test_forced_strip_heights(detector, oracle_mod, monkeypatch, sr):
         small = oracle_mod.synth_frame(300, h, seed=h, frame=1, kind=1)
         for nms in (0, 1):
             assert same_points(detector.detect_array(small, _cfg(25, 9, nms)), oracle_mod.detect(small, 25, 9, nms)), (h, nms)
+    detector.set_tuning()
 
 
 @pytest.mark.parametrize("sr", [32, 64])
-def test_dense_and_sparse_chunks_in_one_strip(detector, oracle_mod, monkeypatch, sr):
+def test_dense_and_sparse_chunks_in_one_strip(detector, oracle_mod, sr):
     """Noise next to flat and scene content: the same CTA alternates between the candidate-queue path and the
-    row-group fallback (queue overflow), in all three modes, and the staging blocks are reused across both."""
-    monkeypatch.setenv("FDF_FORCE_SR", str(sr))
+    dense path (queue overflow), in all three modes, and the staging blocks are reused across both."""
+    detector.set_tuning(strip_rows=sr)
     scene = oracle_mod.synth_frame(1500, 200, seed=5, frame=0, kind=0, amp=4)
     noise = oracle_mod.synth_frame(1500, 200, seed=6, frame=0, kind=1)
     img = scene.copy()
@@ -269,6 +270,7 @@ def test_dense_and_sparse_chunks_in_one_strip(detector, oracle_mod, monkeypatch,
     for t, nms in [(5, 0), (5, 1), (5, 2), (16, 1)]:
         assert same_points(detector.detect_array(img, _cfg(t, 9, nms)), oracle_mod.port_detect(img, t, 9, nms)), (t, nms)
     assert detector.device_flags() == 0
+    detector.set_tuning()
 
 
 def test_noise_batch_takes_the_fallback_everywhere(detector, oracle_mod):
@@ -289,15 +291,15 @@ def test_noise_batch_takes_the_fallback_everywhere(detector, oracle_mod):
             assert oracle_mod.hash_points(pts_h[offs_h[f]:offs_h[f + 1]]) == int(hashes[f]), (nms, f)
 
 
-def test_host_batch_is_pipelined_in_sub_batches(detector, oracle_mod, monkeypatch):
+def test_host_batch_is_pipelined_in_sub_batches(detector, oracle_mod):
     """fdf_detect_batch splits large batches into sub-batches (copy of the next one overlaps the kernels of the
     current one); the packed CSR output must not depend on the split, including when the capacity runs out."""
     import feature_detector_fast_b200 as fdf
 
     frames = np.stack([oracle_mod.synth_frame(1280, 720, seed=12, frame=f, kind=0, amp=4) for f in range(7)])
-    monkeypatch.setenv("FDF_SUB_BATCH_MB", "4096")
+    detector.set_tuning(sub_batch_mb=4096)
     pts1, offs1 = detector.detect_batch(frames, _cfg(16, 9, 1))
-    monkeypatch.setenv("FDF_SUB_BATCH_MB", "2")  # 2 frames per sub-batch -> 4 sub-batches
+    detector.set_tuning(sub_batch_mb=2)  # 2 frames per sub-batch -> 4 sub-batches
     pts4, offs4 = detector.detect_batch(frames, _cfg(16, 9, 1))
     assert (np.asarray(offs1) == np.asarray(offs4)).all()
     assert same_points(pts1, pts4)
@@ -308,6 +310,7 @@ def test_host_batch_is_pipelined_in_sub_batches(detector, oracle_mod, monkeypatc
     with pytest.raises(fdf.FdfError) as ei:
         detector.detect_batch(frames, _cfg(16, 9, 1), out=small)
     assert ei.value.status == 4  # FDF_ERR_CAPACITY
+    detector.set_tuning()
 
 
 # ---- the step in front of the path: RGB8 -> luma8 (main.rs:53-58), fdf_rgb8_to_luma8_device / fdf_detect_rgb8 ----

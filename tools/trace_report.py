@@ -1,50 +1,45 @@
 #!/usr/bin/env python3
 """Reads gpurun_out/trace_<tag>.npy (tools/trace_timeline.py) and prints, for the CTAs that ran on SM 0, the phase
-timeline per chunk: when each group could start, how long each phase took, who waited for whom.
-usage: trace_report.py gpurun_out/trace_c3.npy [first chunk] [chunks to list]"""
+timeline per chunk of the three warp groups of the detection kernel (filter / test / emit).
+usage: trace_report.py trace.npy [first chunk] [chunks to list] [test warps] [emit warps]"""
 import sys
 import numpy as np
 
 a = np.load(sys.argv[1])
 c0 = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-nl = int(sys.argv[3]) if len(sys.argv) > 3 else 12
-NF = 4  # filter warps 0..3, test warps 4..9
+nl = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+NT = int(sys.argv[4]) if len(sys.argv) > 4 else 4
+NE = int(sys.argv[5]) if len(sys.argv) > 5 else 2
+NF = 4
 ctas = [k for k in range(a.shape[0]) if (a[k] != 0).any()]
 print("traced CTAs:", ctas)
+m = lambda x: float(np.nanmean(x))
 for k in ctas:
     t = a[k].astype(np.float64)
     t[t == 0] = np.nan
     nch = int(np.sum(~np.isnan(t[0, :, 0])))
-    print(f"\n=== CTA {k}: {nch} chunks traced")
-    base = np.nanmin(t)
-    t -= base
-    F = t[:NF]      # [warp][chunk][slot]
-    T = t[NF:10]
-    sl = slice(8, max(9, nch - 8))  # steady state
-    def m(x): return float(np.nanmean(x))
-    period = m(np.diff(np.nanmax(T[:, :, 8], axis=0)[sl]))
-    print(f"period per chunk {period:.0f} cycles")
-    # filter group
-    f_ready, f_s1, f_done = F[:, :, 0], F[:, :, 9], F[:, :, 1]
-    prev_done = np.concatenate([np.full((NF, 1), np.nan), f_done[:, :-1]], axis=1)
-    print(f"F: wait tile {m((f_ready - prev_done)[:, sl]):.0f}  stage1 {m((f_s1 - f_ready)[:, sl]):.0f}  "
-          f"stage2+push {m((f_done - f_s1)[:, sl]):.0f}  | spread of A end across the 4 warps "
-          f"{m((np.nanmax(f_done, axis=0) - np.nanmin(f_done, axis=0))[sl]):.0f}")
-    q, b, bar1, req, nms, end = T[:, :, 4], T[:, :, 5], T[:, :, 3], T[:, :, 6], T[:, :, 7], T[:, :, 8]
-    prev_end = np.concatenate([np.full((T.shape[0], 1), np.nan), end[:, :-1]], axis=1)
-    print(f"T: wait queue {m((q - prev_end)[:, sl]):.0f}  B {m((b - q)[:, sl]):.0f}  bar1 wait {m((bar1 - b)[:, sl]):.0f}  "
-          f"request {m((req - bar1)[:, sl]):.0f}  NMS {m((nms - req)[:, sl]):.0f}  bar2+t0 {m((end - nms)[:, sl]):.0f}")
-    # hand-offs: last filter arrival -> first test start; B end (bar1) -> tile ready
-    lastA = np.nanmax(f_done, axis=0)
-    print(f"hand-off last A end -> T start of B: {m((np.nanmin(q, axis=0) - lastA)[sl]):.0f}  "
-          f"(negative = queue was ready before the test group asked)")
-    bar1_all = np.nanmax(bar1, axis=0)
-    tile2 = np.nanmin(f_ready, axis=0)
-    if nch > 4:
-        lat = (tile2[2:] - bar1_all[:-2])
-        print(f"request (bar1 of chunk k) -> first filter warp starts chunk k+2: {m(lat[sl]):.0f}")
-    print("chunk:  F ready(min) A end(max) | T start(min) B end(max=bar1) NMS end(max) chunk end(max)   [cycles from previous chunk end]")
+    t -= np.nanmin(t)
+    F, T, E = t[:NF], t[NF:NF + NT], t[NF + NT:NF + NT + NE]
+    sl = slice(8, max(9, nch - 8))
+    print(f"\n=== CTA {k}: {nch} chunks traced; period per chunk {m(np.diff(np.nanmax(E[:, :, 11], axis=0)[sl])):.0f} cycles")
+    f_ready, f_s1, f_bar, f_done = F[:, :, 0], F[:, :, 9], F[:, :, 10], F[:, :, 1]
+    prev = np.concatenate([np.full((NF, 1), np.nan), f_done[:, :-1]], axis=1)
+    print(f"filter: wait tile {m((f_ready - prev)[:, sl]):.0f}  stage 1 {m((f_s1 - f_ready)[:, sl]):.0f}  barrier {m((f_bar - f_s1)[:, sl]):.0f}"
+          f"  stage 2 + push {m((f_done - f_bar)[:, sl]):.0f}  | spread of the warps' finish {m((np.nanmax(f_done, 0) - np.nanmin(f_done, 0))[sl]):.0f}")
+    t_go, t_b, t_end = T[:, :, 4], T[:, :, 5], T[:, :, 6]
+    prev = np.concatenate([np.full((NT, 1), np.nan), t_end[:, :-1]], axis=1)
+    print(f"test:   wait (queue, plane) {m((t_go - prev)[:, sl]):.0f}  phase B {m((t_b - t_go)[:, sl]):.0f}  hand-over (+ tile request by the last warp) {m((t_end - t_b)[:, sl]):.0f}"
+          f"  | spread of the warps' finish {m((np.nanmax(t_b, 0) - np.nanmin(t_b, 0))[sl]):.0f}")
+    e_go, e_nms, e_end = E[:, :, 7], E[:, :, 8], E[:, :, 11]
+    prev = np.concatenate([np.full((NE, 1), np.nan), e_end[:, :-1]], axis=1)
+    print(f"emit:   wait list {m((e_go - prev)[:, sl]):.0f}  NMS + staging {m((e_nms - e_go)[:, sl]):.0f}  records, wipe, release {m((e_end - e_nms)[:, sl]):.0f}")
+    print(f"hand-offs: last filter arrival -> first test warp starts {m((np.nanmin(t_go, 0) - np.nanmax(f_done, 0))[sl]):.0f}   "
+          f"last test warp done -> first emit warp starts {m((np.nanmin(e_go, 0) - np.nanmax(t_b, 0))[sl]):.0f}")
+    if nch > 6:
+        print(f"tile request (last test warp done with chunk k) -> first filter warp starts chunk k+2: "
+              f"{m((np.nanmin(f_ready, 0)[2:] - np.nanmax(t_b, 0)[:-2])[sl]):.0f}")
+    print("chunk:  filter start(min) end(max) | test start(min) end(max) | emit start(min) end(max)   [cycles from the first event of the listing]")
+    ref = np.nanmin(t[:, c0, :]) if c0 < nch else 0.0
     for c in range(c0, min(c0 + nl, nch)):
-        ref = np.nanmax(end[:, c - 1]) if c > 0 else 0.0
-        print(f"{c:4d}:  {np.nanmin(f_ready[:, c]) - ref:8.0f} {np.nanmax(f_done[:, c]) - ref:8.0f} | {np.nanmin(q[:, c]) - ref:8.0f} "
-              f"{np.nanmax(bar1[:, c]) - ref:8.0f} {np.nanmax(nms[:, c]) - ref:8.0f} {np.nanmax(end[:, c]) - ref:8.0f}")
+        print(f"{c:4d}:  {np.nanmin(f_ready[:, c]) - ref:8.0f} {np.nanmax(f_done[:, c]) - ref:8.0f} | {np.nanmin(t_go[:, c]) - ref:8.0f} "
+              f"{np.nanmax(t_b[:, c]) - ref:8.0f} | {np.nanmin(e_go[:, c]) - ref:8.0f} {np.nanmax(e_end[:, c]) - ref:8.0f}")
