@@ -234,26 +234,31 @@ fdf_status prepare_detect(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_fram
     p.cap = cap;
 
     if (fdf::gather_smem_bytes(mode, sr, p.words_per_row) > 200 * 1024 || w > 65535u ||
-        p.chunks_per_strip * (uint32_t)fdf::kRunsPerChunk > (uint32_t)fdf::kGatherMaxRuns)
+        p.chunks_per_strip > (uint32_t)fdf::kGatherMaxChunks)
         return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "image too wide (%u) for the strip bit plane", w);
     const unsigned long long items = (unsigned long long)n_frames * p.strips_per_frame;
     if (items > 0x7fffffffull) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "batch too large");
 
-    // workspace: [header 64 B: ticket, flags, scan ticket, cursor][scan status][item_count][zeroed up to here per launch]
-    //            [item_dst][run_base][run_count]
+    // workspace: [header 64 B: ticket, flags, scan ticket, cursor][scan status][zeroed up to here per launch]
+    //            [item_dst][run_base][item_count][run_count]
     const size_t scan_tiles = ((size_t)items + fdf::kScanTile - 1) / fdf::kScanTile;
-    const size_t cnt_off = kWorkspaceHeader + scan_tiles * sizeof(unsigned long long);
-    const size_t zeroed_bytes = cnt_off + (size_t)items * sizeof(uint32_t);
-    const size_t runs = (size_t)items * p.chunks_per_strip * (size_t)fdf::kRunsPerChunk;
+    const size_t zeroed_bytes = kWorkspaceHeader + scan_tiles * sizeof(unsigned long long);
+    const size_t runs = (size_t)items * p.chunks_per_strip;  // one run record per chunk
     const size_t dst_off = (zeroed_bytes + 15) & ~(size_t)15;
     const size_t rbase_off = dst_off + (size_t)items * sizeof(unsigned long long);
-    const size_t rcnt_off = rbase_off + runs * sizeof(unsigned long long);
+    const size_t cnt_off = rbase_off + runs * sizeof(unsigned long long);
+    const size_t rcnt_off = cnt_off + (size_t)items * sizeof(uint32_t);
     const size_t ws_bytes = rcnt_off + runs * sizeof(uint32_t);
     FDF_CUDA(ctx, ctx->workspace.reserve(ws_bytes));
-    // Staging holds the emit warps' unordered runs, cut from 4096-entry blocks that a warp takes from a global cursor.
-    // A block's unused tail is lost when the next run may not fit it, so K keypoints can take up to 2 K entries plus
-    // one partly used block per emit warp (kStageSlack).  Overflow is not silent: the kernels raise flag bit 2.
-    p.staging_cap = 2ull * cap + fdf::kStageSlack;
+    // Staging holds one unordered run per chunk, cut from kStageBlock-entry blocks that a CTA takes from a global
+    // cursor.  A block's unused tail is lost when the next run may not fit it (dense content reserves exact sizes and
+    // may leave most of a block behind), so K keypoints can take up to 2 K entries plus one partly used block per CTA
+    // of the grid.  Overflow is not silent: the kernels raise flag bit 2.
+    {
+        unsigned long long ctas = (unsigned long long)ctx->info.sms * 4ull;  // (at most 4 resident CTAs per SM)
+        if (ctas > items) ctas = items;
+        p.staging_cap = 2ull * cap + (ctas + 1ull) * (unsigned long long)fdf::kStageBlock;
+    }
     FDF_CUDA(ctx, ctx->staging.reserve((size_t)p.staging_cap));
     FDF_CUDA(ctx, cudaMemsetAsync(ctx->workspace.ptr, 0, zeroed_bytes, stream));
     p.ticket = reinterpret_cast<uint32_t *>(ctx->workspace.ptr);

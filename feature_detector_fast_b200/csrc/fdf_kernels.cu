@@ -2,32 +2,39 @@
 //
 // One persistent kernel does the detection for a batch of frames (replaces fast_simd.rs:301-620):
 //
-//   work item  = (frame, strip of full-width rows), handed out through an atomic ticket.
-//   8 warps, per chunk of a strip (two block barriers per chunk):
-//     TMA 3-D tiled load (u8 tile 256 x (SR+6), zero-filled outside the image, double buffered,
-//     issued two chunks ahead -- across strip boundaries --, completion on an mbarrier)  -> shared memory
-//     phase A  : two-stage dense SWAR filter.  Stage 1 (every pixel, 16 per lane: LDS.128 + VABSDIFF4 + LOP3)
-//                tests the north/south pair; groups with a survivor go to the warp's own queue (ballot, no
-//                barrier); stage 2 (one lane per queued group) adds the east/west pair (PRMT byte shifts) and
-//                pushes the surviving centres to the CTA's candidate queue           (fast_simd.rs:368-520)
-//                (the NMS pass of the previous chunk runs in the same barrier interval)
-//     phase B  : one thread per candidate: 16 ring bytes, two per 32-bit word -> brighter/darker 16-bit masks
-//                -> rotate-AND arc test -> score in 16-bit lanes -> tagged score plane + keypoint list
-//                                                                     (fast_simd.rs:115-297, 623-749)
-//                (one warp meanwhile copies the previous chunk's surviving keypoints to the staging buffer)
-//     NMS pass : strict 3x3 maximum on the shared-memory score plane          (fast_simd.rs:588-616)
-//                survivors are marked in the chunk's keypoint list
+//   work item  = (frame, strip of full-width rows), handed out through an atomic ticket; a strip is walked left to
+//                right in chunks of 240 columns, each staged as a 256-byte-wide tile.
+//   10 warps per CTA in two groups that are coupled ONLY through mbarriers (no CTA-wide barrier in the chunk loop):
+//     4 filter warps  wait for the chunk's tile (TMA 3-D tiled load, u8 tile 256 x (SR+6), zero-filled outside the
+//                     image, kTileStages buffers, completion on an mbarrier)
+//                     phase A stage 1: every pixel, 16 per lane (LDS.128 + VABSDIFF4 + LOP3), north/south pair; groups
+//                     with a survivor go to the warp's segment of the chunk's entry table (ballot, no atomics);
+//                     one barrier among the filter warps;
+//                     phase A stage 2: one lane per entry, the entries of ALL warps dealt evenly to the filter threads
+//                     (a horizontal edge puts most of a chunk's entries into one warp's rows): adds the east/west pair
+//                     (PRMT byte shifts) and pushes the surviving centres to the chunk's candidate queue
+//                                                                                         (fast_simd.rs:368-520)
+//     6 test warps    wait for the candidate queue
+//                     phase B: one thread per candidate: 16 ring bytes -> one "dual" word per ring pixel -> best
+//                     window (VIMNMX3.U16x2) = segment test AND MaxThreshold score -> tagged score plane + keypoint
+//                     list                                                       (fast_simd.rs:115-297, 623-749)
+//                     barrier among the test warps; one thread requests the tile of chunk k + kTileStages;
+//                     NMS pass: strict 3x3 maximum on the raw plane cells per listed keypoint, survivors written
+//                     directly into the chunk's run of the staging buffer            (fast_simd.rs:588-616)
+//                     barrier; one thread closes the run (run record, strip total)
 //   Every chunk leaves one unordered run of (row, x) entries in the staging buffer plus a run record.
 //
 // Two small kernels finish the ordered compaction (fast_simd.rs:550, 596-613: output is row-major):
 //   fdf_scan_kernel   : exclusive prefix sum of the per-strip counts in (frame, strip) order -- block scan
 //                       + decoupled look-back between scan tiles -- giving every strip's final offset and
 //                       the CSR frame offsets;
-//   fdf_gather_kernel : one CTA per strip scatters the strip's runs into a bit plane in shared memory and
-//                       expands it, row-major, to (x, y) points at the strip's final offset.
+//   fdf_gather_kernel : persistent CTAs, one strip at a time: scatters the strip's runs into a two-level bit plane in
+//                       shared memory and expands it, row-major, to (x, y) points at the strip's final offset (for a
+//                       sharded batch: at the rank's place in the batch result, which may be another GPU's memory).
 // (Doing the look-back inside the detection kernel was measured at +45 % kernel time: with ~450 strips
 // in flight every strip ends up waiting for all in-flight predecessors.  Keeping the strip bit plane inside
-// the detection kernel cost 30 KB of shared memory per CTA, i.e. one resident CTA per SM.)
+// the detection kernel cost 30 KB of shared memory per CTA, i.e. one resident CTA per SM.  Structural variants that
+// were built, measured and rejected are kept as patches under tools/experiments/.)
 #include "fdf_kernels.cuh"
 
 #include <cstdlib>
@@ -46,13 +53,7 @@ constexpr unsigned long long kStatusAggregate = 1ull << 62;
 constexpr unsigned long long kStatusPrefix = 2ull << 62;
 constexpr unsigned long long kStatusValueMask = (1ull << 62) - 1ull;
 constexpr uint32_t kSpinLimit = 1u << 22;
-#ifndef FDF_WAIT_MODE
-#define FDF_WAIT_MODE 0
-#endif
-#ifndef FDF_WAIT_HINT_NS
-#define FDF_WAIT_HINT_NS 100000
-#endif
-constexpr uint32_t kWaitHintNs = FDF_WAIT_HINT_NS;  // mbarrier.try_wait suspend-time hint
+constexpr uint32_t kWaitHintNs = 100000u;  // mbarrier.try_wait suspend-time hint
 constexpr unsigned long long kWaitLimitNs = 4000000000ull;  // 4 s
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -75,60 +76,48 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 
-// Spins on mbarrier.try_wait (each probe suspends the thread in hardware until the phase completes or the time hint
-// runs out) for at most `rounds` probes: the loop is three instructions -- probe, branch out, count-and-branch back --
-// because waiting warps re-issue it all the time and every extra instruction in it is an issue slot (and a logic-pipe
-// slot) taken from the warps that work.  Returns true when the phase has completed.
-__device__ __forceinline__ bool mbar_spin(uint64_t *bar, uint32_t parity, uint32_t rounds) {
-    uint32_t done;
+// try_wait suspends the thread (no issue slots used) until the phase completes or the time hint (ns) runs out
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        ".reg .u32 n;\n"
-        "mov.u32 n, %3;\n"
-        "FDF_SPIN:\n"
-#if FDF_WAIT_MODE == 1   // experiment: no suspend-time hint (the hardware's default time limit)
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-#elif FDF_WAIT_MODE == 2  // experiment: non-blocking test (busy polling)
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-#else
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %4;\n"
-#endif
-        "@p bra FDF_SPIN_DONE;\n"
-        "add.u32 n, n, -1;\n"
-        "setp.ne.u32 p, n, 0;\n"
-        "@p bra FDF_SPIN;\n"
-        "setp.ne.u32 p, n, n;\n"  // (gave up: p = false)
-        "FDF_SPIN_DONE:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(rounds), "r"(kWaitHintNs)
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(kWaitHintNs)
         : "memory");
-    return done != 0;
+    return ok != 0;
 }
 
 // Waits for the phase; a wait that lasts longer than kWaitLimitNs can only be a bug in the pipeline: it is turned
-// into an error flag (the host reports FDF_ERR_INTERNAL) instead of a hung GPU.  The clock and the CTA's abort flag
-// are looked at once per kSpinRounds probes only.
+// into an error flag (the host reports FDF_ERR_INTERNAL) instead of a hung GPU.
 // (`abort` is a flag in shared memory: once one wait of the CTA has timed out, no other wait of the CTA blocks, so
-// that the kernel still ends quickly.)
-constexpr uint32_t kSpinRounds = 4096u;
+// that the kernel still ends quickly.)  A three-instruction PTX spin (probe, branch, count) and named hardware
+// barriers instead of polled mbarriers were both measured: 1 % slower and +-0 (the polls use issue slots that
+// nobody else wants), so the plain loop stays.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *flags, volatile uint32_t *abort) {
-    if (mbar_spin(bar, parity, kSpinRounds)) return;
-    const unsigned long long t0 = global_timer_ns();
-    while (!mbar_spin(bar, parity, kSpinRounds)) {
-        if (*abort != 0u) return;
-        if (global_timer_ns() - t0 > kWaitLimitNs) {
-            atomicOr(flags, kFlagTmaTimeout);
-            *abort = 1u;
-            return;
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0 = 0ull;
+    for (uint32_t spins = 1;; spins++) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((spins & 63u) == 0u) {  // (rarely reached: a wait normally ends within a few rounds)
+            if (*abort != 0u) return;
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0ull) t0 = now;
+            if (now - t0 > kWaitLimitNs) {
+                atomicOr(flags, kFlagTmaTimeout);
+                *abort = 1u;
+                return;
+            }
         }
     }
 }
@@ -171,51 +160,42 @@ __device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned l
 #define FDF_L2_PREFETCH 1
 #endif
 constexpr int kTileStages = FDF_TILE_STAGES;  // tile buffers per CTA: the tile of chunk k + kTileStages is requested when
-                                              // the test warps are done with chunk k
-constexpr int kQueueBufs = kTileStages;       // candidate queues, one per tile buffer
-constexpr int kTicketSlots = 8;               // strips whose tickets can be in flight between the tile requests and the
-                                              // emit warps (a strip can be a single chunk)
-constexpr uint32_t kDenseMark = 0xffffffffu;  // keypoint count of a chunk that went through the dense path
+                                              // phase B of chunk k is done, so TMA latency (~1700 cycles under load)
+                                              // is hidden behind kTileStages - 1 chunks of work
+constexpr int kQueueBufs = kTileStages;       // candidate queues: the filter may run kTileStages - 1 chunks ahead of the test
 static_assert(kTileStages >= 2 && kTileStages <= 4, "misc layout holds up to 4 barriers of each kind");
-
-// score planes / keypoint lists per CTA: two one-byte planes let the test warps fill the plane of chunk k + 1 while
-// the emit warps still read the plane of chunk k; SumAbsolute needs two-byte cells, so it gets one plane and the two
-// groups take turns on it
-__host__ __device__ constexpr int plane_bufs(int mode) { return mode == NMS_SUM_ABSOLUTE ? 1 : 2; }
-__host__ __device__ constexpr int plane_cell_bytes(int mode) { return mode == NMS_SUM_ABSOLUTE ? 2 : 1; }
 
 struct LayoutSizes {
     int tile_bytes, plane_off, plane_bytes, queue_off, klist_off, ent_off, vtab_off, misc_off, total;
 };
-__host__ __device__ constexpr LayoutSizes layout_sizes(int mode, int sr) {
+__host__ __device__ constexpr LayoutSizes layout_sizes(int sr) {
     LayoutSizes l = {};
-    l.tile_bytes = tile_rows(sr) * kTileW;                                  // one TMA box
+    l.tile_bytes = tile_rows(sr) * kTileW;                       // one TMA box
     l.plane_off = kTileStages * l.tile_bytes;
-    l.plane_bytes = sr * kPlaneW * plane_cell_bytes(mode);                  // one plane
-    l.queue_off = l.plane_off + plane_bufs(mode) * l.plane_bytes;           // candidate queues [kQueueBufs][kQueueCap] u16
-    l.klist_off = l.queue_off + kQueueBufs * kQueueCap * 2;                 // keypoint lists [planes][kKlistCap] u16
-    l.ent_off = l.klist_off + plane_bufs(mode) * kKlistCap * 2;             // stage-1 entry tables [2][warps][kWarpQueueCap] u8
-    l.vtab_off = l.ent_off + 2 * kFilterWarps * kWarpQueueCap;              // validity tables: first / middle / last chunk
+    l.plane_bytes = sr * kPlaneW * 2;                            // u16: tag << 12 | score (Off mode: score 1)
+    l.queue_off = l.plane_off + l.plane_bytes;                   // candidate queues [kQueueBufs][kQueueCap] u16
+    l.klist_off = l.queue_off + kQueueBufs * kQueueCap * 2;      // keypoint list of the chunk being tested [kQueueCap] u16
+    l.ent_off = l.klist_off + kQueueCap * 2;                     // stage-1 entry tables [2][warps][kWarpQueueCap] u8
+    l.vtab_off = l.ent_off + 2 * kFilterWarps * kWarpQueueCap;   // validity tables: first / middle / last chunk
     l.misc_off = l.vtab_off + 3 * kVtabWords * 4;
-    l.total = l.misc_off + 256;
+    l.total = l.misc_off + 192;
     return l;
 }
 
 // misc block (byte offsets)
 constexpr int kMiscFullBar = 0;     // [4] u64 tile landed
 constexpr int kMiscQFull = 32;      // [4] u64 candidate queue complete (one arrival per filter warp)
-constexpr int kMiscKFull = 64;      // [2] u64 score plane + keypoint list complete (the last test warp arrives)
-constexpr int kMiscPFree = 80;      // [2] u64 score plane + keypoint list free again (the last emit warp arrives)
-constexpr int kMiscQCount = 96;     // [4] u32 candidate queue fill
-constexpr int kMiscKCount = 112;    // [2] u32 keypoints of the chunk
-constexpr int kMiscTDone = 120;     // [4] u32 test warps done with the chunk
-constexpr int kMiscEDone = 136;     // [2] u32 emit warps done with the chunk
-constexpr int kMiscTicket = 144;    // [8] u32 strip tickets
-constexpr int kMiscNEnt = 176;      // [2][4] u32 stage-1 entries per filter warp
-constexpr int kMiscReqDone = 208;   // u32 tile requests issued so far (they are issued in stream order)
-constexpr int kMiscAbort = 212;     // u32 a wait timed out
-constexpr int kMiscTrace = 216;     // i32 (trace builds) index of this CTA in the trace table
-static_assert(kFilterWarps <= 4 && kTicketSlots == 8, "misc layout");
+constexpr int kMiscQCount = 64;     // [4] u32 candidate queue fill
+constexpr int kMiscTicket = 80;     // [2] u32 strip tickets (strip parity)
+constexpr int kMiscSCount = 88;     // u32 keypoints staged by the chunk so far
+constexpr int kMiscSTotal = 92;     // u32 keypoints of the strip so far
+constexpr int kMiscSBase = 96;      // u64 where the chunk's run starts in the staging buffer
+constexpr int kMiscSBlock = 104;    // [2] u64 the CTA's staging block: next free entry, end
+constexpr int kMiscAbort = 120;     // u32 a wait timed out
+constexpr int kMiscKCount = 124;    // [2] u32 keypoint list fill (chunk parity)
+constexpr int kMiscNEnt = 132;      // [2][4] u32 stage-1 entries per filter warp (chunk parity)
+constexpr int kMiscDropped = 164;   // u32 a staged entry did not fit the staging buffer
+constexpr int kMiscTrace = 168;     // i32 (trace builds) index of this CTA in the trace table
 
 // ---- decoupled look-back (one warp) -------------------------------------------------------------
 // status[i]: bits 63:62 = 0 empty / 1 aggregate of item i / 2 inclusive prefix up to item i.
@@ -269,43 +249,63 @@ __device__ unsigned int g_trace_n;
 #endif
 
 // ---- the detection kernel ----------------------------------------------------------------------
-// Persistent CTAs; a CTA draws strips (frame, rows) from an atomic ticket and walks each strip chunk by chunk.  Its
-// warps form a three-stage pipeline over the stream of chunks, coupled ONLY through mbarriers and a few shared
-// counters -- no CTA-wide barrier, and no barrier at all inside the test and emit groups, whose warps drift freely:
-//
-//   filter warps (kFilterWarps)   wait for the chunk's tile (TMA, full_bar) -> stage 1 over their own rows -> one
-//                                 barrier among the filter warps -> stage 2 over ALL warps' entries, dealt evenly ->
-//                                 candidate queue (one per tile buffer) -> arrive on q_full.
-//   test warps (kTestWarps)       wait q_full and p_free (the plane and keypoint list of chunk k - planes are free) ->
-//                                 exact test + score per candidate -> score plane, keypoint list.  The LAST test warp
-//                                 to finish a chunk (shared counter) arrives on k_full and requests the tile of chunk
-//                                 k + kTileStages: the tile and the candidate queue of chunk k are free now.
-//   emit warps (kEmitWarps)       wait k_full -> strict 3x3 maximum per listed keypoint on the plane -> survivors into
-//                                 the warp's own run of the staging buffer (ballot-ranked, no atomics), run record.  The
-//                                 LAST emit warp wipes the chunk's cells from the plane and arrives on p_free.
-//
-// Why this shape (profiles/r02_v15_timeline_3ctas.txt): with per-warp stage-2 queues one filter warp regularly took
-// 3-4 times as long as the others (a horizontal edge puts most of a chunk's 16-pixel groups into one warp's rows),
-// the test group waited for it, the filter group then waited for the test group's tile request, and the test group's
-// own chain (test -> barrier -> tile request -> NMS -> barrier -> bookkeeping by one thread) was the longest stage.
-// Stream bookkeeping: a chunk is (strip sequence number `it` of this CTA, chunk c of the strip); every warp walks the
-// same sequence on its own.  The ticket of strip `it` sits in s_ticket[it % kTicketSlots]; it is drawn by the thread
-// that requests the strip's first tile.  Tile requests are issued in stream order (s_req_done), so tickets are drawn in
-// order and the first ticket beyond the last strip ends the stream for everybody.
+// Two groups of warps per CTA, coupled only through mbarriers (no CTA-wide barrier inside the chunk loop):
+//   filter warps (0 .. kFilterWarps-1): wait for chunk k's tile, run phase A into candidate queue k % kQueueBufs
+//       (stage 1 per warp -> barrier among the filter warps -> stage 2 over all warps' entries), arrive on q_full,
+//       go on to chunk k + 1;
+//   test warps (the others): wait on q_full, run phase B, barrier among themselves, then one thread requests the tile
+//       of chunk k + kTileStages (tile buffer and candidate queue of chunk k are free now), all run the NMS pass over
+//       the chunk's keypoint list, barrier, and one thread closes the chunk's run while the others already wait for
+//       chunk k + 1.
+// Which buffer is protected by what:
+//   tile[s], queue[s] (s = k % kTileStages): written by TMA / the filter warps after full_bar[s] of chunk k; read by
+//       the test warps until their barrier after phase B of chunk k; the tile of chunk k + kTileStages is requested
+//       after that barrier.  A landed tile therefore implies that its queue is free again.
+//   entry table [k & 1]: written by stage 1 of chunk k before the filter barrier, read by stage 2 after it; chunk
+//       k + 2 writes it again after the filter barrier of chunk k + 1, which every filter warp reaches only after its
+//       stage 2 of chunk k.
+//   plane: cells carry a 4-bit chunk tag, larger tags are newer; written in phase B, read in the NMS pass, both inside
+//       one test-group barrier interval each; cleared every kTagPeriod chunks.
+//   klist, scount, s_base: written / read by the test warps between their two barriers; reset by the thread that
+//       closes the run, before the barrier that opens the next chunk's phase B ... (kcount is double-buffered by chunk
+//       parity because phase B of chunk k + 1 appends while that thread still reads chunk k's count).
+__device__ __forceinline__ void bar_test_group() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kTestThreads) : "memory");
+}
 __device__ __forceinline__ void bar_filter_group() {
-    asm volatile("bar.sync 1, %0;" ::"n"(kFilterThreads) : "memory");
+    asm volatile("bar.sync 2, %0;" ::"n"(kFilterThreads) : "memory");
 }
 
-__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
-    return *reinterpret_cast<const volatile uint32_t *>(p);
+// Staging space is handed out in two levels: a CTA takes blocks of kStageBlock entries from the global cursor
+// (one contended atomic every few dozen chunks instead of one per chunk, which sat on the test warps' critical
+// path) and cuts its runs from the current block.  s_block[0] = next free entry, s_block[1] = end of the block.
+// Only thread t0 calls these, between barriers of the test group.
+// A chunk's run is opened before its size is known (room for a full keypoint list), written by the NMS pass, and
+// closed at its real size: the unused tail goes back to the block.
+__device__ __forceinline__ unsigned long long reserve_staging(uint32_t count, unsigned long long *s_block,
+                                                              const DetectParams &p) {
+    unsigned long long next = s_block[0];
+    if (next + count > s_block[1]) {
+        const unsigned long long n = count > (uint32_t)kStageBlock ? count : (unsigned long long)kStageBlock;
+        next = atomicAdd(p.cursor, n);
+        s_block[1] = next + n;
+    }
+    s_block[0] = next + count;
+    return next;
+}
+
+__device__ __forceinline__ unsigned long long open_run(unsigned long long *s_block, const DetectParams &p) {
+    if (s_block[0] + (unsigned long long)kQueueCap > s_block[1]) {
+        s_block[0] = atomicAdd(p.cursor, (unsigned long long)kStageBlock);
+        s_block[1] = s_block[0] + (unsigned long long)kStageBlock;
+    }
+    return s_block[0];
 }
 
 template <int MODE, int SR>
 __global__ void __launch_bounds__(kThreads, SR >= 48 ? 3 : 4)
 fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p) {
-    typedef typename PlaneCell<MODE>::type cell_t;
-    constexpr LayoutSizes L = layout_sizes(MODE, SR);
-    constexpr int PL = plane_bufs(MODE);
+    constexpr LayoutSizes L = layout_sizes(SR);
     constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;  // score halo (rows and columns) needed by the 3x3 NMS
     constexpr int OUT_R = out_rows(MODE, SR);
     static_assert(L.tile_bytes % 128 == 0, "TMA destination must stay 128-byte aligned");
@@ -315,93 +315,95 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *tiles = smem;
-    cell_t *planes = reinterpret_cast<cell_t *>(smem + L.plane_off);                     // [PL][SR * kPlaneW]
-    uint16_t *queues = reinterpret_cast<uint16_t *>(smem + L.queue_off);                 // [kQueueBufs][kQueueCap]
-    uint16_t *klists = reinterpret_cast<uint16_t *>(smem + L.klist_off);                 // [PL][kKlistCap]
-    uint8_t *ents = smem + L.ent_off;                                                    // [2][kFilterWarps][kWarpQueueCap]
-    uint32_t *vtabs = reinterpret_cast<uint32_t *>(smem + L.vtab_off);                   // [3][kVtabWords]
+    uint16_t *plane = reinterpret_cast<uint16_t *>(smem + L.plane_off);
+    uint16_t *queues = reinterpret_cast<uint16_t *>(smem + L.queue_off);              // [kQueueBufs][kQueueCap]
+    uint16_t *klist = reinterpret_cast<uint16_t *>(smem + L.klist_off);               // [kQueueCap]
+    uint8_t *ents = smem + L.ent_off;                                                 // [2][kFilterWarps][kWarpQueueCap]
+    uint32_t *vtabs = reinterpret_cast<uint32_t *>(smem + L.vtab_off);                 // [3][kVtabWords]
     uint8_t *misc = smem + L.misc_off;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(misc + kMiscFullBar);
     uint64_t *q_full = reinterpret_cast<uint64_t *>(misc + kMiscQFull);
-    uint64_t *k_full = reinterpret_cast<uint64_t *>(misc + kMiscKFull);
-    uint64_t *p_free = reinterpret_cast<uint64_t *>(misc + kMiscPFree);
     uint32_t *qcount = reinterpret_cast<uint32_t *>(misc + kMiscQCount);
-    uint32_t *kcount = reinterpret_cast<uint32_t *>(misc + kMiscKCount);
-    uint32_t *t_done = reinterpret_cast<uint32_t *>(misc + kMiscTDone);
-    uint32_t *e_done = reinterpret_cast<uint32_t *>(misc + kMiscEDone);
     uint32_t *s_ticket = reinterpret_cast<uint32_t *>(misc + kMiscTicket);
-    uint32_t *s_nent = reinterpret_cast<uint32_t *>(misc + kMiscNEnt);
-    uint32_t *s_req_done = reinterpret_cast<uint32_t *>(misc + kMiscReqDone);
+    uint32_t *scount = reinterpret_cast<uint32_t *>(misc + kMiscSCount);
+    uint32_t *s_total = reinterpret_cast<uint32_t *>(misc + kMiscSTotal);
+    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(misc + kMiscSBase);
+    unsigned long long *s_block = reinterpret_cast<unsigned long long *>(misc + kMiscSBlock);
     volatile uint32_t *s_abort = reinterpret_cast<volatile uint32_t *>(misc + kMiscAbort);
+    uint32_t *kcount = reinterpret_cast<uint32_t *>(misc + kMiscKCount);
+    uint32_t *s_nent = reinterpret_cast<uint32_t *>(misc + kMiscNEnt);
+    uint32_t *s_dropped = reinterpret_cast<uint32_t *>(misc + kMiscDropped);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = (int)p.w, H = (int)p.h;
     const int NC = (int)p.chunks_per_strip;
     const uint32_t total_items = p.n_frames * p.strips_per_frame;
+    const bool is_filter = warp < kFilterWarps;
+    const int ttid = tid - kFilterThreads;  // thread index inside the test group
+    // the thread that draws tickets, requests tiles and keeps the run records: lane 0 of the LAST test warp, which gets
+    // the smallest share of every candidate / keypoint list -- its serial work between the group's barriers then
+    // overlaps the other warps' list work instead of extending the critical path
+    const bool t0 = ttid == 32 * (kTestWarps - 1);
 
-    // Requests the tile of stream position r = chunk cr of strip sequence number itr (one thread).  Requests are issued
-    // in stream order: the caller for position r waits until the requests 0 .. r-1 have been issued, which also makes
-    // the ticket of a strip, drawn with its first tile, visible to the requests of its other tiles.  When the tickets
-    // are exhausted the barrier is completed without a tile, so that the filter warps wake up and see the end ticket.
-    auto request_tile = [&](uint32_t r, uint32_t itr, int cr) {
-        const unsigned long long t_begin = global_timer_ns();
-        while (ld_volatile_shared(s_req_done) != r) {
-            if (*s_abort != 0u) return;
-            if (global_timer_ns() - t_begin > kWaitLimitNs) {
-                atomicOr(p.flags, kFlagTmaTimeout);
-                *s_abort = 1u;
-                return;
+    uint32_t cur = 0u, nxt = 0xffffffffu;
+    bool have_nxt = false;
+    const int ahead = NC >= kTileStages ? kTileStages : NC;  // tiles requested this many chunks ahead (never beyond the next strip)
+
+    // request the tile of chunk c of the current strip (c < NC) or of chunk c - NC of the next strip; `it` is the
+    // current strip's sequence number in this CTA.  When the work is exhausted the barrier is completed without
+    // a tile, so that the filter warps wake up and see the end ticket.
+    auto request_tile = [&](int c, uint32_t stream_index, uint32_t it) {
+        uint32_t item = cur;
+        if (c >= NC) {
+            if (c - NC >= NC) return;
+            if (!have_nxt) {
+                nxt = atomicAdd(p.ticket, 1u);
+                have_nxt = true;
+                s_ticket[(it + 1u) & 1u] = nxt;
             }
+            item = nxt;
+            c -= NC;
         }
-        __threadfence_block();
-        uint32_t item;
-        if (cr == 0) {
-            item = atomicAdd(p.ticket, 1u);
-            s_ticket[itr % (uint32_t)kTicketSlots] = item;
-        } else {
-            item = s_ticket[itr % (uint32_t)kTicketSlots];
-        }
-        const uint32_t stage = r % (uint32_t)kTileStages;
+        const uint32_t stage = stream_index % (uint32_t)kTileStages;
         if (item >= total_items) {
             mbar_arrive(&full_bar[stage]);
-        } else {
-            const uint32_t frame = item / p.strips_per_frame;
-            const uint32_t strip = item - frame * p.strips_per_frame;
-            const int ty0 = first_out_row(MODE) + (int)strip * OUT_R - HS - 3;  // image row of tile row 0
-            mbar_expect_tx(&full_bar[stage], (uint32_t)L.tile_bytes);
-            tma_load_3d(tiles + stage * L.tile_bytes, &tmap, cr * kChunkW - kTileLead, ty0, (int)frame, &full_bar[stage]);
-            // and pull the strip's next tile into L2 (cp.async.bulk.prefetch.tensor: no shared memory, no completion), so
-            // that its load, one chunk from now, is an L2 hit
-            if (FDF_L2_PREFETCH > 0 && cr + FDF_L2_PREFETCH < NC)
-                tma_prefetch_l2_3d(&tmap, (cr + FDF_L2_PREFETCH) * kChunkW - kTileLead, ty0, (int)frame);
+            return;
         }
-        __threadfence_block();
-        *reinterpret_cast<volatile uint32_t *>(s_req_done) = r + 1u;
+        const uint32_t frame = item / p.strips_per_frame;
+        const uint32_t strip = item - frame * p.strips_per_frame;
+        const int ty0 = first_out_row(MODE) + (int)strip * OUT_R - HS - 3;  // image row of tile row 0
+        mbar_expect_tx(&full_bar[stage], (uint32_t)L.tile_bytes);
+        tma_load_3d(tiles + stage * L.tile_bytes, &tmap, c * kChunkW - kTileLead, ty0, (int)frame, &full_bar[stage]);
+        // and pull the strip's next tile into L2 (cp.async.bulk.prefetch.tensor: no shared memory, no completion), so
+        // that its load, one chunk from now, is an L2 hit (+1 %; 2 or 4 chunks ahead measured no better)
+        if (FDF_L2_PREFETCH > 0 && c + FDF_L2_PREFETCH < NC)
+            tma_prefetch_l2_3d(&tmap, (c + FDF_L2_PREFETCH) * kChunkW - kTileLead, ty0, (int)frame);
     };
 
-    if (tid == 0) {
+    if (t0) {
         tma_prefetch_desc(&tmap);
-        for (int i = 0; i < kTileStages; i++) {
-            mbar_init(&full_bar[i], 1);
+        for (int i = 0; i < kTileStages; i++) mbar_init(&full_bar[i], 1);
+        for (int i = 0; i < kQueueBufs; i++) {
             mbar_init(&q_full[i], kFilterWarps);
             qcount[i] = 0u;
-            t_done[i] = 0u;
-        }
-        for (int i = 0; i < 2; i++) {
-            mbar_init(&k_full[i], 1);
-            mbar_init(&p_free[i], 1);
-            kcount[i] = 0u;
-            e_done[i] = 0u;
         }
         fence_mbar_init();
-        *s_req_done = 0u;
+        *scount = 0u;
+        *s_total = 0u;
         *s_abort = 0u;
+        *s_dropped = 0u;
+        kcount[0] = kcount[1] = 0u;
+        s_block[0] = s_block[1] = 0ull;
+        *s_base = open_run(s_block, p);
+        cur = atomicAdd(p.ticket, 1u);
+        s_ticket[0] = cur;
     }
     if (tid < 3 * kVtabWords) vtabs[tid] = valid_word<MODE>(W, vtab_chunk(tid / kVtabWords, NC), tid % kVtabWords);
-    {
-        uint4 *pz = reinterpret_cast<uint4 *>(planes);
-        for (int i = tid; i < PL * L.plane_bytes / 16; i += kThreads) pz[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
+    auto clear_plane = [&](int i0, int n) {  // by n threads, i0 = index of this one
+        uint4 *pz = reinterpret_cast<uint4 *>(plane);
+        for (int i = i0; i < L.plane_bytes / 16; i += n) pz[i] = make_uint4(0u, 0u, 0u, 0u);
+    };
+    clear_plane(tid, kThreads);
 #ifdef FDF_TRACE
     volatile int &s_trace_cta = *reinterpret_cast<volatile int *>(misc + kMiscTrace);
     if (tid == 0) {
@@ -418,246 +420,145 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
 #ifdef FDF_TRACE
     const int trace_cta = s_trace_cta;
 #endif
-    if (tid == 0) {  // the first kTileStages tiles of the stream
-        uint32_t itr = 0u;
-        int cr = 0;
-        for (uint32_t r = 0; r < (uint32_t)kTileStages; r++) {
-            request_tile(r, itr, cr);
-            if (++cr == NC) {
-                cr = 0;
-                itr++;
-            }
-        }
-    }
+    cur = s_ticket[0];
+    if (t0)
+        for (int c = 0; c < ahead; c++) request_tile(c, (uint32_t)c, 0u);  // (ahead <= NC: all of the first strip)
 
     const int t = (int)p.threshold, n = (int)p.count;
-    uint32_t gc = 0;            // stream position of the chunk this warp works on
+    uint32_t gc = 0;   // chunks processed by this CTA so far
     uint32_t qb = 0, qpar = 0;  // tile stage = queue buffer = gc % kTileStages, and the parity of their mbarrier phases
-    uint32_t pi = 0, ppar = 0;  // plane / keypoint list = gc % PL, and the parity of their mbarrier phases
-    uint32_t cur = 0;           // ticket (frame, strip) of the current strip
-    auto next_chunk = [&]() {
-        gc++;
-        if (++qb == (uint32_t)kQueueBufs) {
-            qb = 0;
-            qpar ^= 1u;
-        }
-        if (++pi == (uint32_t)PL) {
-            pi = 0;
-            ppar ^= 1u;
-        }
-    };
 
-    if (warp < kFilterWarps) {
+    if (is_filter) {
         // ================================ filter warps =================================================
         const uint32_t kbias = filter_kbias(p.threshold);
-        for (uint32_t it = 0;; it++) {
-            for (int c = 0; c < NC; c++) {
-                mbar_wait(&full_bar[qb], qpar, p.flags, s_abort);  // the tile has landed (also: queue qb is free again)
-                if (c == 0) {
-                    cur = s_ticket[it % (uint32_t)kTicketSlots];
-                    if (cur >= total_items || *s_abort != 0u) {  // the stream has ended: pass the news on and leave
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&q_full[qb]);
-                        return;
-                    }
-                }
-                FDF_CLK(0)
-                const uint32_t frame = cur / p.strips_per_frame;
-                const uint32_t strip = cur - frame * p.strips_per_frame;
+        for (uint32_t it = 0; cur < total_items; it++) {
+            const uint32_t frame = cur / p.strips_per_frame;
+            const uint32_t strip = cur - frame * p.strips_per_frame;
+            for (int c = 0; c < NC; c++, gc++) {
                 const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
                 const uint8_t *tile = tiles + qb * L.tile_bytes;
+                mbar_wait(&full_bar[qb], qpar, p.flags, s_abort);  // the tile has landed (also: queue qb is free again)
+                FDF_CLK(0)
                 uint8_t *eb = ents + (gc & 1u) * (kFilterWarps * kWarpQueueCap);
                 uint32_t *nent = s_nent + (gc & 1u) * 4u;
                 const uint32_t ne = phase_a_stage1<MODE, SR, kFilterWarps>(warp, lane, tile, eb + warp * kWarpQueueCap, g, kbias);
                 if (lane == 0) nent[warp] = ne;
                 FDF_CLK(9)
                 bar_filter_group();  // every warp's entries of this chunk are in the table
-                FDF_CLK(10)
                 phase_a_stage2<MODE, SR, kFilterWarps>(tid, kFilterThreads, tile, eb, nent,
                                                        vtabs + vtab_variant(c, NC) * kVtabWords, queues + qb * kQueueCap,
                                                        &qcount[qb], kbias);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&q_full[qb]);
                 FDF_CLK(1)
-                next_chunk();
-            }
-        }
-    } else if (warp < kFilterWarps + kTestWarps) {
-        // ==================================== test warps ===================================================
-        const int twarp = warp - kFilterWarps, ttid = tid - kFilterThreads;
-        for (uint32_t it = 0;; it++) {
-            for (int c = 0; c < NC; c++) {
-                mbar_wait(&q_full[qb], qpar, p.flags, s_abort);
-                mbar_wait(&full_bar[qb], qpar, p.flags, s_abort);  // (completed long ago: makes the tile visible here too)
-                if (c == 0) cur = s_ticket[it % (uint32_t)kTicketSlots];
-                const bool ended = cur >= total_items || *s_abort != 0u;
-                mbar_wait(&p_free[pi], ppar ^ 1u, p.flags, s_abort);  // plane pi and its keypoint list are free
-                FDF_CLK(4)
-                uint32_t qn = 0u;
-                if (!ended) {
-                    const uint32_t frame = cur / p.strips_per_frame;
-                    const uint32_t strip = cur - frame * p.strips_per_frame;
-                    const uint8_t *tile = tiles + qb * L.tile_bytes;
-                    cell_t *plane = planes + pi * (SR * kPlaneW);
-                    qn = qcount[qb];
-                    if (qn <= (uint32_t)kQueueCap) {
-                        phase_b<MODE, SR>(ttid, lane, kTestThreads, qn, tile, queues + qb * kQueueCap, klists + pi * kKlistCap,
-                                          &kcount[pi], plane, t, n);
-                    } else {  // very dense content: every pixel, straight from the tile
-                        const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
-                        phase_b_dense<MODE, SR>(twarp, lane, kTestWarps, tile, plane, g, c, t, n);
-                    }
+                if (++qb == (uint32_t)kQueueBufs) {
+                    qb = 0;
+                    qpar ^= 1u;
                 }
+            }
+            // the next strip's ticket is published before its first tile is requested (or the end is signalled)
+            mbar_wait(&full_bar[qb], qpar, p.flags, s_abort);
+            cur = s_ticket[(it + 1u) & 1u];
+        }
+        return;
+    }
+
+    // ==================================== test warps ===================================================
+    uint32_t tag = 1u;  // (gc % kTagPeriod) + 1
+    const int twarp = warp - kFilterWarps;
+    // t0, between the group's barriers: the chunk's run record and the strip's running total
+    auto close_run = [&](uint32_t slot, uint32_t count, bool last) {
+        if (count != 0u) p.run_base[slot] = *s_base;
+        p.run_count[slot] = count;
+        const uint32_t tot = *s_total + count;
+        if (last) p.item_count[cur] = tot;
+        *s_total = last ? 0u : tot;
+    };
+    for (uint32_t it = 0; cur < total_items; it++) {
+        const uint32_t frame = cur / p.strips_per_frame;
+        const uint32_t strip = cur - frame * p.strips_per_frame;
+        for (int c = 0; c < NC; c++, gc++) {
+            const uint8_t *tile = tiles + qb * L.tile_bytes;
+            uint16_t *queue = queues + qb * kQueueCap;
+            const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
+            const uint32_t slot = cur * (uint32_t)NC + (uint32_t)c;
+            if (tag == 1u && gc != 0u) {  // every 15 chunks: restart the tags on a cleared plane
+                clear_plane(ttid, kTestThreads);
+                bar_test_group();
+            }
+            mbar_wait(&q_full[qb], qpar, p.flags, s_abort);
+            mbar_wait(&full_bar[qb], qpar, p.flags, s_abort);  // (completed long ago: makes the tile visible here too)
+            FDF_CLK(4)
+            const uint32_t qn = qcount[qb];
+            bool dropped = false;
+            if (qn <= (uint32_t)kQueueCap) {
+                phase_b<MODE, SR>(ttid, lane, kTestThreads, qn, tile, queue, klist, &kcount[gc & 1u], plane, t, n, tag);
                 FDF_CLK(5)
-                __syncwarp();
-                // the last test warp to get here hands the chunk on and recycles its tile and candidate queue
-                uint32_t last = 0u;
-                if (lane == 0) {
-                    __threadfence_block();
-                    last = atomicAdd(&t_done[qb], 1u) == (uint32_t)(kTestWarps - 1) ? 1u : 0u;
-                    if (last) {
-                        __threadfence_block();
-                        t_done[qb] = 0u;
-                        if (!ended) {
-                            if (qn > (uint32_t)kQueueCap) kcount[pi] = kDenseMark;
-                            qcount[qb] = 0u;
-                        }
-                        __threadfence_block();
-                        mbar_arrive(&k_full[pi]);
-                        if (!ended) {
-                            uint32_t itr = it;
-                            int cr = c + kTileStages;
-                            while (cr >= NC) {
-                                cr -= NC;
-                                itr++;
-                            }
-                            request_tile(gc + (uint32_t)kTileStages, itr, cr);
-                        }
-                    }
+                bar_test_group();  // every score of this chunk is in the plane and its keypoint list is complete
+                if (t0) {
+                    qcount[qb] = 0u;
+                    request_tile(c + ahead, gc + (uint32_t)ahead, it);
                 }
                 FDF_CLK(6)
-                if (ended) return;
-                next_chunk();
-            }
-        }
-    } else {
-        // ==================================== emit warps ===================================================
-        const int ewarp = warp - kFilterWarps - kTestWarps;
-        constexpr int kEmitThreads = kEmitWarps * 32;
-        const uint32_t lt = (1u << lane) - 1u;
-        unsigned long long blk_next = 0ull, blk_end = 0ull;  // this warp's staging block (warp-uniform)
-        uint32_t strip_total = 0u;                           // keypoints this warp staged for the current strip
-        bool overflow = false;
-        // room for `need` entries in the warp's block, or a new block from the global cursor
-        auto ensure_room = [&](uint32_t need) {
-            if (blk_next + need > blk_end) {
-                const unsigned long long nblk = need > (uint32_t)kStageBlock ? need : (unsigned long long)kStageBlock;
-                unsigned long long b = 0ull;
-                if (lane == 0) b = atomicAdd(p.cursor, nblk);
-                blk_next = __shfl_sync(0xffffffffu, b, 0);
-                blk_end = blk_next + nblk;
-            }
-        };
-        for (uint32_t it = 0;; it++) {
-            for (int c = 0; c < NC; c++) {
-                mbar_wait(&k_full[pi], ppar, p.flags, s_abort);
-                if (c == 0) cur = s_ticket[it % (uint32_t)kTicketSlots];
-                if (cur >= total_items || *s_abort != 0u) {
-                    if (overflow && lane == 0) atomicOr(p.flags, kFlagStagingOverflow);
-                    return;
-                }
+                dropped = emit_list<MODE, SR>(ttid, kTestThreads, kcount[gc & 1u], klist, plane, scount, *s_base,
+                                              p.staging_cap, p.staging, g);
                 FDF_CLK(7)
-                const uint32_t frame = cur / p.strips_per_frame;
-                const uint32_t strip = cur - frame * p.strips_per_frame;
-                const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
-                const cell_t *plane = planes + pi * (SR * kPlaneW);
-                const uint16_t *klist = klists + pi * kKlistCap;
-                const uint32_t kn = kcount[pi];
-                uint32_t count = 0u;
-                if (kn <= (uint32_t)kKlistCap) {
-                    // this warp's share of the keypoint list: entries ewarp * 32 + lane, + kEmitThreads, ...
-                    ensure_room(kn);
-                    for (uint32_t ib = (uint32_t)(ewarp * 32); ib < kn; ib += (uint32_t)kEmitThreads) {
-                        const uint32_t i = ib + (uint32_t)lane;
-                        const uint32_t ent = klist[i < kn ? i : ib];
-                        const bool keep = i < kn && list_entry_survives<MODE, SR>(ent, plane, g);
-                        const uint32_t b = __ballot_sync(0xffffffffu, keep);
-                        if (keep) {
-                            const unsigned long long o = blk_next + count + (uint32_t)__popc(b & lt);
-                            if (o < p.staging_cap) p.staging[o] = staged_entry<MODE>((int)(ent >> 8), (int)(ent & 0xffu), g);
-                            else overflow = true;
-                        }
-                        count += (uint32_t)__popc(b);
-                    }
-                } else {
-                    // the list overflowed or the chunk went through the dense path: scan this warp's rows of the plane,
-                    // count first (the run is reserved at its exact size), then write
-                    constexpr int kCells = SR * kPlaneW, kPer = (kCells + kEmitWarps - 1) / kEmitWarps;
-                    const int i0 = ewarp * kPer, i1 = min(kCells, i0 + kPer);
-                    for (int ib = i0; ib < i1; ib += 32) {
-                        const int i = ib + lane;
-                        const bool keep = i < i1 && plane_cell_survives<MODE, SR>(i, plane, g);
-                        count += (uint32_t)__popc(__ballot_sync(0xffffffffu, keep));
-                    }
-                    ensure_room(count);
-                    uint32_t at = 0u;
-                    for (int ib = i0; ib < i1; ib += 32) {
-                        const int i = ib + lane;
-                        const bool keep = i < i1 && plane_cell_survives<MODE, SR>(i, plane, g);
-                        const uint32_t b = __ballot_sync(0xffffffffu, keep);
-                        if (keep) {
-                            const unsigned long long o = blk_next + at + (uint32_t)__popc(b & lt);
-                            if (o < p.staging_cap) p.staging[o] = staged_entry<MODE>(i / kPlaneW, i % kPlaneW + kPlaneLead, g);
-                            else overflow = true;
-                        }
-                        at += (uint32_t)__popc(b);
-                    }
+                bar_test_group();  // the run is complete; the keypoint list is free
+                if (t0) {
+                    const uint32_t count = *scount;
+                    *scount = 0u;
+                    kcount[gc & 1u] = 0u;  // (next used two chunks from now)
+                    close_run(slot, count, c == NC - 1);
+                    s_block[0] = *s_base + count;  // give the unused tail back
+                    *s_base = open_run(s_block, p);
                 }
                 FDF_CLK(8)
-                if (lane == 0) {  // the warp's run record of this chunk
-                    const size_t slot = ((size_t)cur * (size_t)NC + (size_t)c) * kRunsPerChunk + (size_t)ewarp;
-                    p.run_base[slot] = blk_next;
-                    p.run_count[slot] = count;
+            } else {
+                // very dense content (e.g. noise): the queue overflowed.  Every scored pixel of the chunk gets the full
+                // test straight from the tile, then the score plane is scanned: count, reserve the run at its exact size,
+                // write
+                phase_b_dense<MODE, SR>(twarp, lane, kTestWarps, tile, plane, g, c, t, n, tag);
+                bar_test_group();  // every score of this chunk is in the plane; tile and queue are free
+                if (t0) {
+                    qcount[qb] = 0u;
+                    request_tile(c + ahead, gc + (uint32_t)ahead, it);
                 }
-                blk_next += count;
-                strip_total += count;
-                if (c == NC - 1) {
-                    if (lane == 0 && strip_total != 0u) atomicAdd(&p.item_count[cur], strip_total);
-                    strip_total = 0u;
+                nms_dense<MODE, SR>(ttid, kTestThreads, 0, plane, scount, 0ull, p.staging_cap, p.staging, g, tag);
+                bar_test_group();
+                const uint32_t kn = *scount;
+                bar_test_group();
+                if (t0) {
+                    *scount = 0u;
+                    s_block[0] = *s_base;  // the run opened for this chunk is not used: the exact size is known now
+                    *s_base = reserve_staging(kn, s_block, p);
                 }
-                __syncwarp();
-                // the last emit warp to get here wipes the chunk's cells and gives plane and list back
-                uint32_t last = 0u;
-                if (lane == 0) {
-                    __threadfence_block();
-                    last = atomicAdd(&e_done[pi], 1u) == (uint32_t)(kEmitWarps - 1) ? 1u : 0u;
+                bar_test_group();
+                if (kn != 0u)
+                    dropped = nms_dense<MODE, SR>(ttid, kTestThreads, 1, plane, scount, *s_base, p.staging_cap, p.staging, g, tag);
+                bar_test_group();
+                if (t0) {
+                    *scount = 0u;
+                    close_run(slot, kn, c == NC - 1);
+                    *s_base = open_run(s_block, p);
                 }
-                last = __shfl_sync(0xffffffffu, last, 0);
-                if (last) {
-                    __threadfence_block();
-                    cell_t *wplane = planes + pi * (SR * kPlaneW);
-                    if (kn <= (uint32_t)kKlistCap) {
-                        for (uint32_t i = (uint32_t)lane; i < kn; i += 32u) {
-                            const uint32_t ent = klist[i];
-                            wplane[(ent >> 8) * kPlaneW + (ent & 0xffu) - kPlaneLead] = (cell_t)0;
-                        }
-                    } else {
-                        uint4 *pz = reinterpret_cast<uint4 *>(wplane);
-                        for (int i = lane; i < L.plane_bytes / 16; i += 32) pz[i] = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        kcount[pi] = 0u;
-                        e_done[pi] = 0u;
-                        __threadfence_block();
-                        mbar_arrive(&p_free[pi]);
-                    }
-                }
-                FDF_CLK(11)
-                next_chunk();
+            }
+            if (dropped) *s_dropped = 1u;
+            tag = tag == (uint32_t)kTagPeriod ? 1u : tag + 1u;
+            if (++qb == (uint32_t)kQueueBufs) {
+                qb = 0;
+                qpar ^= 1u;
             }
         }
+        if (t0 && !have_nxt) {  // (only when the look-ahead never reached the next strip: cannot happen with ahead >= 1)
+            nxt = atomicAdd(p.ticket, 1u);
+            s_ticket[(it + 1u) & 1u] = nxt;
+        }
+        have_nxt = false;
+        bar_test_group();  // the next ticket and the next run's base are visible to the whole group
+        cur = s_ticket[(it + 1u) & 1u];
     }
+    // an entry that did not fit the staging buffer makes the result invalid: say so (the host maps it to an error)
+    if (t0 && *s_dropped != 0u) atomicOr(p.flags, kFlagStagingOverflow);
 }
 
 // ---- ordered compaction, step 2: exclusive scan of the per-strip counts -------------------------------
@@ -731,29 +632,29 @@ struct StripRecord {
 __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const DetectParams p, uint32_t n_items) {
     extern __shared__ __align__(16) uint32_t gsm[];
     __shared__ uint32_t warp_sums[kGatherThreads / 32];
-    __shared__ unsigned long long s_run_base[kGatherMaxRuns];
-    __shared__ uint32_t s_run_count[kGatherMaxRuns];
+    __shared__ unsigned long long s_run_base[kGatherMaxChunks];
+    __shared__ uint32_t s_run_count[kGatherMaxChunks];
     __shared__ StripRecord s_rec;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mode = (int)p.mode, sr = (int)p.sr;
-    const int WW = (int)p.words_per_row, NR = (int)p.chunks_per_strip * kRunsPerChunk;  // run records per strip
+    const int WW = (int)p.words_per_row, NC = (int)p.chunks_per_strip;
     const int nwords = out_rows(mode, sr) * WW;
     const int nsum = (nwords + 31) / 32;  // level-2 words
     uint32_t *bits = gsm, *summary = gsm + nsum * 32;
     for (int i = tid; i < nsum * 33; i += kGatherThreads) gsm[i] = 0u;
 
-    // records of a strip: thread r < NR holds run r, thread NR the strip's total and destination
+    // records of a strip: thread c < NC holds chunk c's run, thread NC the strip's total and destination
     unsigned long long r_base = 0ull;
     uint32_t r_count = 0u;
     auto fetch = [&](uint32_t item) {
         r_base = 0ull;
         r_count = 0u;
         if (item >= n_items) return;
-        if (tid < NR) {
-            const size_t slot = (size_t)item * NR + tid;
+        if (tid < NC) {
+            const size_t slot = (size_t)item * NC + tid;
             r_count = p.run_count[slot];
             r_base = r_count != 0u ? p.run_base[slot] : 0ull;
-        } else if (tid == NR) {
+        } else if (tid == NC) {
             r_count = p.item_count[item];
             r_base = p.item_dst[item];
         }
@@ -783,10 +684,10 @@ __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const Detect
     const int row_step = (32 * kGatherThreads) / WW, col_step = 32 * kGatherThreads - row_step * WW;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         __syncthreads();  // the previous strip is finished with the records (and, the first time, the bitmap is zero)
-        if (tid < NR) {
+        if (tid < NC) {
             s_run_base[tid] = r_base;
             s_run_count[tid] = r_count;
-        } else if (tid == NR) {
+        } else if (tid == NC) {
             s_rec.dst = r_base;
             s_rec.total = r_count;
         }
@@ -795,12 +696,12 @@ __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const Detect
         if (s_rec.total == 0u) continue;  // (block-uniform)
         const uint32_t strip = item % p.strips_per_frame;
         const uint32_t y0 = (uint32_t)(first_out_row(mode) + (int)strip * out_rows(mode, sr));
-        // one warp per run: its entries -> bits
-        for (int c = warp; c < NR; c += kGatherThreads / 32) {
+        // one warp per chunk: its run -> bits
+        for (int c = warp; c < NC; c += kGatherThreads / 32) {
             const unsigned long long base = s_run_base[c];
             const uint32_t cnt = s_run_count[c];
             for (uint32_t i = (uint32_t)lane; i < cnt; i += 32u) {
-                if (base + i >= p.staging_cap) {  // (the emit warp that dropped these entries has raised the flag too)
+                if (base + i >= p.staging_cap) {  // (the detection kernel that dropped these entries has raised the flag too)
                     atomicOr(p.flags, kFlagStagingOverflow);
                     break;
                 }
@@ -959,7 +860,10 @@ constexpr size_t kGatherSmemLimit = 200 * 1024;
 
 }  // namespace
 
-size_t detect_smem_bytes(int mode, int sr) { return (size_t)layout_sizes(mode, sr).total; }
+size_t detect_smem_bytes(int mode, int sr) {
+    (void)mode;
+    return (size_t)layout_sizes(sr).total;
+}
 
 size_t gather_smem_bytes(int mode, int sr, uint32_t words_per_row) {
     const size_t nsum = ((size_t)out_rows(mode, sr) * words_per_row + 31) / 32;  // level-2 words

@@ -9,26 +9,13 @@ namespace fdf {
 // Geometry shared by host and device.  A frame is cut into STRIPS of full-width rows; a CTA
 // takes one strip at a time (atomic ticket) and walks it left to right in CHUNKS.  For every chunk a 256-byte-wide tile
 // (chunk + halo) is staged into shared memory by one TMA 3-D tiled load.
-//
-// Warp roles of the detection kernel (three groups coupled only through mbarriers, see fdf_kernels.cu):
-//   filter warps   dense two-stage filter of a chunk -> candidate queue
-//   test warps     exact segment test + score per candidate -> score plane + keypoint list
-//   emit warps     3x3 non-maximal suppression over the keypoint list -> staging runs, run records
-#ifndef FDF_TEST_WARPS
-#define FDF_TEST_WARPS 4
-#endif
-#ifndef FDF_EMIT_WARPS
-#define FDF_EMIT_WARPS 2
-#endif
-constexpr int kFilterWarps = 4;
-constexpr int kTestWarps = FDF_TEST_WARPS;
-constexpr int kEmitWarps = FDF_EMIT_WARPS;
-constexpr int kThreads = (kFilterWarps + kTestWarps + kEmitWarps) * 32;  // threads per CTA of the detection kernel
+constexpr int kFilterWarps = 4;  // warps 0 .. 3 run phase A (dense filter), the others everything per candidate
+constexpr int kTestWarps = 6;
+constexpr int kThreads = (kFilterWarps + kTestWarps) * 32;  // threads per CTA of the detection kernel
 constexpr int kFilterThreads = kFilterWarps * 32;
 constexpr int kTestThreads = kTestWarps * 32;
 constexpr int kGatherThreads = 256; // threads per CTA of the gather kernel
-constexpr int kRunsPerChunk = kEmitWarps;  // every emit warp leaves its own run of staged keypoints per chunk
-constexpr int kGatherMaxRuns = kGatherThreads - 1;  // run records per strip the gather kernel holds
+constexpr int kGatherMaxChunks = kGatherThreads - 1;  // chunks per strip the gather kernel holds records for
 constexpr int kTileW = 256;     // tile width in bytes = TMA box inner extent (the maximum)
 constexpr int kChunkW = 240;    // output columns per chunk (the last chunk of a row may take one more)
 constexpr int kTileLead = 16;   // chunk c's tile starts at image column c*kChunkW - kTileLead: TMA needs the
@@ -38,11 +25,13 @@ constexpr int kLeftHalo = 12;   // the chunk's first output column is tile colum
 constexpr int kPlaneW = 248;    // score plane row pitch in cells: plane column = tile column - kPlaneLead
 constexpr int kPlaneLead = 8;   // (scored tile columns are 11 .. 252 = plane columns 3 .. 244; the NMS reads 3 .. 245)
 
-constexpr int kQueueCap = 1024; // candidate queue entries per chunk (typical fill: ~320 at 64 rows); more -> dense path
-constexpr int kKlistCap = 512;  // keypoint list entries per chunk (typical: ~170); more -> the emit warps scan the plane
-constexpr int kStageBlock = 4096;   // staging entries an emit warp reserves at a time from the global cursor
-constexpr unsigned long long kStageSlack = 2048ull * kStageBlock;  // what partly used blocks can waste (<= 1024 CTAs x 2 emit warps)
-constexpr int kWarpQueueCap = 256;  // 16-pixel groups one filter warp can pass from stage 1 to stage 2 per chunk
+constexpr int kTagPeriod = 15;  // score plane entries carry a 4-bit chunk tag (1..15) above the 12-bit score; the
+                                // plane is cleared every 15 chunks a CTA processes, so entries of
+                                // earlier chunks simply read as "no keypoint" and no per-chunk clear is needed
+constexpr int kQueueCap = 1024; // candidate queue entries per chunk (typical fill: ~320 at 64 rows); more -> dense path.
+                                // The keypoint lists have the same capacity, so they cannot overflow when the queue did not.
+constexpr int kStageBlock = 4096;   // staging entries a CTA reserves at a time from the global cursor
+constexpr int kWarpQueueCap = 256;  // 16-pixel groups one warp can pass from filter stage 1 to stage 2 per chunk
                                     // (= 32 lanes x 8 rows, the most stage 1 looks at)
 
 __host__ __device__ constexpr int chunks_per_row(int w) { return (w + kChunkW - 1) / kChunkW; }
@@ -60,15 +49,15 @@ struct DetectParams {
     uint32_t threshold, count;
     uint32_t mode, sr;       // (the gather kernel is not templated)
     unsigned long long cap;  // capacity of out, in points
-    unsigned long long staging_cap;   // capacity of staging: 2 cap + kStageSlack (blocks are not used to the end)
+    unsigned long long staging_cap;   // capacity of staging: 2 cap + one block per CTA (blocks are not used to the end)
     uint2 *out;              // fdf_point[cap], packed over the whole batch, row-major per frame
-    uint32_t *staging;       // [staging_cap] keypoints as (row in strip << 16 | x), kRunsPerChunk unordered runs per chunk
+    uint32_t *staging;       // [staging_cap] keypoints as (row in strip << 16 | x), one unordered run per chunk
     unsigned long long *offsets;      // n_frames + 1
     unsigned long long *cursor;       // staging bump allocator (zeroed per launch)
-    uint32_t *item_count;             // [items] keypoints of each (frame, strip)  (zeroed per launch; emit warps add to it)
+    uint32_t *item_count;             // [items] keypoints of each (frame, strip)
     unsigned long long *item_dst;     // [items] where the strip's points go in out (exclusive scan of item_count)
-    unsigned long long *run_base;     // [items * chunks * kRunsPerChunk] where a run sits in staging
-    uint32_t *run_count;              // [items * chunks * kRunsPerChunk] its length (every record is written, 0 = empty)
+    unsigned long long *run_base;     // [items * chunks] where the chunk's run sits in staging
+    uint32_t *run_count;              // [items * chunks] its length (every record is written; 0 = no run)
     unsigned long long *scan_status;  // look-back words of the scan kernel's tiles (zeroed per launch)
     uint32_t *ticket;                 // strip tickets of the detection kernel (zeroed per launch)
     uint32_t *scan_ticket;            // tile tickets of the scan kernel (zeroed per launch)

@@ -35,18 +35,6 @@ FDF_HD int lowest_set_bit(uint32_t m) {  // m != 0
 #endif
 }
 
-// Score plane cell: the MaxThreshold score of a keypoint is the smallest ring difference of its arc, at most 255,
-// and Off mode only records "keypoint here": one byte.  SumAbsolute sums up to 16 differences (<= 4080): two bytes.
-// 0 = no keypoint (fast_simd.rs:366, 598-603: every keypoint scores at least 1).
-template <int MODE>
-struct PlaneCell {
-    typedef uint8_t type;
-};
-template <>
-struct PlaneCell<NMS_SUM_ABSOLUTE> {
-    typedef uint16_t type;
-};
-
 struct ChunkGeo {
     int w, h;   // image size
     int ys0;    // image row of scored row 0
@@ -242,8 +230,8 @@ FDF_HD void phase_a_stage2(int ftid, int nthreads, const uint8_t *tile, const ui
         cnt[v] = nent[v];
         total += cnt[v];
     }
-    for (uint32_t gidx = (uint32_t)ftid; gidx < total; gidx += (uint32_t)nthreads) {
-        uint32_t i = gidx;
+    // entry gidx of the concatenated segments -> (scored row, group)
+    auto locate = [&](uint32_t i, int &rr, int &q) {
         int v = 0;
 #pragma unroll
         for (int u = 0; u < NW - 1; u++)
@@ -252,7 +240,32 @@ FDF_HD void phase_a_stage2(int ftid, int nthreads, const uint8_t *tile, const ui
                 v = u + 1;
             }
         const uint32_t e = ents[v * kWarpQueueCap + (int)i];
-        const int rr = v * RW + (int)(e >> 4), q = (int)(e & 15u);
+        rr = v * RW + (int)(e >> 4);
+        q = (int)(e & 15u);
+    };
+#if defined(FDF_STAGE2_X2)
+    // two entries per thread and step: two independent dependency chains (loads, masks) and one queue reservation
+    for (uint32_t gidx = (uint32_t)ftid; gidx < total; gidx += 2u * (uint32_t)nthreads) {
+        const bool two = gidx + (uint32_t)nthreads < total;
+        int rr0, q0, rr1, q1;
+        locate(gidx, rr0, q0);
+        locate(two ? gidx + (uint32_t)nthreads : gidx, rr1, q1);
+        const uint32_t m0 = stage2_mask(rr0, q0, tile, vtab, kbias);
+        uint32_t m1 = stage2_mask(rr1, q1, tile, vtab, kbias);
+        if (!two) m1 = 0u;
+        const uint32_t c0 = (uint32_t)popc32(m0), c1 = (uint32_t)popc32(m1);
+        if (c0 + c1 != 0u) {
+            const uint32_t slot = atomic_add_u32(qcount, c0 + c1);
+            if (slot + c0 + c1 <= (uint32_t)kQueueCap) {
+                push_candidates(rr0, q0, m0, queue, slot);
+                push_candidates(rr1, q1, m1, queue, slot + c0);
+            }
+        }
+    }
+#else
+    for (uint32_t gidx = (uint32_t)ftid; gidx < total; gidx += (uint32_t)nthreads) {
+        int rr, q;
+        locate(gidx, rr, q);
         const uint32_t m = stage2_mask(rr, q, tile, vtab, kbias);
         if (m != 0u) {
             const uint32_t c = (uint32_t)popc32(m);
@@ -260,15 +273,16 @@ FDF_HD void phase_a_stage2(int ftid, int nthreads, const uint8_t *tile, const ui
             if (slot + c <= (uint32_t)kQueueCap) push_candidates(rr, q, m, queue, slot);
         }
     }
+#endif
 }
 
 // ---- phase B: exact segment test (+ score) per candidate (replaces fast_simd.rs:115-297, 623-749)
 // One thread per queue entry: 16 ring bytes + the centre from the tile, one dual word per ring pixel (fdf_core.cuh),
 // best window -> keypoint yes / no and the MaxThreshold score in the same ~50 instructions.  Every keypoint writes
-// its score into the score plane at (scored row, tile column - kPlaneLead) -- in Off mode the score is 1 and only the
-// dense path reads it -- and is appended to the chunk's keypoint list as scored row << 8 | tile column (one ballot per
-// warp step, one shared atomic per warp step that found a keypoint).  *kcount counts every keypoint, also those that
-// no longer fit the list (the emit warps then scan the plane instead).
+// (tag << 12 | score) into the score plane at (scored row, tile column - kPlaneLead) -- in Off mode the score is 1
+// and only the dense path reads it -- and is appended to the chunk's keypoint list as scored row << 8 | tile
+// column (one ballot per warp step, one shared atomic per warp step that found a keypoint).  klist == nullptr
+// (dense path): no list.
 // On the device the 32 lanes of a warp call it together (lane >= 0); the host emulator calls it once per thread
 // with lane = -1.
 struct KeypointTest {
@@ -276,74 +290,88 @@ struct KeypointTest {
     uint32_t score;
 };
 
-template <int MODE>
+// NFIX: the consecutive count as a compile-time constant (9), or 0 = use n (see best_window)
+template <int MODE, int NFIX>
 FDF_HD KeypointTest test_pixel(const uint8_t *pc, int t, int n) {
     RingDual ring;
     const uint32_t bias = dual_bias((int)pc[0]);
 #pragma unroll
     for (int k = 0; k < 16; k++) ring.w[k] = dual_word((uint32_t)pc[FDF_RING_DY(k) * kTileW + FDF_RING_DX(k)], bias);
-    const uint32_t best = best_of_lanes(best_window(ring, n));
+    const uint32_t best = best_of_lanes(best_window<NFIX>(ring, n));
     KeypointTest r;
     r.kp = best > (uint32_t)(256 + t);
     r.score = 1u;  // Off mode: the plane only records "keypoint here" (used by the dense path)
     if (MODE == NMS_MAX_THRESHOLD) r.score = best - 256u;                  // (garbage unless kp)
-    if (MODE == NMS_SUM_ABSOLUTE) r.score = score_sum_abs_dual(ring, t);  // <= 4080
+    if (MODE == NMS_SUM_ABSOLUTE) r.score = score_sum_abs_dual(ring, t);  // <= 4080 < 2^12
     return r;
 }
 
-template <int MODE, int SR>
-FDF_HD void phase_b(int tid, int lane, int nthreads, uint32_t qn, const uint8_t *tile, const uint16_t *queue,
-                    uint16_t *klist, uint32_t *kcount, typename PlaneCell<MODE>::type *plane, int t, int n) {
-    typedef typename PlaneCell<MODE>::type cell_t;
+template <int MODE, int SR, int NFIX>
+FDF_HD void phase_b_loop(int tid, int lane, int nthreads, uint32_t qn, const uint8_t *tile, const uint16_t *queue,
+                         uint16_t *klist, uint32_t *kcount, uint16_t *plane, int t, int n, uint32_t tag) {
     const int l = lane < 0 ? 0 : lane;
-    for (uint32_t ib = (uint32_t)(tid - l); ib < qn; ib += (uint32_t)nthreads) {  // (warp-uniform trip count)
-        const uint32_t i = ib + (uint32_t)l;
-        const bool valid = i < qn;
-        const uint32_t ent = queue[valid ? i : ib];
+    uint32_t ib = (uint32_t)(tid - l);
+    if (ib >= qn) return;
+    uint32_t ent = queue[ib + (uint32_t)l < qn ? ib + (uint32_t)l : ib];
+    while (true) {  // (warp-uniform trip count)
+        const bool valid = ib + (uint32_t)l < qn;
+        const uint32_t nb = ib + (uint32_t)nthreads;
+        const bool more = nb < qn;
+        uint32_t ent_next = 0u;
+        if (more) ent_next = queue[nb + (uint32_t)l < qn ? nb + (uint32_t)l : nb];  // (in flight during the arithmetic)
         const int rr = (int)(ent >> 9);
         const int j = (int)((ent >> 5) & 15u) * 16 + mask_bit_to_px((int)(ent & 31u));
-        const KeypointTest r = test_pixel<MODE>(tile + (rr + 3) * kTileW + j, t, n);
+        const KeypointTest r = test_pixel<MODE, NFIX>(tile + (rr + 3) * kTileW + j, t, n);
         const bool kp = valid && r.kp;
-        if (kp) plane[rr * kPlaneW + j - kPlaneLead] = (cell_t)r.score;
+        if (kp) plane[rr * kPlaneW + j - kPlaneLead] = (uint16_t)((tag << 12) | r.score);
 #if defined(__CUDA_ARCH__)
         const uint32_t b = __ballot_sync(0xffffffffu, kp);
         if (b != 0u) {
             uint32_t base = 0u;
             if (lane == 0) base = atomicAdd(kcount, (uint32_t)__popc(b));
             base = __shfl_sync(0xffffffffu, base, 0);
-            const uint32_t at = base + (uint32_t)__popc(b & ((1u << lane) - 1u));
-            if (kp && at < (uint32_t)kKlistCap) klist[at] = (uint16_t)((rr << 8) | j);
+            if (kp) klist[base + (uint32_t)__popc(b & ((1u << lane) - 1u))] = (uint16_t)((rr << 8) | j);
         }
 #else
-        if (kp) {
-            const uint32_t at = (*kcount)++;
-            if (at < (uint32_t)kKlistCap) klist[at] = (uint16_t)((rr << 8) | j);
-        }
+        if (kp) klist[(*kcount)++] = (uint16_t)((rr << 8) | j);
 #endif
+        if (!more) break;
+        ib = nb;
+        ent = ent_next;
     }
 }
 
-// Dense path (the candidate queue overflowed: very dense content): every scored pixel of the chunk gets the full test
-// straight from the tile, no filter, no queue, no list -- warp `twarp` of `ntwarps` takes scored rows twarp, twarp +
-// ntwarps, ..., its lanes the columns.  The emit warps then scan the plane.
+// The loop is instantiated for n = 9 (the reference's and OpenCV's default) and once more for "any n": the run-time
+// form costs an indirect branch per candidate.
 template <int MODE, int SR>
-FDF_HD void phase_b_dense(int twarp, int lane, int ntwarps, const uint8_t *tile, typename PlaneCell<MODE>::type *plane,
-                          const ChunkGeo &g, int chunk, int t, int n) {
-    typedef typename PlaneCell<MODE>::type cell_t;
+FDF_HD void phase_b(int tid, int lane, int nthreads, uint32_t qn, const uint8_t *tile, const uint16_t *queue,
+                    uint16_t *klist, uint32_t *kcount, uint16_t *plane, int t, int n, uint32_t tag) {
+    if (n == 9) phase_b_loop<MODE, SR, 9>(tid, lane, nthreads, qn, tile, queue, klist, kcount, plane, t, n, tag);
+    else phase_b_loop<MODE, SR, 0>(tid, lane, nthreads, qn, tile, queue, klist, kcount, plane, t, n, tag);
+}
+
+// Dense path (the candidate queue overflowed: very dense content, e.g. noise): every scored pixel of the chunk gets
+// the full test straight from the tile, no filter, no queue, no list -- warp `twarp` of `ntwarps` takes scored rows
+// twarp, twarp + ntwarps, ..., its lanes the columns.  nms_dense then scans the plane.
+template <int MODE, int SR>
+FDF_HD void phase_b_dense(int twarp, int lane, int ntwarps, const uint8_t *tile, uint16_t *plane, const ChunkGeo &g,
+                          int chunk, int t, int n, uint32_t tag) {
     const RowRange rows = live_rows(g, SR);
     const ColRange cols = scored_cols<MODE>(g.w, chunk);
     const int l0 = lane < 0 ? 0 : lane, lstep = lane < 0 ? 1 : 32;
     for (int rr = rows.lo + twarp; rr < rows.hi; rr += ntwarps)
         for (int j = cols.lo + l0; j < cols.hi; j += lstep) {
-            const KeypointTest r = test_pixel<MODE>(tile + (rr + 3) * kTileW + j, t, n);
-            if (r.kp) plane[rr * kPlaneW + j - kPlaneLead] = (cell_t)r.score;
+            const KeypointTest r = test_pixel<MODE, 0>(tile + (rr + 3) * kTileW + j, t, n);
+            if (r.kp) plane[rr * kPlaneW + j - kPlaneLead] = (uint16_t)((tag << 12) | r.score);
         }
 }
 
 // ---- NMS: strict maximum over the 8 neighbours (replaces fast_simd.rs:588-616) -------------------
 // Only this chunk's own columns and this strip's own rows are emitted; rows 3 and h-4 are scored
 // (they act as neighbours) but never emitted (fast_simd.rs:589-596, opencv_compat.rs:238-240).
-// The plane holds the scores of this chunk's keypoints and zeros (it is cleaned after every chunk).
+// Plane cells hold tag << 12 | score with score >= 1.  Tags only grow between two clears of the plane, so a stale
+// cell (an earlier chunk's) is smaller than tag << 12, i.e. smaller than any current cell: comparing the raw cells
+// is the same as comparing the scores with stale cells read as "no keypoint".
 FDF_HD uint32_t max3u(uint32_t a, uint32_t b, uint32_t c) {
 #if defined(__CUDA_ARCH__)
     return __vimax3_u32(a, b, c);
@@ -360,10 +388,9 @@ FDF_HD bool nms_emits(int rr, int j, const ChunkGeo &g) {
     return !(rr < 1 || rr > SR - 2 || x < g.x0 || x >= g.x1 || y >= g.h - 4);
 }
 
-// is the cell pp a strict maximum of its 3x3 neighbourhood?  (branch-free; pp must have a full neighbourhood
-// inside the plane)
-template <class cell_t>
-FDF_HD bool nms_is_max(const cell_t *pp) {
+// is the (current) cell pp a strict maximum of its 3x3 neighbourhood?  (branch-free; pp must have a full
+// neighbourhood inside the plane)
+FDF_HD bool nms_is_max(const uint16_t *pp) {
     const uint32_t a = max3u(pp[-kPlaneW - 1], pp[-kPlaneW], pp[-kPlaneW + 1]);
     const uint32_t b = max3u(pp[kPlaneW - 1], pp[kPlaneW], pp[kPlaneW + 1]);
     const uint32_t c = max3u(pp[-1], pp[1], a);
@@ -376,23 +403,49 @@ FDF_HD uint32_t staged_entry(int rr, int j, const ChunkGeo &g) {
     return (uint32_t)((rr - (MODE == NMS_OFF ? 0 : 1)) << 16) | (uint32_t)(g.xt0 + j);
 }
 
-// does the keypoint list entry survive (Off mode: is it one of the chunk's own columns)?
+// The chunk's keypoint list: every keypoint that survives the NMS (Off mode: every keypoint of the chunk's own
+// columns) is written to the staging buffer at base + slot, slots handed out through *scount.  A slot beyond the
+// staging buffer's capacity is not written; the function then returns true and the kernel raises the overflow flag
+// (the count still includes the keypoint, so the host sees both the needed size and the flag).
 template <int MODE, int SR>
-FDF_HD bool list_entry_survives(uint32_t ent, const typename PlaneCell<MODE>::type *plane, const ChunkGeo &g) {
-    const int rr = (int)(ent >> 8), j = (int)(ent & 0xffu);
-    const bool in = nms_emits<MODE, SR>(rr, j, g);
-    // (a keypoint that cannot be emitted is looked up at a harmless cell with a full neighbourhood)
-    if (MODE != NMS_OFF) return nms_is_max(plane + (in ? rr * kPlaneW + j - kPlaneLead : kPlaneW + 1)) && in;
-    return in;
+FDF_HD bool emit_list(int tid, int nthreads, uint32_t kn, const uint16_t *klist, const uint16_t *plane,
+                      uint32_t *scount, unsigned long long base, unsigned long long cap, uint32_t *staging,
+                      const ChunkGeo &g) {
+    bool dropped = false;
+    for (uint32_t i = (uint32_t)tid; i < kn; i += (uint32_t)nthreads) {
+        const uint32_t ent = klist[i];
+        const int rr = (int)(ent >> 8), j = (int)(ent & 0xffu);
+        const bool in = nms_emits<MODE, SR>(rr, j, g);
+        bool keep = in;
+        // (a keypoint that cannot be emitted is looked up at a harmless cell with a full neighbourhood)
+        if (MODE != NMS_OFF) keep = nms_is_max(plane + (in ? rr * kPlaneW + j - kPlaneLead : kPlaneW + 1)) && in;
+        if (keep) {
+            const unsigned long long o = base + atomic_add_u32(scount, 1u);
+            if (o < cap) staging[o] = staged_entry<MODE>(rr, j, g);
+            else dropped = true;
+        }
+    }
+    return dropped;
 }
 
-// does plane cell i hold a keypoint that this chunk emits?  (dense path: the emit warps scan the plane)
+// Dense path: every cell of the plane.  Pass 0 counts the survivors, pass 1 writes them to staging[base + slot]
+// with slots handed out through *counter.  Returns true if an entry did not fit the staging buffer.
 template <int MODE, int SR>
-FDF_HD bool plane_cell_survives(int i, const typename PlaneCell<MODE>::type *plane, const ChunkGeo &g) {
-    if (plane[i] == 0) return false;
-    const int rr = i / kPlaneW, j = i % kPlaneW + kPlaneLead;
-    if (!nms_emits<MODE, SR>(rr, j, g)) return false;
-    return MODE == NMS_OFF || nms_is_max(plane + i);
+FDF_HD bool nms_dense(int tid, int nthreads, int pass, const uint16_t *plane, uint32_t *counter, unsigned long long base,
+                      unsigned long long cap, uint32_t *staging, const ChunkGeo &g, uint32_t tag) {
+    bool dropped = false;
+    for (int i = tid; i < SR * kPlaneW; i += nthreads) {
+        if (plane[i] < (tag << 12)) continue;
+        const int rr = i / kPlaneW, j = i % kPlaneW + kPlaneLead;
+        if (!nms_emits<MODE, SR>(rr, j, g)) continue;
+        if (MODE != NMS_OFF && !nms_is_max(plane + i)) continue;
+        const uint32_t slot = atomic_add_u32(counter, 1u);
+        if (pass == 1) {
+            if (base + slot < cap) staging[base + slot] = staged_entry<MODE>(rr, j, g);
+            else dropped = true;
+        }
+    }
+    return dropped;
 }
 
 // ---- emission (gather kernel): bit plane -> points, row-major ------------------------------------------

@@ -12,6 +12,7 @@
 
 #include "../../feature_detector_fast_b200/csrc/fdf_strip.cuh"
 #include "../../oracle/fdf_oracle.h"
+#include "second_impl.h"
 
 namespace {
 
@@ -19,13 +20,11 @@ using namespace fdf;
 
 // Mirrors what the kernel does with one chunk: stage 1 by every filter warp, stage 2 by the filter threads over all
 // warps' entries, phase B by the test threads (or the dense path over every scored pixel when the candidate queue
-// overflowed), then the emit warps' pass over the chunk's keypoint list (or over the whole plane when the list
-// overflowed or the chunk was dense); the survivors go to the staging buffer as unordered runs and the chunk's cells
-// are wiped from the plane.  At the end of a strip the gather kernel's part follows: runs -> bit plane -> row-major
-// points.
+// overflowed), NMS pass over the chunk's keypoint list (or over the whole plane in the dense path), then the chunk's
+// surviving keypoints go to the staging buffer as one unordered run.  At the end of a strip the gather kernel's part
+// follows: runs -> bit plane -> row-major points.
 template <int MODE, int SR>
 int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2 *out, size_t cap, int *fallbacks) {
-    typedef typename PlaneCell<MODE>::type cell_t;
     constexpr int OUT_R = out_rows(MODE, SR);
     constexpr int TR = tile_rows(SR);
     const long long rows = (long long)h - 2 * first_out_row(MODE);
@@ -34,8 +33,7 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
     const int NC = chunks_per_row(w);
     const int WW = (w + 31) / 32;
     alignas(16) static uint8_t tile[tile_rows(64) * kTileW];
-    std::vector<cell_t> plane((size_t)SR * kPlaneW, (cell_t)0);
-    std::vector<uint16_t> queue(kQueueCap), klist(kKlistCap);
+    std::vector<uint16_t> plane((size_t)SR * kPlaneW), queue(kQueueCap), klist(kQueueCap);
     std::vector<uint8_t> ents((size_t)kFilterWarps * kWarpQueueCap);
     alignas(16) uint32_t vtab[3][kVtabWords];  // validity tables: first / middle / last chunk of a row
     for (int v = 0; v < 3; v++)
@@ -43,9 +41,10 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
     std::vector<uint32_t> bits((size_t)OUT_R * WW), staged;
     const uint32_t kbias = filter_kbias((uint32_t)t);
     unsigned long long total = 0;
+    uint32_t gc = 0, tag = 1;
     for (int strip = 0; strip < S; strip++) {
         staged.clear();
-        for (int c = 0; c < NC; c++) {
+        for (int c = 0; c < NC; c++, gc++) {
             const ChunkGeo g = make_geo<MODE>(w, h, strip, c, SR);
             const int ty0 = g.ys0 - 3;
             if (g.xt0 % 16 != 0) return -16;  // TMA: innermost box start must be 16-byte aligned
@@ -54,8 +53,6 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
                     const int y = ty0 + r, x = g.xt0 + j;
                     tile[r * kTileW + j] = (y >= 0 && y < h && x >= 0 && x < w) ? img[(size_t)y * pitch + x] : 0;
                 }
-            for (cell_t v : plane)
-                if (v != 0) return -24;  // the plane must be clean between chunks
             const uint32_t *vt = vtab[vtab_variant(c, NC)];
             uint32_t qcount = 0, nent[kFilterWarps];
             for (int warp = 0; warp < kFilterWarps; warp++)
@@ -63,31 +60,37 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
             for (int ftid = 0; ftid < kFilterThreads; ftid++)
                 phase_a_stage2<MODE, SR, kFilterWarps>(ftid, kFilterThreads, tile, ents.data(), nent, vt, queue.data(), &qcount, kbias);
             const uint32_t qn = qcount;
-            uint32_t kn = 0;
+            if (tag == 1u && gc != 0u) std::fill(plane.begin(), plane.end(), (uint16_t)0);
             if (qn <= (uint32_t)kQueueCap) {
+                uint32_t kn = 0;
                 for (int tid = 0; tid < kTestThreads; tid++)
-                    phase_b<MODE, SR>(tid, -1, kTestThreads, qn, tile, queue.data(), klist.data(), &kn, plane.data(), t, n);
+                    phase_b<MODE, SR>(tid, -1, kTestThreads, qn, tile, queue.data(), klist.data(), &kn, plane.data(), t, n, tag);
                 if (kn > qn) return -19;
+                std::vector<uint32_t> run(kn + 1);
+                uint32_t scount = 0;
+                bool dropped = false;
+                for (int tid = 0; tid < kTestThreads; tid++)
+                    dropped |= emit_list<MODE, SR>(tid, kTestThreads, kn, klist.data(), plane.data(), &scount, 0ull, kn, run.data(), g);
+                if (scount > kn || dropped) return -20;
+                staged.insert(staged.end(), run.begin(), run.begin() + scount);
             } else {
                 if (fallbacks) fallbacks[0]++;
                 for (int twarp = 0; twarp < kTestWarps; twarp++)
-                    phase_b_dense<MODE, SR>(twarp, -1, kTestWarps, tile, plane.data(), g, c, t, n);
-                kn = 0xffffffffu;
-            }
-            if (kn <= (uint32_t)kKlistCap) {
-                for (uint32_t i = 0; i < kn; i++) {
-                    const uint32_t ent = klist[i];
-                    if (list_entry_survives<MODE, SR>(ent, plane.data(), g))
-                        staged.push_back(staged_entry<MODE>((int)(ent >> 8), (int)(ent & 0xffu), g));
-                }
-                for (uint32_t i = 0; i < kn; i++) plane[(klist[i] >> 8) * kPlaneW + (klist[i] & 0xffu) - kPlaneLead] = (cell_t)0;
-            } else {
+                    phase_b_dense<MODE, SR>(twarp, -1, kTestWarps, tile, plane.data(), g, c, t, n, tag);
                 if (fallbacks) fallbacks[1]++;
-                for (int i = 0; i < SR * kPlaneW; i++)
-                    if (plane_cell_survives<MODE, SR>(i, plane.data(), g))
-                        staged.push_back(staged_entry<MODE>(i / kPlaneW, i % kPlaneW + kPlaneLead, g));
-                std::fill(plane.begin(), plane.end(), (cell_t)0);
+                uint32_t counter = 0;
+                for (int tid = 0; tid < kTestThreads; tid++)
+                    nms_dense<MODE, SR>(tid, kTestThreads, 0, plane.data(), &counter, 0ull, 0ull, nullptr, g, tag);
+                std::vector<uint32_t> run(counter + 1);
+                const uint32_t kn = counter;
+                counter = 0;
+                bool dropped = false;
+                for (int tid = 0; tid < kTestThreads; tid++)
+                    dropped |= nms_dense<MODE, SR>(tid, kTestThreads, 1, plane.data(), &counter, 0ull, kn, run.data(), g, tag);
+                if (counter != kn || dropped) return -21;
+                staged.insert(staged.end(), run.begin(), run.begin() + kn);
             }
+            tag = tag == (uint32_t)kTagPeriod ? 1u : tag + 1u;
         }
         // the gather kernel's part: the strip's runs -> bit plane -> row-major points
         std::fill(bits.begin(), bits.end(), 0u);
@@ -123,7 +126,7 @@ extern "C" {
 int64_t fdf_emulate_detect(const uint8_t *img, uint32_t w, uint32_t h, uint32_t pitch, uint8_t t, uint8_t n,
                            uint8_t nms, int sr, fdf_oracle_point *out, size_t cap, int *fallbacks) {
     uint2 *o = reinterpret_cast<uint2 *>(out);
-    if (fallbacks) fallbacks[0] = fallbacks[1] = 0;  // [0] queue overflow -> dense test, [1] plane scan by the emit warps
+    if (fallbacks) fallbacks[0] = fallbacks[1] = 0;  // chunks that took the dense path: [0] every-pixel test, [1] plane scan
 #define CASE(M, S) \
     if (nms == M && sr == S) return emulate<M, S>(img, (int)w, (int)h, (int)pitch, t, n, o, cap, fallbacks);
     CASE(0, 32) CASE(0, 48) CASE(0, 64) CASE(1, 32) CASE(1, 48) CASE(1, 64) CASE(2, 32) CASE(2, 48) CASE(2, 64)
@@ -184,7 +187,8 @@ int64_t fdf_core_check(uint64_t iterations, uint64_t seed) {
         // the form the kernel uses: one dual word per ring pixel, test and MaxThreshold score from the best window
         RingDual rd;
         for (int i = 0; i < 16; i++) rd.w[i] = dual_word((uint32_t)ring[i], dual_bias(c));
-        const uint32_t best = best_of_lanes(best_window(rd, n));
+        const uint32_t best = best_of_lanes(best_window<0>(rd, n));
+        if (n == 9 && best_window<9>(rd, n) != best_window<0>(rd, n)) bad++;  // the kernel's n = 9 instantiation
         if ((best > (uint32_t)(256 + t)) != (kp_bright || kp_dark)) bad++;
         if ((kp_bright || kp_dark) &&
             best - 256u != fdf_oracle_score_max_threshold_px((uint8_t)c, ring8, (uint8_t)n))
