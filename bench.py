@@ -6,9 +6,11 @@
 
 Workload (BASELINE.json configs[4]): a batch of synthetic 3840x2160 grey frames, threshold 20, count 9,
 max-threshold NMS.  One "step" = one pass of the detection path over this rank's resident batch
-(512 frames per GPU; frames are independent units, so ranks share nothing on the data path and the job is
-weak-scaled: N GPUs process N x 512 frames per step) followed, for N > 1, by the path's only exchange
-step: one NCCL all-gather of per-frame keypoint counts -> global CSR offsets.
+(512 frames per GPU; frames are independent units, so ranks share nothing on the data path and the headline is
+weak-scaled: N GPUs process N x 512 frames per step).  For N > 1 a step goes through the product's sharded path
+(feature_detector_fast_b200.sharding.ShardedDetector): detection per rank, ONE NCCL all-gather of the ranks' local CSR
+offsets, and every rank's emission kernel writes its points straight into rank 0's result buffer over NVLink -- one
+batch result.  `strong` repeats the measurement for the literal config 5: ONE 512-frame batch sharded over the N GPUs.
 
   value        Mpix/s, whole job, frames already resident in HBM when the timed region starts
   e2e          same metric through the C-ABI call `fdf_detect_batch` on HOST (pinned) buffers: host->device
@@ -18,7 +20,11 @@ step: one NCCL all-gather of per-frame keypoint counts -> global CSR offsets.
                library on the launching stream during the timed steps), against the measured HBM copy
                bandwidth in MEASURED_PEAKS.json
   cpu_baseline AVX2 port of the reference's fast_simd.rs (oracle/fdf_avx2_port.cpp) on the host cores,
-               bounded sample of the same frames (rank 0, N = 1 only); reported, not the target
+               bounded sample of the same frames (rank 0, N = 1 only); reported, not the target.  It also re-checks the
+               GPU result: per-frame hashes (tests/compare.rs:5-20 format) of the sampled frames must be equal.
+  by_config    (rank 0, N = 1) the other BASELINE configs on resident synthetic 1080p frames: configs 1-3 (t16 n9, the
+               three NMS modes), config 4 (n = 9..16 x three modes), the uniform-noise stress frame, and the crate's
+               criterion triple (benches/benchmark.rs: one frame per call through fdf_detect, mean and 95 % CI)
 
 `--impl reference` times that CPU port alone (the reference crate is Rust and cannot be built in this
 image, so the port stands in for it), with all host threads, on bounded samples of the same workload.
@@ -41,6 +47,13 @@ FRAMES_PER_GPU = 512
 SEED = 20240
 METRIC = "Mpixels/sec (FAST-n detection; also 1080p frames/sec and HBM GB/s vs peak)"
 WORKLOAD = "configs[4]: 512 synthetic 3840x2160 frames per GPU, t=20, n=9, max-threshold NMS"
+
+
+def workload_config(frames_per_gpu):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "frames_per_gpu": frames_per_gpu, "width": W, "height": H, "threshold": THRESHOLD,
+            "count": COUNT, "nms": "max_threshold",
+            "l2": "inputs larger than L2 (4.2 GB per GPU per step vs 126 MB)"}
 
 
 def measured_hbm_peak():
@@ -174,22 +187,69 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def time_cpu_port(frames_np, n_threads, min_seconds, oracle):
+def criterion_triple(run, label):
+    """benches/benchmark.rs restated (SURVEY 8f F4): the crate's three criterion functions -- simd_t16_c_9_off /
+    _max_threshold / _sum_abs, one 1920x1080 frame per iteration -- timed criterion-style (warm-up, then samples; mean
+    and a 95 % confidence interval of the mean).  `run(nms)` performs one iteration and returns the keypoint count."""
+    import math
+
+    names = {0: "simd_t16_c_9_off", 1: "simd_t16_c_9_max_threshold", 2: "simd_t16_c_9_sum_abs"}
+    out = {}
+    for nms, name in names.items():
+        t_end = time.perf_counter() + 0.3  # warm-up
+        found = run(nms)
+        while time.perf_counter() < t_end:
+            found = run(nms)
+        samples = []
+        t_end = time.perf_counter() + 1.0
+        while len(samples) < 100 or (time.perf_counter() < t_end and len(samples) < 2000):
+            t0 = time.perf_counter()
+            run(nms)
+            samples.append((time.perf_counter() - t0) * 1e3)
+        mean = sum(samples) / len(samples)
+        sd = math.sqrt(sum((x - mean) ** 2 for x in samples) / (len(samples) - 1))
+        half = 1.96 * sd / math.sqrt(len(samples))
+        out[name] = {"ci95_ms": [round(mean - half, 4), round(mean, 4), round(mean + half, 4)], "samples": len(samples),
+                     "keypoints": int(found), "mpix_per_s": round(1920 * 1080 / mean / 1e3, 1)}
+    out["protocol"] = ("benches/benchmark.rs restated: one synthetic 1920x1080 scene frame per call (the reference's "
+                       "screenshot is not shipped), t=16 n=9, warm-up then >= 100 samples; " + label)
+    return out
+
+
+def synth_frames_host(oracle, n, w, h, first=0, threads=1):
+    """n synthetic frames (F, H, W) generated on the host cores, with slack after the last frame (the AVX2 port's gathers
+    over-read by <= 3 bytes)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+
+    pad = np.zeros(n * h * w + 64, np.uint8)
+    frames = pad[: n * h * w].reshape(n, h, w)
+
+    def fill(f):
+        frames[f] = oracle.synth_frame(w, h, SEED, first + f, 0, 4)
+
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+        list(ex.map(fill, range(n)))
+    return frames
+
+
+def time_cpu_port(frames_np, n_threads, min_seconds, oracle, want_hashes=False):
     """AVX2 port over `frames_np` (F, H, W) with n_threads workers, repeated for >= min_seconds."""
     f = frames_np.shape[0]
     reps, t0 = 0, time.perf_counter()
-    counts = None
+    counts = hashes = None
     while True:
-        counts, _ = oracle.port_detect_many(frames_np, THRESHOLD, COUNT, NMS, n_threads=n_threads, want_hashes=False)
+        counts, hashes = oracle.port_detect_many(frames_np, THRESHOLD, COUNT, NMS, n_threads=n_threads,
+                                                 want_hashes=want_hashes)
         reps += 1
         dt = time.perf_counter() - t0
         if dt >= min_seconds:
             break
-    return (reps * f * W * H) / dt / 1e6, dt, reps, counts
+    return (reps * f * W * H) / dt / 1e6, dt, reps, counts, hashes
 
 
 def run_reference_arm(args, rank):
-    """CPU port of the reference path, all host threads, bounded samples of the same workload."""
+    """CPU port of the reference path, all host threads, the full workload per step (512 frames)."""
     if rank != 0:
         return 0
     import numpy as np
@@ -198,13 +258,8 @@ def run_reference_arm(args, rank):
 
     oracle.build()
     cores = host_threads()
-    n = max(cores, 8)
-    frames = np.zeros((n, H, W), np.uint8)
-    for f in range(n):
-        frames[f] = oracle.synth_frame(W, H, SEED, f, 0, 4)
-    pad = np.zeros(frames.size + 64, np.uint8)
-    pad[: frames.size] = frames.reshape(-1)
-    frames = pad[: frames.size].reshape(n, H, W)
+    n = args.frames
+    frames = synth_frames_host(oracle, n, W, H, threads=cores)
     for _ in range(args.warmup):
         oracle.port_detect_many(frames, THRESHOLD, COUNT, NMS, n_threads=cores, want_hashes=False)
     t0 = time.perf_counter()
@@ -212,17 +267,21 @@ def run_reference_arm(args, rank):
         oracle.port_detect_many(frames, THRESHOLD, COUNT, NMS, n_threads=cores, want_hashes=False)
     dt = time.perf_counter() - t0
     mpix = args.steps * n * W * H / dt / 1e6
-    sample = f"{n} of the workload's 3840x2160 frames per step, one frame per thread, {cores} threads"
+    sample = f"the workload's {n} 3840x2160 frames per step, one frame per thread at a time, {cores} threads"
+    frame1080 = synth_frames_host(oracle, 1, 1920, 1080)[0]
+    crit = criterion_triple(lambda nms: len(oracle.port_detect(frame1080, 16, 9, nms)),
+                            "CPU port of fast_simd.rs on one thread of this host")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(mpix, 2), "unit": "Mpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": n, "width": W, "height": H, "threshold": THRESHOLD,
-                   "count": COUNT, "nms": "max_threshold",
-                   "note": "CPU port of fast_simd.rs (the Rust reference cannot be built here: no cargo/rustc)"},
+        "config": workload_config(n),
+        "note": "CPU port of fast_simd.rs (the Rust reference cannot be built here: no cargo/rustc); the CPU arm is one "
+                "host whatever --gpus says",
         "cpu_baseline": {"value": round(mpix, 2), "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(mpix, 2), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "fps_1080p_equiv": round(mpix * 1e6 / (1920 * 1080), 1),
+        "criterion": crit,
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -230,54 +289,68 @@ def run_reference_arm(args, rank):
 
 
 def run_criterion(args, rank):
-    """benches/benchmark.rs restated (SURVEY 8f F4): the crate's three criterion functions -- simd_t16_c_9_off /
-    _max_threshold / _sum_abs, one 1920x1080 frame per iteration -- timed criterion-style (warm-up, then samples;
-    mean and a 95 % confidence interval of the mean) for one arm: `--impl b200` = one fdf_detect call per iteration
-    through the C ABI with HOST buffers (copies included), `--impl reference` = the CPU port on one thread.
-    Prints one JSON line per function.  The reference's published numbers (README.md:55-65, i7-4770TE, its private
-    1080p screenshot): 5.34 / 8.71 / 7.23 ms."""
+    """`--criterion`: only the benches/benchmark.rs triple, one JSON line per arm."""
     if rank != 0:
         return 0
-    import math
-
-    import numpy as np
-
     import oracle  # (synthetic frame generator; the CPU arm also times the port -- bench.py's CPU-baseline role)
 
     oracle.build()
-    w, h = 1920, 1080
-    frame = oracle.synth_frame(w, h, SEED, 0, 0, 4)
-    pad = np.zeros(frame.size + 64, np.uint8)
-    pad[: frame.size] = frame.reshape(-1)
-    frame = pad[: frame.size].reshape(h, w)
-    names = {0: "simd_t16_c_9_off", 1: "simd_t16_c_9_max_threshold", 2: "simd_t16_c_9_sum_abs"}
+    frame = synth_frames_host(oracle, 1, 1920, 1080)[0]
     if args.impl == "b200":
         import feature_detector_fast_b200 as fdf
 
         det = fdf.Detector(0)
-        run = lambda nms: len(det.detect_array(frame, fdf.Config(16, 9, fdf.NonMaximalSuppression(nms))))
+        crit = criterion_triple(lambda nms: len(det.detect_array(frame, fdf.Config(16, 9, fdf.NonMaximalSuppression(nms)))),
+                                "fdf_detect through the C ABI, host buffers, copies included")
     else:
-        run = lambda nms: len(oracle.port_detect(frame, 16, 9, nms))
-    for nms, name in names.items():
-        t_end = time.perf_counter() + 1.0  # warm-up
-        while time.perf_counter() < t_end:
-            found = run(nms)
-        samples = []
-        t_end = time.perf_counter() + 4.0
-        while len(samples) < 100 or (time.perf_counter() < t_end and len(samples) < 2000):
-            t0 = time.perf_counter()
-            run(nms)
-            samples.append((time.perf_counter() - t0) * 1e3)
-        mean = sum(samples) / len(samples)
-        sd = math.sqrt(sum((x - mean) ** 2 for x in samples) / (len(samples) - 1))
-        half = 1.96 * sd / math.sqrt(len(samples))
-        print(json.dumps({"criterion": name, "impl": args.impl, "unit": "ms per 1920x1080 frame",
-                          "ci95": [round(mean - half, 4), round(mean, 4), round(mean + half, 4)],
-                          "samples": len(samples), "keypoints": found, "mpix_per_s": round(w * h / mean / 1e3, 1),
-                          "data": "synthetic 1080p scene frame (the reference's screenshot is not shipped)",
-                          "api": "fdf_detect, host buffers" if args.impl == "b200" else "CPU port of fast_simd.rs, 1 thread"}),
-              flush=True)
+        crit = criterion_triple(lambda nms: len(oracle.port_detect(frame, 16, 9, nms)),
+                                "CPU port of fast_simd.rs on one thread of this host")
+    print(json.dumps({"criterion": crit, "impl": args.impl}), flush=True)
     return 0
+
+
+def bench_by_config(det, fdf, torch, peak):
+    """The other BASELINE configs, device-resident, on synthetic 1080p frames (rank 0, N = 1).  Every entry: Mpix/s of
+    the whole step (three kernels), the detection kernel's milliseconds and its fraction of the HBM roofline."""
+    w, h, f = 1920, 1080, 256
+    frames = det.synth_frames(f, w, h, seed=SEED + 1, first_frame=0, kind=0, amp=4)
+    points = torch.empty((f * 60000, 2), dtype=torch.int32, device=frames.device)
+    offsets = torch.empty(f + 1, dtype=torch.int64, device=frames.device)
+    names = {0: "off", 1: "max_threshold", 2: "sum_absolute"}
+
+    def one(frames, t, n, nms, steps=5):
+        cfg = fdf.Config(t, n, fdf.NonMaximalSuppression(nms))
+        nf = frames.shape[0]
+        for _ in range(2):
+            det.detect_device(frames, cfg, points=points, offsets=offsets)
+        torch.cuda.synchronize()
+        found = int(offsets[nf].item())
+        if found > points.shape[0] or det.device_flags() != 0:
+            raise SystemExit("bench.py: by_config run invalid (capacity or device flags)")
+        det.set_timing(steps)
+        for _ in range(steps):
+            det.detect_device(frames, cfg, points=points, offsets=offsets)
+        torch.cuda.synchronize()
+        ms = [det.get_timing(i) for i in range(steps)]
+        det.set_timing(0)
+        k = sum(m[0] for m in ms) / steps
+        step = sum(sum(m) for m in ms) / steps
+        algo = nf * w * h + 8 * found + 8 * (nf + 1)
+        return {"mpix_per_s": round(nf * w * h / step / 1e3, 1), "detect_kernel_ms": round(k, 4), "step_ms": round(step, 4),
+                "roofline_frac": round(algo / (k * 1e-3) / 1e9 / peak, 4), "keypoints_per_frame": round(found / nf, 1)}
+
+    out = {"frames": f"{f} resident synthetic 1920x1080 scene frames (seed {SEED + 1}); the reference's 1080p screenshot is "
+                     "not shipped, its published counts 23184 / 7646 / 8307 are not reproducible"}
+    out["configs_1_to_3_t16_n9"] = {names[nms]: one(frames, 16, 9, nms) for nms in (0, 1, 2)}
+    sweep = {}
+    for n in range(9, 17):
+        sweep[f"n{n}"] = {names[nms]: one(frames[:64], 16, n, nms, steps=3) for nms in (0, 1, 2)}
+    out["config_4_count_sweep_t16"] = {"frames": 64, "by_count": sweep}
+    noise = det.synth_frames(32, w, h, seed=SEED + 2, first_frame=0, kind=1, amp=0)
+    del points
+    points = torch.empty((32 * w * h // 3, 2), dtype=torch.int32, device=frames.device)
+    out["uniform_noise_stress_t20_n9_max_threshold"] = one(noise, 20, 9, 1, steps=3)
+    return out
 
 
 def main():
@@ -291,6 +364,7 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU (default: the named config)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-by-config", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
@@ -322,74 +396,153 @@ def main():
     cfg = fdf.Config(THRESHOLD, COUNT, fdf.NonMaximalSuppression.MaxThreshold)
     F = args.frames
     n_total = F * world
+    per_frame_cap = 100000  # ~2.4x the expected keypoints of this workload (about 18.6k per 4K frame); checked below
     frames = det.synth_frames(F, W, H, seed=SEED, first_frame=rank * F, kind=0, amp=4)
-    cap = F * 100000  # ~2.4x the expected keypoints of this workload (about 42k per 4K frame); checked below
-    points = torch.empty((cap, 2), dtype=torch.int32, device=dev)
-    offsets = torch.empty(F + 1, dtype=torch.int64, device=dev)
+    cap = F * per_frame_cap
     torch.cuda.synchronize()
-
-    def step():
-        det.detect_device(frames, cfg, points=points, offsets=offsets)
-        if world > 1:
-            counts = sharding.counts_from_offsets(offsets)
-            return sharding.global_offsets(sharding.gather_frame_counts(counts, n_total))
-        return offsets
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    found = int(offsets[-1].item())
-    if found > cap or det.device_flags() != 0:
-        raise SystemExit(f"bench.py: invalid run (found {found} > cap {cap} or device flags set)")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # One step of the product path.  N = 1: fdf_detect_device.  N > 1: the sharded path (one batch result on rank 0).
+    sd = None
+    if world == 1:
+        points = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+        offsets = torch.empty(F + 1, dtype=torch.int64, device=dev)
+
+        def step():
+            det.detect_device(frames, cfg, points=points, offsets=offsets)
+    else:
+        sd = sharding.ShardedDetector(det, n_total, cap_total=n_total * per_frame_cap, cap_local=cap)
+
+        def step():
+            sd.detect(frames, cfg)
+
+    def timed_steps(step_fn, steps, fence=None):
+        """exactly `steps` steps between barriers; CUDA events on the launching stream; max over ranks"""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            step_fn()
+        if fence is not None:
+            fence()  # (rank 0 may read the other ranks' points only after this; it is part of the timed region)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt[0])
+        return ms
+
+    for _ in range(args.warmup):
+        step()
+    if sd is not None:
+        sd.fence()
+    torch.cuda.synchronize()
+    if world == 1:
+        found = int(offsets[-1].item())
+        local_found = found
+    else:
+        goffs = sd.global_offsets
+        found = int(goffs[-1].item())
+        lo, hi = sharding.frame_shard(n_total, rank, world)
+        local_found = int((goffs[hi] - goffs[lo]).item())
+    if local_found > cap or det.device_flags() != 0:
+        raise SystemExit(f"bench.py: invalid run (found {local_found} > cap {cap} or device flags set)")
+
     # ---- device-resident timing: exactly K steps, CUDA events, max over ranks --------------------
     sampler = ClockSampler(local_rank)
     det.set_timing(args.steps)  # CUDA events around each launch, recorded by the library on the launching stream
     launches0 = det.kernel_launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if rank == 0:
         sampler.start()
         sampler.wait_ready()
     barrier()
     sampler.mark_begin()
-    ev0.record()
-    for i in range(args.steps):
-        det.detect_device(frames, cfg, points=points, offsets=offsets)
-        if world > 1:
-            counts = sharding.counts_from_offsets(offsets)
-            sharding.global_offsets(sharding.gather_frame_counts(counts, n_total))
-    ev1.record()
-    barrier()
+    total_ms = timed_steps(step, args.steps, fence=sd.fence if sd is not None else None)
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches = det.kernel_launches - launches0
-    total_ms = ev0.elapsed_time(ev1)
     per_launch = [det.get_timing(i) for i in range(args.steps)]
     det.set_timing(0)
     kern_ms = sum(t[0] for t in per_launch) / args.steps        # the dominant kernel: fdf_detect_kernel
     scan_ms = sum(t[1] for t in per_launch) / args.steps
-    gather_ms = sum(t[2] for t in per_launch) / args.steps
+    gather_ms = sum(t[2] for t in per_launch) / args.steps       # (0 in the sharded path: its emission launch is not timed)
     if world > 1:
-        tt = torch.tensor([total_ms, kern_ms], device=dev)
+        tt = torch.tensor([kern_ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms, kern_ms = float(tt[0]), float(tt[1])
+        kern_ms = float(tt[0])
     ms_per_step = total_ms / args.steps
     mpix = n_total * W * H / (ms_per_step * 1e-3) / 1e6
 
     peak, peak_src = measured_hbm_peak()
-    algo_bytes = F * W * H + 8 * found + 8 * (F + 1)
+    algo_bytes = F * W * H + 8 * local_found + 8 * (F + 1)
     achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": committed_traffic(), "peak_source": peak_src,
                 "kernel": "fdf_detect_kernel<MaxThreshold,64>", "kernel_ms": round(kern_ms, 4),
                 "other_kernels_ms": {"fdf_scan_kernel": round(scan_ms, 4), "fdf_gather_kernel": round(gather_ms, 4)},
                 "algorithmic_bytes_per_launch": algo_bytes,
-                "read_only_frac": round(F * W * H / (kern_ms * 1e-3) / 1e9 / peak, 4)}
+                "read_only_frac": round(F * W * H / (kern_ms * 1e-3) / 1e9 / peak, 4),
+                "whole_step_frac": round(algo_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4)}
+
+    # ---- N > 1: rank 0 verifies the one batch result the timed steps produced ---------------------------
+    multi_check = None
+    if world > 1:
+        ok, detail = True, ""
+        blocks = sd._all.clone()
+        want_offs, bases = sharding.global_offsets_from_blocks(blocks, n_total, world)
+        if not torch.equal(want_offs, sd.global_offsets):
+            ok, detail = False, "global offsets differ from the scan of the ranks' counts"
+        if rank == 0:
+            import oracle
+
+            oracle.build()
+            offs_h = sd.global_offsets.cpu().numpy()
+            checked = []
+            for r in range(world):
+                lo_r, hi_r = sharding.frame_shard(n_total, r, world)
+                for f in sorted({lo_r, hi_r - 1}):
+                    want = oracle.port_detect(oracle.synth_frame(W, H, SEED, f, 0, 4), THRESHOLD, COUNT, NMS)
+                    got = sd.points[int(offs_h[f]):int(offs_h[f + 1])].cpu().numpy().astype(np.uint32)
+                    same = got.shape == want.shape and oracle.hash_points(got) == oracle.hash_points(want)
+                    checked.append(f)
+                    if not same:
+                        ok, detail = False, f"frame {f} (rank {r}) differs from the CPU port"
+            multi_check = {"frames_hash_checked_on_rank0": checked}
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            raise SystemExit(f"bench.py: multi-GPU result check failed on some rank ({detail})")
+        if rank == 0:
+            multi_check.update({"global_offsets_equal_scan_of_all_ranks_counts": True, "hashes_equal_cpu_port": True,
+                                "keypoints_in_batch_result": found})
+
+    # ---- strong scaling: the literal config 5, ONE 512-frame batch sharded over the N GPUs -----------------
+    strong = None
+    strong_total = FRAMES_PER_GPU
+    if world == 1:
+        if F == strong_total:
+            strong = {"frames_total": strong_total, "frames_per_gpu": F, "value": round(mpix, 1), "unit": "Mpix/s",
+                      "ms_per_step": round(ms_per_step, 4), "steps": args.steps, "note": "same measurement as `value` at N = 1"}
+    elif strong_total % world == 0 and strong_total // world <= F:
+        fs = strong_total // world
+        s_frames = frames[:fs]  # (frame content does not matter for the timing; the check above covered correctness)
+        sds = sharding.ShardedDetector(det, strong_total, cap_total=strong_total * per_frame_cap, cap_local=fs * per_frame_cap)
+        s_steps = max(20, args.steps)
+        for _ in range(3):
+            sds.detect(s_frames, cfg)
+        sds.fence()
+        s_ms = timed_steps(lambda: sds.detect(s_frames, cfg), s_steps, fence=sds.fence)
+        strong = {"frames_total": strong_total, "frames_per_gpu": fs, "unit": "Mpix/s", "steps": s_steps,
+                  "value": round(strong_total * W * H / (s_ms / s_steps * 1e-3) / 1e6, 1),
+                  "ms_per_step": round(s_ms / s_steps, 4),
+                  "note": "one 512-frame batch, looped; every step ends in one batch result on rank 0"}
+        sds.close()
 
     # ---- end to end through the C ABI with host (pinned) buffers ------------------------------------
     e2e = None
@@ -416,14 +569,14 @@ def main():
             tt = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt[0])
-        assert k == found, "end-to-end path found a different number of keypoints"
+        assert k == local_found, "end-to-end path found a different number of keypoints"
         e2e = {"value": round(n_total * W * H * e2e_steps / dt / 1e6, 1), "unit": "Mpix/s",
-               "h2d_bytes_per_step": F * W * H, "d2h_bytes_per_step": 8 * (F + 1) + 8 * found + 4,
+               "h2d_bytes_per_step": F * W * H, "d2h_bytes_per_step": 8 * (F + 1) + 8 * local_found + 4,
                "steps": e2e_steps, "ms_per_step": round(dt / e2e_steps * 1e3, 3),
                "api": "fdf_detect_batch (C ABI, pinned host buffers)", "host_placement": numa or "default"}
         del h_frames, h_points
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only), which also re-checks the GPU counts ---------------
+    # ---- CPU baseline beside it (rank 0, N = 1 only), which also re-checks the GPU result ---------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
@@ -435,31 +588,50 @@ def main():
         pad = np.zeros(sample.size + 64, np.uint8)
         pad[: sample.size] = sample.reshape(-1)
         sample = pad[: sample.size].reshape(n_s, H, W)
-        one_mpix, _, _, _ = time_cpu_port(sample[:4], 1, 4.0, oracle)
-        all_mpix, dt_all, reps, counts = time_cpu_port(sample, cores, 8.0, oracle)
-        gpu_counts = (offsets[1:n_s + 1] - offsets[:n_s]).cpu().numpy()
-        if not (gpu_counts == counts).all():
-            raise SystemExit("bench.py: GPU keypoint counts differ from the CPU port on the sampled frames")
+        one_mpix, _, _, _, _ = time_cpu_port(sample[:4], 1, 4.0, oracle)
+        all_mpix, dt_all, reps, counts, hashes = time_cpu_port(sample, cores, 8.0, oracle, want_hashes=True)
+        offs_h = offsets.cpu().numpy()
+        pts_h = points[: int(offs_h[n_s])].cpu().numpy().astype(np.uint32)
+        for f in range(n_s):
+            if oracle.hash_points(pts_h[offs_h[f]:offs_h[f + 1]]) != int(hashes[f]) or offs_h[f + 1] - offs_h[f] != counts[f]:
+                raise SystemExit(f"bench.py: GPU keypoints of frame {f} differ from the CPU port (hash of the ordered list)")
         cpu = {"value": round(all_mpix, 1), "unit": "Mpix/s", "cores": cores, "kind": "port",
                "sample": f"{n_s} of the batch's frames x {reps} passes, one frame per thread ({dt_all:.1f} s); "
                          f"single thread on 4 frames: {one_mpix:.1f} Mpix/s",
-               "single_thread_value": round(one_mpix, 1), "counts_match_gpu": True}
+               "single_thread_value": round(one_mpix, 1), "hashes_match_gpu": True}
+
+    # ---- the other BASELINE configs (rank 0, N = 1 only) ---------------------------------------------
+    by_config = None
+    if rank == 0 and world == 1 and not args.no_by_config:
+        del points
+        torch.cuda.empty_cache()
+        by_config = bench_by_config(det, fdf, torch, peak)
+        import oracle
+
+        oracle.build()
+        frame1080 = synth_frames_host(oracle, 1, 1920, 1080)[0]
+        by_config["criterion"] = criterion_triple(
+            lambda nms: len(det.detect_array(frame1080, fdf.Config(16, 9, fdf.NonMaximalSuppression(nms)))),
+            "fdf_detect through the C ABI, host buffers, copies included")
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(mpix, 1), "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": F, "width": W, "height": H, "threshold": THRESHOLD,
-                       "count": COUNT, "nms": "max_threshold", "keypoints_per_step_rank0": found,
-                       "l2": "inputs larger than L2 (4.2 GB per GPU per step vs 126 MB)",
-                       "collective": "all_gather of per-frame counts (NCCL)" if world > 1 else "none (1 GPU)"},
+            "config": workload_config(F),
+            "details": {"keypoints_per_step_rank0": local_found, "keypoints_per_step_all_ranks": found,
+                        "collective": ("one all_gather of the ranks' local CSR offsets (NCCL); points are written by the "
+                                       "emission kernels straight into rank 0's result over NVLink") if world > 1
+                        else "none (1 GPU)"},
             "fps_1080p_equiv": round(mpix * 1e6 / (1920 * 1080), 1),
             "fps_4k": round(mpix * 1e6 / (W * H), 1),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "strong": strong, "multi_gpu_check": multi_check,
+            "by_config": by_config, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    if sd is not None:
+        sd.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

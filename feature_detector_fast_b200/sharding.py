@@ -97,7 +97,7 @@ class ShardedDetector:
         self.device = torch.device("cuda", detector.device)
         lib, ctx = detector._lib, detector._ctx
         self._all = torch.zeros(self.world * self.block, dtype=torch.int64, device=self.device)
-        self._mine = self._all[self.rank * self.block: (self.rank + 1) * self.block]
+        self._mine = torch.zeros(self.block, dtype=torch.int64, device=self.device)  # this rank's block (send buffer)
         self.global_offsets = torch.zeros(self.n_frames + 1, dtype=torch.int64, device=self.device)
         self._fence = torch.zeros(1, dtype=torch.int32, device=self.device)
         # rank 0 allocates the result and broadcasts its IPC handle; the others map it (peer access over NVLink)
@@ -136,7 +136,7 @@ class ShardedDetector:
         if st != 0:
             from .api import _raise
             _raise(lib, det._ctx, st)
-        dist.all_gather_into_tensor(self._all, self._mine, group=self.group)  # in place: rank r's block is its input
+        dist.all_gather_into_tensor(self._all, self._mine, group=self.group)
         st = lib.fdf_detect_shard_finish(det._ctx, self._all.data_ptr(), self.block, self.world, self.rank,
                                          self.n_frames, self._ptr, self.cap_total, self.global_offsets.data_ptr(), s)
         if st != 0:
