@@ -56,11 +56,9 @@ def load_library() -> C.CDLL:
     lib.fdf_detect_batch.argtypes = [vp, vp, u32, u32, u32, u32, u64, u8, u8, u8, vp, sz, vp]
     lib.fdf_detect_device.restype = C.c_int
     lib.fdf_detect_device.argtypes = [vp, vp, u32, u32, u32, u32, u64, u8, u8, u8, vp, sz, vp, vp]
-    if hasattr(lib, "fdf_detect_shard_begin"):  # (what-if builds of older sources loaded through FDF_LIB lack these)
-        lib.fdf_detect_shard_begin.restype = C.c_int
-        lib.fdf_detect_shard_begin.argtypes = [vp, vp, u32, u32, u32, u32, u64, u8, u8, u8, sz, vp, vp]
-        lib.fdf_detect_shard_finish.restype = C.c_int
-        lib.fdf_detect_shard_finish.argtypes = [vp, vp, u32, u32, u32, u32, vp, sz, vp, vp]
+    if hasattr(lib, "fdf_shard_push"):  # (what-if builds of older sources loaded through FDF_LIB lack these)
+        lib.fdf_shard_push.restype = C.c_int
+        lib.fdf_shard_push.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, sz, vp, vp]
         lib.fdf_shared_alloc.restype = C.c_int
         lib.fdf_shared_alloc.argtypes = [vp, sz, C.POINTER(vp), vp]
         lib.fdf_shared_open.restype = C.c_int

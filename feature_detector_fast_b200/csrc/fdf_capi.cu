@@ -67,8 +67,6 @@ struct fdf_ctx {
     fdf::DeviceInfo info;        // SM count, kernel occupancies, experiment knobs: looked up once in fdf_create
     int force_sr = 0;            // FDF_FORCE_SR (experiments / tests): strip height override, read once in fdf_create
     unsigned long long sub_batch_bytes = 128ull << 20;  // fdf_detect_batch sub-batch size (FDF_SUB_BATCH_MB, read once)
-    fdf::DetectParams shard_params;  // fdf_detect_shard_begin -> fdf_detect_shard_finish
-    bool shard_pending = false;
     std::vector<void *> shared_owned, shared_opened;  // fdf_shared_alloc / fdf_shared_open
     std::vector<cudaEvent_t> timing_events;  // 4 per slot: before detection, after it, after scan, after gather
     uint64_t timing_calls = 0;
@@ -324,61 +322,13 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
 }
 
 // ---- sharded batches: one process per GPU, one exchange step -------------------------------------------
-fdf_status fdf_detect_shard_begin(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h,
-                                  uint32_t pitch, uint64_t frame_stride, uint8_t threshold, uint8_t count, uint8_t nms,
-                                  size_t cap_local, uint64_t *d_local_offsets, void *stream_handle) {
+fdf_status fdf_shard_push(fdf_ctx *ctx, const uint64_t *d_all_offsets, uint32_t block, uint32_t n_ranks, uint32_t rank,
+                          uint32_t total_frames, const fdf_point *d_points, fdf_point *d_result, size_t cap_total,
+                          uint64_t *d_global_offsets, void *stream_handle) {
     if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
-    ctx->shard_pending = false;
-    fdf_status st = check_config(ctx, count, nms);
-    if (st != FDF_OK) return st;
-    if (!d_local_offsets) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null output pointer");
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_handle);
-    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
-    fdf::DetectParams p;
-    CUtensorMap tmap;
-    bool empty = false;
-    st = prepare_detect(ctx, d_frames, n_frames, w, h, pitch, frame_stride, threshold, count, nms, cap_local, stream, p,
-                        tmap, &empty);
-    if (st != FDF_OK) return st;
-    if (empty) {  // (this rank has no frames, or no frame can hold a keypoint: it still takes part in the exchange)
-        FDF_CUDA(ctx, cudaMemsetAsync(d_local_offsets, 0, ((size_t)n_frames + 1) * sizeof(uint64_t), stream));
-        p = fdf::DetectParams();
-        p.n_frames = 0;
-        ctx->shard_params = p;
-        ctx->shard_pending = true;
-        return FDF_OK;
-    }
-    p.out = nullptr;
-    p.offsets = reinterpret_cast<unsigned long long *>(d_local_offsets);
-    cudaEvent_t *ev = nullptr;
-    if (!ctx->timing_events.empty()) {
-        const size_t slots = ctx->timing_events.size() / 4;
-        ev = &ctx->timing_events[4 * (size_t)(ctx->timing_calls++ % slots)];
-        FDF_CUDA(ctx, cudaEventRecord(ev[0], stream));
-    }
-    FDF_CUDA(ctx, fdf::launch_detect((int)p.mode, (int)p.sr, tmap, p, stream, ctx->info));
-    if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[1], stream));
-    FDF_CUDA(ctx, fdf::launch_scan(p, stream));
-    if (ev) {
-        FDF_CUDA(ctx, cudaEventRecord(ev[2], stream));
-        FDF_CUDA(ctx, cudaEventRecord(ev[3], stream));  // (the gather launch of a sharded call is not timed)
-    }
-    ctx->launches += 2;
-    ctx->shard_params = p;
-    ctx->shard_pending = true;
-    return FDF_OK;
-}
-
-fdf_status fdf_detect_shard_finish(fdf_ctx *ctx, const uint64_t *d_all_offsets, uint32_t block, uint32_t n_ranks,
-                                   uint32_t rank, uint32_t total_frames, fdf_point *d_result, size_t cap_total,
-                                   uint64_t *d_global_offsets, void *stream_handle) {
-    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
-    if (!ctx->shard_pending) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "fdf_detect_shard_finish without a begin");
-    ctx->shard_pending = false;
-    if (!d_all_offsets || !d_global_offsets || (!d_result && cap_total > 0))
+    if (!d_all_offsets || !d_global_offsets || (d_result && !d_points))
         return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null pointer");
     if (n_ranks == 0 || rank >= n_ranks) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "bad rank %u of %u", rank, n_ranks);
-    const uint32_t mine = fdf::shard_lo(total_frames, rank + 1, n_ranks) - fdf::shard_lo(total_frames, rank, n_ranks);
     uint32_t widest = 0;
     for (uint32_t r = 0; r < n_ranks; r++) {
         const uint32_t fr = fdf::shard_lo(total_frames, r + 1, n_ranks) - fdf::shard_lo(total_frames, r, n_ranks);
@@ -387,19 +337,10 @@ fdf_status fdf_detect_shard_finish(fdf_ctx *ctx, const uint64_t *d_all_offsets, 
     if (block < widest + 1) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "block %u < largest shard + 1 (%u)", block, widest + 1);
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_handle);
     FDF_CUDA(ctx, cudaSetDevice(ctx->device));
-    fdf::DetectParams p = ctx->shard_params;
-    if (p.n_frames != mine && !(p.n_frames == 0))
-        return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "rank %u owns %u of %u frames but began with %u", rank, mine,
-                    total_frames, p.n_frames);
-    p.out = reinterpret_cast<uint2 *>(d_result);
-    p.cap = cap_total;
-    p.all_offsets = reinterpret_cast<const unsigned long long *>(d_all_offsets);
-    p.global_offsets = reinterpret_cast<unsigned long long *>(d_global_offsets);
-    p.shard_block = block;
-    p.shard_ranks = n_ranks;
-    p.shard_rank = rank;
-    p.total_frames = total_frames;
-    FDF_CUDA(ctx, fdf::launch_gather(p, stream, ctx->info));
+    FDF_CUDA(ctx, fdf::launch_shard_push(reinterpret_cast<const unsigned long long *>(d_all_offsets), block, n_ranks, rank,
+                                         total_frames, reinterpret_cast<const uint2 *>(d_points),
+                                         reinterpret_cast<uint2 *>(d_result), cap_total,
+                                         reinterpret_cast<unsigned long long *>(d_global_offsets), ctx->info.sms, stream));
     ctx->launches += 1;
     return FDF_OK;
 }

@@ -660,25 +660,6 @@ __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const Detect
         }
     };
     fetch(blockIdx.x);
-    // sharded batch: where this rank's points start in the batch result, and (first CTA) the global CSR offsets
-    unsigned long long shard_base = 0ull;
-    if (p.all_offsets != nullptr) {
-        for (uint32_t r = 0; r < p.shard_rank; r++) {
-            const uint32_t fr = shard_lo(p.total_frames, r + 1u, p.shard_ranks) - shard_lo(p.total_frames, r, p.shard_ranks);
-            shard_base += p.all_offsets[(size_t)r * p.shard_block + fr];
-        }
-        if (blockIdx.x == 0) {
-            unsigned long long rb = 0ull;
-            for (uint32_t r = 0; r < p.shard_ranks; r++) {
-                const uint32_t lo = shard_lo(p.total_frames, r, p.shard_ranks);
-                const uint32_t fr = shard_lo(p.total_frames, r + 1u, p.shard_ranks) - lo;
-                const unsigned long long *blk = p.all_offsets + (size_t)r * p.shard_block;
-                for (uint32_t f = (uint32_t)tid; f < fr; f += kGatherThreads) p.global_offsets[lo + f] = rb + blk[f];
-                rb += blk[fr];
-            }
-            if (tid == 0) p.global_offsets[p.total_frames] = rb;
-        }
-    }
     // (row, column) of the first level-1 word of each round of this thread: fixed for the whole kernel
     const int row_first = (32 * tid) / WW, col_first = 32 * tid - row_first * WW;
     const int row_step = (32 * kGatherThreads) / WW, col_step = 32 * kGatherThreads - row_step * WW;
@@ -712,7 +693,7 @@ __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const Detect
             }
         }
         __syncthreads();
-        const unsigned long long o = s_rec.dst + shard_base;
+        const unsigned long long o = s_rec.dst;
         uint32_t block_off = 0u;
         int row0 = row_first, col0 = col_first;  // of level-1 word 32 * ts
         for (int t0 = 0; t0 < nsum; t0 += kGatherThreads) {  // (one round unless the image is wider than ~8000 pixels)
@@ -764,6 +745,46 @@ __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const Detect
                 row0++;
             }
         }
+    }
+}
+
+// ---- sharded batches: this rank's points -> their place in the batch result (possibly another GPU's memory) ------
+__global__ void __launch_bounds__(256) fdf_shard_push_kernel(const unsigned long long *all_offsets, uint32_t block,
+                                                            uint32_t n_ranks, uint32_t rank, uint32_t total_frames,
+                                                            const uint2 *points, uint2 *result,
+                                                            unsigned long long cap_total,
+                                                            unsigned long long *global_offsets) {
+    unsigned long long base = 0ull, mine = 0ull;
+    for (uint32_t r = 0; r <= rank; r++) {
+        const uint32_t fr = shard_lo(total_frames, r + 1u, n_ranks) - shard_lo(total_frames, r, n_ranks);
+        const unsigned long long tot = all_offsets[(size_t)r * block + fr];
+        if (r < rank) base += tot;
+        else mine = tot;
+    }
+    if (blockIdx.x == 0) {  // the batch's global CSR offsets: every rank's local offsets shifted by the lower ranks' totals
+        unsigned long long rb = 0ull;
+        for (uint32_t r = 0; r < n_ranks; r++) {
+            const uint32_t lo = shard_lo(total_frames, r, n_ranks);
+            const uint32_t fr = shard_lo(total_frames, r + 1u, n_ranks) - lo;
+            const unsigned long long *blk = all_offsets + (size_t)r * block;
+            for (uint32_t f = threadIdx.x; f < fr; f += blockDim.x) global_offsets[lo + f] = rb + blk[f];
+            rb += blk[fr];
+        }
+        if (threadIdx.x == 0) global_offsets[total_frames] = rb;
+    }
+    if (result == nullptr || result + base == points) return;  // (nothing to move: the points already sit in place)
+    if (base >= cap_total) return;
+    if (base + mine > cap_total) mine = cap_total - base;  // (the caller sees offsets[total] > cap)
+    uint2 *dst = result + base;
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(points)) & 15u) == 0u) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(points);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (unsigned long long i = i0; i < mine / 2ull; i += step) d4[i] = s4[i];
+        if ((mine & 1ull) && i0 == 0ull) dst[mine - 1ull] = points[mine - 1ull];
+    } else {
+        for (unsigned long long i = i0; i < mine; i += step) dst[i] = points[i];
     }
 }
 
@@ -930,8 +951,7 @@ cudaError_t launch_scan(const DetectParams &p, cudaStream_t stream) {
 
 cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream, DeviceInfo &info) {
     const unsigned long long items = (unsigned long long)p.n_frames * p.strips_per_frame;
-    // (a rank without frames still launches one CTA in a sharded call: it writes the batch's global offsets)
-    if ((items == 0 && p.all_offsets == nullptr) || items > 0x7fffffffull) return cudaErrorInvalidValue;
+    if (items == 0 || items > 0x7fffffffull) return cudaErrorInvalidValue;
     const size_t smem = gather_smem_bytes((int)p.mode, (int)p.sr, p.words_per_row);
     if (smem > kGatherSmemLimit) return cudaErrorInvalidValue;
     if (smem != info.gather_smem) {  // (occupancy depends on the image width only: looked up when the width changes)
@@ -944,8 +964,17 @@ cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream, DeviceInfo
     }
     unsigned long long grid = (unsigned long long)info.sms * (unsigned)info.gather_per_sm;
     if (grid > items) grid = items;
-    if (grid == 0) grid = 1;
     fdf_gather_kernel<<<(unsigned)grid, kGatherThreads, smem, stream>>>(p, (uint32_t)items);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_shard_push(const unsigned long long *all_offsets, uint32_t block, uint32_t n_ranks, uint32_t rank,
+                              uint32_t total_frames, const uint2 *points, uint2 *result, unsigned long long cap_total,
+                              unsigned long long *global_offsets, int sms, cudaStream_t stream) {
+    // a fraction of the SMs is enough to fill NVLink; the rest stays free for the next step's detection kernel
+    const unsigned grid = (unsigned)(sms > 0 ? (sms + 3) / 4 : 32);
+    fdf_shard_push_kernel<<<grid, 256, 0, stream>>>(all_offsets, block, n_ranks, rank, total_frames, points, result,
+                                                   cap_total, global_offsets);
     return cudaGetLastError();
 }
 

@@ -63,17 +63,10 @@ struct DetectParams {
     uint32_t *scan_ticket;            // tile tickets of the scan kernel (zeroed per launch)
     uint32_t *flags;                  // zeroed per launch; bit 0 look-back timeout, bit 1 TMA wait timeout,
                                       // bit 2 staging buffer overflow (entries dropped)
-    // Sharded batches (multi-GPU, one process per GPU; null / zero otherwise).  all_offsets holds every rank's LOCAL
-    // CSR offsets after the all-gather: rank r's block starts at r * shard_block and has frames(r) + 1 entries, where
-    // rank r owns frames [r * total / ranks, (r + 1) * total / ranks).  The gather kernel then writes this rank's
-    // points at out[(sum of the lower ranks' totals) + local position] -- `out` may be a peer-mapped buffer of
-    // another GPU -- and the batch's global CSR offsets to global_offsets[total_frames + 1].
-    const unsigned long long *all_offsets;
-    unsigned long long *global_offsets;
-    uint32_t shard_block, shard_ranks, shard_rank, total_frames;
 };
 
-// frames [lo, hi) of a batch of `total` frames owned by rank r of n (contiguous blocks; sharding.frame_shard)
+// Sharded batches (multi-GPU, one process per GPU): frames [lo, hi) of a batch of `total` frames owned by rank r of n
+// (contiguous blocks; sharding.frame_shard)
 __host__ __device__ inline uint32_t shard_lo(uint32_t total, uint32_t r, uint32_t n) {
     return (uint32_t)(((unsigned long long)r * total) / n);
 }
@@ -105,6 +98,14 @@ cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const Detec
 // runs into row-major points at their final position (through a bit plane of the strip in shared memory).
 cudaError_t launch_scan(const DetectParams &p, cudaStream_t stream);
 cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream, DeviceInfo &info);
+
+// Sharded batches, after the all-gather of the ranks' local CSR offsets (all_offsets: rank r's block starts at
+// r * block and has frames(r) + 1 entries): copies this rank's points[0 .. its total) to result[(sum of the lower ranks'
+// totals) + i] -- `result` may be another GPU's memory mapped over NVLink; the copy is coalesced, 16 bytes per thread --
+// and writes the batch's global CSR offsets (total_frames + 1 entries).
+cudaError_t launch_shard_push(const unsigned long long *all_offsets, uint32_t block, uint32_t n_ranks, uint32_t rank,
+                              uint32_t total_frames, const uint2 *points, uint2 *result, unsigned long long cap_total,
+                              unsigned long long *global_offsets, int sms, cudaStream_t stream);
 
 // RGB8 (interleaved, 3 bytes per pixel) -> luma8: kind 0 = the `image` crate's integer weights (main.rs:53-58),
 // kind 1 = (r + g + b) / 3 as util.rs:5-41 (`Rgb8ToLuma16View::to_grey`) does.

@@ -3,9 +3,9 @@
 The detection path has no cross-frame dependency (a frame is never split across GPUs), so the only
 exchange step is ONE all-gather of the ranks' local CSR offsets, from which every rank derives the
 global offsets of the batch result and each rank learns where its points start in it.
-The points themselves are not sent by a second collective: the emitting kernel of every rank writes them
-straight to their final position in rank 0's result buffer, which the other ranks map over NVLink (CUDA IPC,
-`fdf_shared_alloc` / `fdf_shared_open`).  `torch.distributed` is plumbing: NCCL on the GPUs (the all-gather,
+The points themselves are not sent by a second collective: one kernel per rank copies them to their final position in
+rank 0's result buffer, which the other ranks map over NVLink (CUDA IPC, `fdf_shared_alloc` / `fdf_shared_open`); the
+collective and that copy run on a second stream and overlap the detection of the next batch.  `torch.distributed` is plumbing: NCCL on the GPUs (the all-gather,
 the 64-byte handle broadcast, the closing barrier), gloo in the CPU tests of the index arithmetic.
 """
 from __future__ import annotations
@@ -74,14 +74,20 @@ class ShardedDetector:
     offsets into one batch result over NVLink").
 
     Every rank constructs it with the same arguments (collective).  Rank 0 owns the result buffer of `cap_total` points;
-    the other ranks map it.  `detect(local_frames, config)` enqueues, on torch's current stream:
-        detection + offset scan of the local frames   (2 launches, writes the local offsets into the all-gather buffer)
-        all_gather_into_tensor of the offset blocks    (1 NCCL launch: the exchange step)
-        ordered emission                               (1 launch: every rank's points land at their final position in
-                                                        rank 0's buffer; also writes the global CSR offsets)
+    the other ranks map it.  `detect(local_frames, config)` enqueues
+
+      on torch's current stream   detection, offset scan and ordered emission of the local frames into a local buffer
+                                  (the three launches of the single-GPU path: nothing of the exchange is on the
+                                  critical path of the next batch)
+      on the exchange stream      all_gather_into_tensor of the ranks' local offsets (the one collective), then ONE
+                                  kernel that copies the rank's points to their final position in rank 0's buffer over
+                                  NVLink (coalesced 16-byte stores) and writes the global CSR offsets.  (Rank 0's own
+                                  emission already lands in the result: it copies nothing.)
+
     and returns (points, global_offsets): `points` is the (cap_total, 2) int32 view of the result on rank 0 and None
-    elsewhere; global_offsets is an int64 (F + 1,) device tensor on every rank.  Call `fence()` (an all-reduce on the
-    same stream) before rank 0 reads points that other ranks wrote.
+    elsewhere; global_offsets is an int64 (F + 1,) device tensor on every rank.  Local buffers alternate between calls,
+    so the exchange of batch k overlaps the detection of batch k + 1.  `fence()` makes both valid for work enqueued
+    afterwards on the current stream (also the other ranks' points: it ends in an all-reduce).
     """
 
     def __init__(self, detector, n_frames: int, cap_total: int, cap_local: Optional[int] = None, group=None):
@@ -97,9 +103,16 @@ class ShardedDetector:
         self.device = torch.device("cuda", detector.device)
         lib, ctx = detector._lib, detector._ctx
         self._all = torch.zeros(self.world * self.block, dtype=torch.int64, device=self.device)
-        self._mine = torch.zeros(self.block, dtype=torch.int64, device=self.device)  # this rank's block (send buffer)
         self.global_offsets = torch.zeros(self.n_frames + 1, dtype=torch.int64, device=self.device)
         self._fence = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._xstream = torch.cuda.Stream(device=self.device)
+        self._turn = 0
+        # per buffer: the rank's block of the all-gather (its local offsets) and, except on rank 0, its local points
+        self._mine = [torch.zeros(self.block, dtype=torch.int64, device=self.device) for _ in range(2)]
+        self._local = [None, None]
+        if self.rank != 0:
+            self._local = [torch.empty((max(1, self.cap_local), 2), dtype=torch.int32, device=self.device) for _ in range(2)]
+        self._done = [None, None]  # exchange-stream events: buffer i may be written again
         # rank 0 allocates the result and broadcasts its IPC handle; the others map it (peer access over NVLink)
         handle = torch.zeros(64, dtype=torch.uint8, device=self.device)
         self._ptr = C.c_void_p()
@@ -124,36 +137,64 @@ class ShardedDetector:
         import torch
         import torch.distributed as dist
 
+        from .api import _raise
+
         det, lib = self.det, self.det._lib
         f, h, w = local_frames.shape
         if f != self.hi - self.lo:
             raise ValueError(f"rank {self.rank} owns frames [{self.lo}, {self.hi}) but got {f} frames")
-        s = torch.cuda.current_stream(self.device).cuda_stream
-        st = lib.fdf_detect_shard_begin(det._ctx, local_frames.data_ptr() if f else None, f, w, h,
-                                        local_frames.stride(1) if f else w, local_frames.stride(0) if f else w * h,
-                                        int(config.threshold), int(config.count), int(config.non_maximal_supression),
-                                        self.cap_local, self._mine.data_ptr(), s)
-        if st != 0:
-            from .api import _raise
-            _raise(lib, det._ctx, st)
-        dist.all_gather_into_tensor(self._all, self._mine, group=self.group)
-        st = lib.fdf_detect_shard_finish(det._ctx, self._all.data_ptr(), self.block, self.world, self.rank,
-                                         self.n_frames, self._ptr, self.cap_total, self.global_offsets.data_ptr(), s)
-        if st != 0:
-            from .api import _raise
-            _raise(lib, det._ctx, st)
+        i = self._turn
+        self._turn ^= 1
+        main = torch.cuda.current_stream(self.device)
+        if self._done[i] is not None:
+            main.wait_event(self._done[i])  # the exchange that last used buffer i (two batches ago) is over
+        mine = self._mine[i]
+        # rank 0 emits straight into the result (its points start at 0); the others into a local buffer
+        out_ptr = self._ptr.value if self.rank == 0 else self._local[i].data_ptr()
+        out_cap = self.cap_total if self.rank == 0 else self.cap_local
+        if f > 0:
+            st = lib.fdf_detect_device(det._ctx, local_frames.data_ptr(), f, w, h, local_frames.stride(1),
+                                       local_frames.stride(0), int(config.threshold), int(config.count),
+                                       int(config.non_maximal_supression), out_ptr, out_cap, mine.data_ptr(),
+                                       main.cuda_stream)
+            if st != 0:
+                _raise(lib, det._ctx, st)
+        else:
+            mine.zero_()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        xs = self._xstream
+        xs.wait_event(ready)
+        with torch.cuda.stream(xs):
+            dist.all_gather_into_tensor(self._all, mine, group=self.group)
+            st = lib.fdf_shard_push(det._ctx, self._all.data_ptr(), self.block, self.world, self.rank, self.n_frames,
+                                    None if self.rank == 0 else self._local[i].data_ptr(),
+                                    None if self.rank == 0 else self._ptr.value, self.cap_total,
+                                    self.global_offsets.data_ptr(), xs.cuda_stream)
+            if st != 0:
+                _raise(lib, det._ctx, st)
+            self._done[i] = torch.cuda.Event()
+            self._done[i].record(xs)
         return self.points, self.global_offsets
 
     def fence(self) -> None:
-        """Orders every rank's emission before whatever rank 0 enqueues next on this stream."""
+        """Orders every rank's exchange (offsets, points in rank 0's buffer) before whatever is enqueued next on the
+        current stream."""
+        import torch
         import torch.distributed as dist
 
+        main = torch.cuda.current_stream(self.device)
+        for ev in self._done:
+            if ev is not None:
+                main.wait_event(ev)
         dist.all_reduce(self._fence, group=self.group)
 
     def close(self) -> None:
+        import torch
         import torch.distributed as dist
 
         if getattr(self, "_ptr", None) is not None and self._ptr.value:
+            torch.cuda.synchronize(self.device)
             if self.rank != 0:
                 self.det._lib.fdf_shared_close(self.det._ctx, self._ptr)
             dist.barrier(group=self.group)  # nobody has the buffer mapped any more

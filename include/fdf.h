@@ -101,27 +101,24 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
  * contiguous blocks over n_ranks processes, one per GPU -- rank r owns frames [r*total/n, (r+1)*total/n) -- and the
  * path's only exchange step is one all-gather of the ranks' local CSR offsets (NCCL over NVLink; the caller's
  * communication library does it, this library has no networking code).  The reference has no counterpart: its
- * `detect` (lib.rs:62-64) handles one image on one thread.
+ * `detect` (lib.rs:62-64) handles one image on one thread.  Per rank and batch:
  *
- *   fdf_detect_shard_begin   detection + offset scan of this rank's frames; writes the n_frames + 1 LOCAL offsets to
- *                            d_local_offsets (typically this rank's block of the all-gather send/receive buffer).
- *                            cap_local sizes the rank's internal staging buffer (>= its keypoint count).
- *   <all-gather>             every rank's block of `block` >= (largest shard + 1) uint64 entries into
- *                            d_all_offsets[n_ranks * block].
- *   fdf_detect_shard_finish  ordered emission of this rank's points DIRECTLY at their place in the batch result:
- *                            d_result[(keypoints of all lower ranks) + local position].  d_result may be memory of
- *                            another GPU mapped with fdf_shared_open (rank 0's buffer: the result is then assembled
- *                            over NVLink by the emitting kernel itself, no extra copy); also writes the batch's global
- *                            CSR offsets (total_frames + 1 entries) to this rank's d_global_offsets.
- * All work is enqueued on `stream`.  A reader of d_result on another rank needs a later collective or barrier
- * on that stream before it looks at the points.
+ *   fdf_detect_device     the rank's frames -> d_points (LOCAL order and offsets) and the n_frames + 1 local offsets,
+ *                         written straight into the rank's block of the all-gather buffer.
+ *   <all-gather>          every rank's block of `block` >= (largest shard + 1) uint64 entries into
+ *                         d_all_offsets[n_ranks * block].
+ *   fdf_shard_push        one kernel: copies the rank's points to their place in the batch result,
+ *                         d_result[(keypoints of all lower ranks) + i] -- d_result is typically rank 0's buffer mapped
+ *                         with fdf_shared_open, so the batch result is assembled over NVLink with coalesced 16-byte
+ *                         stores and no host round trip (d_result == NULL: offsets only) -- and writes the batch's global
+ *                         CSR offsets (total_frames + 1 entries) to this rank's d_global_offsets.
+ * The all-gather and the push do not feed the next batch's detection, so a caller can put them on a second stream
+ * and overlap them with it (feature_detector_fast_b200.sharding.ShardedDetector does).  A reader of d_result on another
+ * rank needs a later collective or barrier on that stream before it looks at the points.
  */
-fdf_status fdf_detect_shard_begin(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_frames, uint32_t w, uint32_t h,
-                                  uint32_t pitch, uint64_t frame_stride, uint8_t threshold, uint8_t count, uint8_t nms,
-                                  size_t cap_local, uint64_t *d_local_offsets, void *stream);
-fdf_status fdf_detect_shard_finish(fdf_ctx *ctx, const uint64_t *d_all_offsets, uint32_t block, uint32_t n_ranks,
-                                   uint32_t rank, uint32_t total_frames, fdf_point *d_result, size_t cap_total,
-                                   uint64_t *d_global_offsets, void *stream);
+fdf_status fdf_shard_push(fdf_ctx *ctx, const uint64_t *d_all_offsets, uint32_t block, uint32_t n_ranks, uint32_t rank,
+                          uint32_t total_frames, const fdf_point *d_points, fdf_point *d_result, size_t cap_total,
+                          uint64_t *d_global_offsets, void *stream);
 
 /* Device memory that other processes on the same node can map (CUDA IPC): fdf_shared_alloc returns the pointer and a
  * 64-byte handle to send to the peers, fdf_shared_open maps a peer's allocation into this process (peer access over
