@@ -365,6 +365,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-by-config", action="store_true")
+    ap.add_argument("--strong-frames", type=int, default=FRAMES_PER_GPU,
+                    help="total frames of the strong-scaling batch (default: the 512 of config 5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
@@ -524,7 +526,7 @@ def main():
 
     # ---- strong scaling: the literal config 5, ONE 512-frame batch sharded over the N GPUs -----------------
     strong = None
-    strong_total = FRAMES_PER_GPU
+    strong_total = args.strong_frames
     if world == 1:
         if F == strong_total:
             strong = {"frames_total": strong_total, "frames_per_gpu": F, "value": round(mpix, 1), "unit": "Mpix/s",
@@ -537,8 +539,15 @@ def main():
         for _ in range(3):
             sds.detect(s_frames, cfg)
         sds.fence()
+        t_host = time.perf_counter()
+        for _ in range(s_steps):
+            sds.detect(s_frames, cfg)
+        host_us = (time.perf_counter() - t_host) / s_steps * 1e6  # host time to enqueue one step (the GPU lags behind)
+        sds.fence()
+        torch.cuda.synchronize()
         s_ms = timed_steps(lambda: sds.detect(s_frames, cfg), s_steps, fence=sds.fence)
         strong = {"frames_total": strong_total, "frames_per_gpu": fs, "unit": "Mpix/s", "steps": s_steps,
+                  "host_enqueue_us_per_step": round(host_us, 1),
                   "value": round(strong_total * W * H / (s_ms / s_steps * 1e-3) / 1e6, 1),
                   "ms_per_step": round(s_ms / s_steps, 4),
                   "note": "one 512-frame batch, looped; every step ends in one batch result on rank 0"}
@@ -612,7 +621,13 @@ def main():
         frame1080 = synth_frames_host(oracle, 1, 1920, 1080)[0]
         by_config["criterion"] = criterion_triple(
             lambda nms: len(det.detect_array(frame1080, fdf.Config(16, 9, fdf.NonMaximalSuppression(nms)))),
-            "fdf_detect through the C ABI, host buffers, copies included")
+            "fdf_detect through the C ABI, PAGEABLE host image (what image::GrayImage's Vec<u8> is), copies included")
+        pinned = torch.empty((1080, 1920), dtype=torch.uint8, pin_memory=True)
+        pinned.copy_(torch.from_numpy(frame1080))
+        pinned_np = pinned.numpy()
+        by_config["criterion_pinned_input"] = criterion_triple(
+            lambda nms: len(det.detect_array(pinned_np, fdf.Config(16, 9, fdf.NonMaximalSuppression(nms)))),
+            "fdf_detect through the C ABI, host image in PINNED memory (cudaHostRegister'ed by the caller), copies included")
 
     if rank == 0:
         line = {

@@ -109,15 +109,23 @@ class Detector:
         a = _as_gray(img)
         h, w = a.shape
         worst = max(0, w - 6) * max(0, h - 6)
-        cap = worst if cap is None else int(cap)
-        buf = self._scratch(max(cap, 1))
-        n = C.c_size_t(0)
-        st = self._lib.fdf_detect(self._ctx, a.ctypes.data, w, h, a.strides[0], int(config.threshold),
-                                  int(config.count), int(config.non_maximal_supression), buf.ctypes.data, cap,
-                                  C.byref(n))
-        if st != 0:
-            _raise(self._lib, self._ctx, st)
-        return buf[: n.value].copy()
+        # Without a caller's capacity: room for 1 keypoint in 16 pixels (real images have < 2 %), grown to the exact need
+        # and retried when the library reports FDF_ERR_CAPACITY (it returns the number found) -- the result is the same,
+        # the buffers are 16 times smaller than "every pixel a keypoint".
+        grow = cap is None
+        cap = min(worst, max(4096, worst // 16)) if cap is None else int(cap)
+        while True:
+            buf = self._scratch(max(cap, 1))
+            n = C.c_size_t(0)
+            st = self._lib.fdf_detect(self._ctx, a.ctypes.data, w, h, a.strides[0], int(config.threshold),
+                                      int(config.count), int(config.non_maximal_supression), buf.ctypes.data, cap,
+                                      C.byref(n))
+            if st == 4 and grow and n.value > cap:  # FDF_ERR_CAPACITY
+                cap = n.value
+                continue
+            if st != 0:
+                _raise(self._lib, self._ctx, st)
+            return buf[: n.value].copy()
 
     def detect_rgb8_array(self, rgb, config: Config, cap: Optional[int] = None) -> np.ndarray:
         """fdf_detect_rgb8 (main.rs:53-67: to_rgb8 -> to_luma8 -> detect) on an (H, W, 3) uint8 array."""

@@ -47,6 +47,11 @@ namespace fdf {
 cudaError_t read_trace(long long *out, size_t bytes);
 }
 #endif
+#ifdef FDF_CHECKS
+namespace fdf {
+cudaError_t read_check_failure(int *line);
+}
+#endif
 
 struct fdf_ctx {
     int device = 0;
@@ -63,6 +68,13 @@ struct fdf_ctx {
     DeviceBuffer<unsigned long long> staged_offsets;
     unsigned long long *pinned_offsets = nullptr;
     size_t pinned_offsets_count = 0;
+    // single-image path (fdf_detect): one device block [offsets u64 x 2 | flags | pad to 64 B | points], a pinned copy of
+    // its head for the one device->host copy of a call, and a pinned staging buffer for pageable input images
+    DeviceBuffer<uint8_t> single_block;
+    uint8_t *pinned_head = nullptr;
+    size_t pinned_head_bytes = 0;
+    uint8_t *pinned_in = nullptr;
+    size_t pinned_in_bytes = 0;
     uint64_t launches = 0;
     fdf::DeviceInfo info;        // SM count, kernel occupancies, experiment knobs: looked up once in fdf_create
     int force_sr = 0;            // FDF_FORCE_SR (experiments / tests): strip height override, read once in fdf_create
@@ -191,6 +203,9 @@ void fdf_destroy(fdf_ctx *ctx) {
     ctx->staged_points.release();
     ctx->staged_offsets.release();
     if (ctx->pinned_offsets) cudaFreeHost(ctx->pinned_offsets);
+    if (ctx->pinned_head) cudaFreeHost(ctx->pinned_head);
+    if (ctx->pinned_in) cudaFreeHost(ctx->pinned_in);
+    ctx->single_block.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -539,16 +554,92 @@ fdf_status fdf_detect_batch(fdf_ctx *ctx, const uint8_t *frames, uint32_t n_fram
     return FDF_OK;
 }
 
+namespace {
+constexpr size_t kSingleHead = 64;          // bytes in front of the points in the single-image device block
+constexpr size_t kSingleFirstPoints = 32768;  // points that come back with the first (usually only) device->host copy
+
+fdf_status reserve_pinned(fdf_ctx *ctx, uint8_t **buf, size_t *have, size_t need) {
+    if (*have >= need) return FDF_OK;
+    if (*buf) cudaFreeHost(*buf);
+    *buf = nullptr;
+    *have = 0;
+    FDF_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(buf), need));
+    *have = need;
+    return FDF_OK;
+}
+}  // namespace
+
+// One image, one call, as few host round trips as the problem allows: the image goes up with one asynchronous copy
+// when the caller's buffer is pinned (cudaHostRegister / cudaHostAlloc), otherwise in four slices through a pinned
+// staging buffer of the context (the host copy of slice k + 1 overlaps the DMA of slice k: a pageable cudaMemcpy would
+// do the same staging inside the driver, serially); the three kernels follow; offsets, flags and the first 32 K
+// points come back in ONE copy from one device block, then one synchronisation.  (fdf_detect_batch is the throughput
+// path; this is the latency path of lib.rs:62-64.)
 fdf_status fdf_detect(fdf_ctx *ctx, const uint8_t *img, uint32_t w, uint32_t h, uint32_t pitch, uint8_t threshold,
                       uint8_t count, uint8_t nms, fdf_point *out, size_t cap, size_t *n_out) {
     if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
     if (!n_out) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null n_out");
     *n_out = 0;
-    uint64_t offsets[2] = {0, 0};
-    fdf_status st = fdf_detect_batch(ctx, img, 1, w, h, pitch, (uint64_t)pitch * h, threshold, count, nms, out, cap,
-                                     offsets);
-    if (st == FDF_OK || st == FDF_ERR_CAPACITY) *n_out = (size_t)offsets[1];
-    return st;
+    fdf_status st = check_config(ctx, count, nms);
+    if (st != FDF_OK) return st;
+    if (!out && cap > 0) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null output pointer");
+    if (w < 7 || h < 7) return FDF_OK;  // nothing can be a keypoint
+    if (!img) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null image pointer");
+    if (pitch < w) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "pitch %u < width %u", pitch, w);
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    const uint32_t dpitch = (w + 15u) & ~15u;
+    const size_t worst = (size_t)(w - 6) * (size_t)(h - 6), dcap = cap < worst ? cap : worst;
+    const size_t first = dcap < kSingleFirstPoints ? dcap : kSingleFirstPoints;
+    FDF_CUDA(ctx, ctx->staged_frames.reserve((size_t)dpitch * h));
+    FDF_CUDA(ctx, ctx->single_block.reserve(kSingleHead + (dcap ? dcap : 1) * sizeof(fdf_point)));
+    if ((st = reserve_pinned(ctx, &ctx->pinned_head, &ctx->pinned_head_bytes, kSingleHead + kSingleFirstPoints * sizeof(fdf_point))) != FDF_OK)
+        return st;
+    uint8_t *block = ctx->single_block.ptr;
+    uint64_t *d_offsets = reinterpret_cast<uint64_t *>(block);
+    fdf_point *d_points = reinterpret_cast<fdf_point *>(block + kSingleHead);
+
+    // ---- the image ----
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, img) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // (an unregistered pointer is not an error here)
+    if (pinned) {
+        FDF_CUDA(ctx, cudaMemcpy2DAsync(ctx->staged_frames.ptr, dpitch, img, pitch, w, h, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        if ((st = reserve_pinned(ctx, &ctx->pinned_in, &ctx->pinned_in_bytes, (size_t)dpitch * h)) != FDF_OK) return st;
+        const uint32_t slices = h >= 64 ? 4u : 1u;
+        for (uint32_t k = 0; k < slices; k++) {
+            const uint32_t r0 = (uint32_t)((uint64_t)h * k / slices), r1 = (uint32_t)((uint64_t)h * (k + 1) / slices);
+            uint8_t *stage = ctx->pinned_in + (size_t)r0 * dpitch;
+            if (pitch == dpitch) {
+                memcpy(stage, img + (size_t)r0 * pitch, (size_t)(r1 - r0) * pitch);
+            } else {
+                for (uint32_t r = r0; r < r1; r++) memcpy(stage + (size_t)(r - r0) * dpitch, img + (size_t)r * pitch, w);
+            }
+            FDF_CUDA(ctx, cudaMemcpyAsync(ctx->staged_frames.ptr + (size_t)r0 * dpitch, stage, (size_t)(r1 - r0) * dpitch,
+                                          cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    // ---- the kernels ----
+    st = fdf_detect_device(ctx, ctx->staged_frames.ptr, 1, w, h, dpitch, (uint64_t)dpitch * h, threshold, count, nms,
+                           d_points, dcap, d_offsets, ctx->stream);
+    if (st != FDF_OK) return st;
+    // ---- offsets + flags + the first points: one copy, one synchronisation ----
+    FDF_CUDA(ctx, cudaMemcpyAsync(block + 16, ctx->workspace.ptr + 4, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    FDF_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_head, block, kSingleHead + first * sizeof(fdf_point), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    FDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint64_t found = reinterpret_cast<const uint64_t *>(ctx->pinned_head)[1];
+    const uint32_t flags = *reinterpret_cast<const uint32_t *>(ctx->pinned_head + 16);
+    *n_out = (size_t)found;
+    if (flags & ~4u) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x (look-back or pipeline wait timed out)", flags);
+    if (found > cap) return fail(ctx, FDF_ERR_CAPACITY, "%llu keypoints found, capacity %zu", (unsigned long long)found, cap);
+    if (flags) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x (staging buffer overflow)", flags);
+    const size_t n = (size_t)found;
+    memcpy(out, ctx->pinned_head + kSingleHead, (n < first ? n : first) * sizeof(fdf_point));
+    if (n > first)  // (rare: more than 32 K keypoints in one image)
+        FDF_CUDA(ctx, cudaMemcpy(out + first, d_points + first, (n - first) * sizeof(fdf_point), cudaMemcpyDeviceToHost));
+    return FDF_OK;
 }
 
 namespace {
@@ -626,6 +717,16 @@ fdf_status fdf_detect_rgb8(fdf_ctx *ctx, const uint8_t *rgb, uint32_t w, uint32_
     if (ncopy) FDF_CUDA(ctx, cudaMemcpy(out, ctx->staged_points.ptr, ncopy * sizeof(fdf_point), cudaMemcpyDeviceToHost));
     return FDF_OK;
 }
+
+#ifdef FDF_CHECKS
+// (checks builds only: tools/build_variant.sh checks -DFDF_CHECKS) source line of a failed shared-memory index check since the last call
+fdf_status fdf_debug_check_failure(fdf_ctx *ctx, int *line) {
+    if (!ctx || !line) return FDF_ERR_INVALID_ARGUMENT;
+    FDF_CUDA(ctx, cudaDeviceSynchronize());
+    FDF_CUDA(ctx, fdf::read_check_failure(line));
+    return FDF_OK;
+}
+#endif
 
 #ifdef FDF_TRACE
 // (debug builds only) the timeline table of the last launch: [cta 4][warp 16][chunk 200][slot 12] clock64 values

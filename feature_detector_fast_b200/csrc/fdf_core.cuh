@@ -37,6 +37,33 @@ using std::max;
 using std::min;
 #endif
 
+// Index checks of the shared-memory structures (compute-sanitizer is closed on the development pool, so the kernels
+// carry their own): FDF_BOUND(i, n) records the source line when i is outside [0, n).  Always active in the host
+// build (tests/host/strip_emulator.cpp runs every CPU-tier image through them); on the device only in -DFDF_CHECKS
+// builds (tools/checks_build.sh), where fdf_debug_check_failure() reads the line back (0 = clean).
+#if defined(__CUDACC__) && defined(FDF_CHECKS)
+__device__ int g_check_failure_line;
+#endif
+#if !defined(__CUDA_ARCH__)
+inline int &check_failure_line() {
+    static int line = 0;
+    return line;
+}
+#define FDF_BOUND(i, n)                                                                       \
+    do {                                                                                      \
+        if ((unsigned long long)(i) >= (unsigned long long)(n)) ::fdf::check_failure_line() = __LINE__; \
+    } while (0)
+#elif defined(FDF_CHECKS)
+#define FDF_BOUND(i, n)                                                                            \
+    do {                                                                                           \
+        if ((unsigned long long)(i) >= (unsigned long long)(n)) atomicMax(&::fdf::g_check_failure_line, __LINE__); \
+    } while (0)
+#else
+#define FDF_BOUND(i, n) \
+    do {                \
+    } while (0)
+#endif
+
 enum : int { NMS_OFF = 0, NMS_MAX_THRESHOLD = 1, NMS_SUM_ABSOLUTE = 2 };
 
 // Ring offsets (dx, dy), index 0 = north, clockwise, y down.  fast_simd.rs:79-98

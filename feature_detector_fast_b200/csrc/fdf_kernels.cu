@@ -850,6 +850,17 @@ __global__ void fdf_luma_kernel(const uint8_t *rgb, uint32_t n_frames, uint32_t 
     }
 }
 
+#ifdef FDF_CHECKS
+}  // namespace
+cudaError_t read_check_failure(int *line) {  // and resets it
+    cudaError_t e = cudaMemcpyFromSymbol(line, g_check_failure_line, sizeof(int));
+    if (e != cudaSuccess) return e;
+    const int zero = 0;
+    return cudaMemcpyToSymbol(g_check_failure_line, &zero, sizeof(zero));
+}
+namespace {
+#endif
+
 #ifdef FDF_TRACE
 }  // namespace
 cudaError_t read_trace(long long *out, size_t bytes) {  // and resets the CTA counter for the next launch

@@ -176,7 +176,10 @@ FDF_HD uint32_t phase_a_stage1(int warp, int lane_or_minus1, const uint8_t *tile
     for (int i = 0; i < BH; i++) {
         const bool mine = (need >> i) & 1u;
         const uint32_t b = __ballot_sync(0xffffffffu, mine);
-        if (mine) ent[n + (uint32_t)__popc(b & lt)] = (uint8_t)(e0 + (uint32_t)(i << 4));
+        if (mine) {
+            FDF_BOUND(n + (uint32_t)__popc(b & lt), kWarpQueueCap);
+            ent[n + (uint32_t)__popc(b & lt)] = (uint8_t)(e0 + (uint32_t)(i << 4));
+        }
         n += (uint32_t)__popc(b);
     }
 #else
@@ -188,7 +191,10 @@ FDF_HD uint32_t phase_a_stage1(int warp, int lane_or_minus1, const uint8_t *tile
     }
     for (int i = 0; i < BH; i++)
         for (int lane = 0; lane < 32; lane++)
-            if ((need[lane] >> i) & 1u) ent[n++] = (uint8_t)(((((lane >> 4) * BH) + i) << 4) | (lane & 15));
+            if ((need[lane] >> i) & 1u) {
+                FDF_BOUND(n, kWarpQueueCap);
+                ent[n++] = (uint8_t)(((((lane >> 4) * BH) + i) << 4) | (lane & 15));
+            }
 #endif
     return n;
 }
@@ -213,6 +219,7 @@ FDF_HD void push_candidates(int rr, int q, uint32_t m, uint16_t *queue, uint32_t
     while (m != 0u) {
         const uint32_t p = (uint32_t)highest_set_bit(m);
         m ^= 1u << p;
+        FDF_BOUND(out - queue, kQueueCap);
         *out++ = (uint16_t)(base + p);
     }
 }
@@ -239,30 +246,13 @@ FDF_HD void phase_a_stage2(int ftid, int nthreads, const uint8_t *tile, const ui
                 i -= cnt[u];
                 v = u + 1;
             }
+        FDF_BOUND(i, kWarpQueueCap);
         const uint32_t e = ents[v * kWarpQueueCap + (int)i];
         rr = v * RW + (int)(e >> 4);
         q = (int)(e & 15u);
+        FDF_BOUND(rr, SR);
+        FDF_BOUND((rr + 6) * kTileW + q * 16 + 15, tile_rows(SR) * kTileW);  // the group's south ring row is in the tile
     };
-#if defined(FDF_STAGE2_X2)
-    // two entries per thread and step: two independent dependency chains (loads, masks) and one queue reservation
-    for (uint32_t gidx = (uint32_t)ftid; gidx < total; gidx += 2u * (uint32_t)nthreads) {
-        const bool two = gidx + (uint32_t)nthreads < total;
-        int rr0, q0, rr1, q1;
-        locate(gidx, rr0, q0);
-        locate(two ? gidx + (uint32_t)nthreads : gidx, rr1, q1);
-        const uint32_t m0 = stage2_mask(rr0, q0, tile, vtab, kbias);
-        uint32_t m1 = stage2_mask(rr1, q1, tile, vtab, kbias);
-        if (!two) m1 = 0u;
-        const uint32_t c0 = (uint32_t)popc32(m0), c1 = (uint32_t)popc32(m1);
-        if (c0 + c1 != 0u) {
-            const uint32_t slot = atomic_add_u32(qcount, c0 + c1);
-            if (slot + c0 + c1 <= (uint32_t)kQueueCap) {
-                push_candidates(rr0, q0, m0, queue, slot);
-                push_candidates(rr1, q1, m1, queue, slot + c0);
-            }
-        }
-    }
-#else
     for (uint32_t gidx = (uint32_t)ftid; gidx < total; gidx += (uint32_t)nthreads) {
         int rr, q;
         locate(gidx, rr, q);
@@ -273,7 +263,6 @@ FDF_HD void phase_a_stage2(int ftid, int nthreads, const uint8_t *tile, const ui
             if (slot + c <= (uint32_t)kQueueCap) push_candidates(rr, q, m, queue, slot);
         }
     }
-#endif
 }
 
 // ---- phase B: exact segment test (+ score) per candidate (replaces fast_simd.rs:115-297, 623-749)
@@ -321,19 +310,31 @@ FDF_HD void phase_b_loop(int tid, int lane, int nthreads, uint32_t qn, const uin
         if (more) ent_next = queue[nb + (uint32_t)l < qn ? nb + (uint32_t)l : nb];  // (in flight during the arithmetic)
         const int rr = (int)(ent >> 9);
         const int j = (int)((ent >> 5) & 15u) * 16 + mask_bit_to_px((int)(ent & 31u));
+        FDF_BOUND(rr, SR);
+        FDF_BOUND(j - 3, kTileW - 6);  // the ring stays inside the tile row
         const KeypointTest r = test_pixel<MODE, NFIX>(tile + (rr + 3) * kTileW + j, t, n);
         const bool kp = valid && r.kp;
-        if (kp) plane[rr * kPlaneW + j - kPlaneLead] = (uint16_t)((tag << 12) | r.score);
+        if (kp) {
+            FDF_BOUND(rr * kPlaneW + j - kPlaneLead, SR * kPlaneW);
+            FDF_BOUND(j - kPlaneLead, kPlaneW);
+            plane[rr * kPlaneW + j - kPlaneLead] = (uint16_t)((tag << 12) | r.score);
+        }
 #if defined(__CUDA_ARCH__)
         const uint32_t b = __ballot_sync(0xffffffffu, kp);
         if (b != 0u) {
             uint32_t base = 0u;
             if (lane == 0) base = atomicAdd(kcount, (uint32_t)__popc(b));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (kp) klist[base + (uint32_t)__popc(b & ((1u << lane) - 1u))] = (uint16_t)((rr << 8) | j);
+            if (kp) {
+                FDF_BOUND(base + (uint32_t)__popc(b & ((1u << lane) - 1u)), kQueueCap);
+                klist[base + (uint32_t)__popc(b & ((1u << lane) - 1u))] = (uint16_t)((rr << 8) | j);
+            }
         }
 #else
-        if (kp) klist[(*kcount)++] = (uint16_t)((rr << 8) | j);
+        if (kp) {
+            FDF_BOUND(*kcount, kQueueCap);
+            klist[(*kcount)++] = (uint16_t)((rr << 8) | j);
+        }
 #endif
         if (!more) break;
         ib = nb;
@@ -361,6 +362,9 @@ FDF_HD void phase_b_dense(int twarp, int lane, int ntwarps, const uint8_t *tile,
     const int l0 = lane < 0 ? 0 : lane, lstep = lane < 0 ? 1 : 32;
     for (int rr = rows.lo + twarp; rr < rows.hi; rr += ntwarps)
         for (int j = cols.lo + l0; j < cols.hi; j += lstep) {
+            FDF_BOUND(rr, SR);
+            FDF_BOUND(j - 3, kTileW - 6);
+            FDF_BOUND(j - kPlaneLead, kPlaneW);
             const KeypointTest r = test_pixel<MODE, 0>(tile + (rr + 3) * kTileW + j, t, n);
             if (r.kp) plane[rr * kPlaneW + j - kPlaneLead] = (uint16_t)((tag << 12) | r.score);
         }
@@ -418,7 +422,12 @@ FDF_HD bool emit_list(int tid, int nthreads, uint32_t kn, const uint16_t *klist,
         const bool in = nms_emits<MODE, SR>(rr, j, g);
         bool keep = in;
         // (a keypoint that cannot be emitted is looked up at a harmless cell with a full neighbourhood)
-        if (MODE != NMS_OFF) keep = nms_is_max(plane + (in ? rr * kPlaneW + j - kPlaneLead : kPlaneW + 1)) && in;
+        if (MODE != NMS_OFF) {
+            const int cell = in ? rr * kPlaneW + j - kPlaneLead : kPlaneW + 1;
+            FDF_BOUND(cell - kPlaneW - 1, SR * kPlaneW);
+            FDF_BOUND(cell + kPlaneW + 1, SR * kPlaneW);
+            keep = nms_is_max(plane + cell) && in;
+        }
         if (keep) {
             const unsigned long long o = base + atomic_add_u32(scount, 1u);
             if (o < cap) staging[o] = staged_entry<MODE>(rr, j, g);
@@ -438,7 +447,11 @@ FDF_HD bool nms_dense(int tid, int nthreads, int pass, const uint16_t *plane, ui
         if (plane[i] < (tag << 12)) continue;
         const int rr = i / kPlaneW, j = i % kPlaneW + kPlaneLead;
         if (!nms_emits<MODE, SR>(rr, j, g)) continue;
-        if (MODE != NMS_OFF && !nms_is_max(plane + i)) continue;
+        if (MODE != NMS_OFF) {
+            FDF_BOUND(i - kPlaneW - 1, SR * kPlaneW);
+            FDF_BOUND(i + kPlaneW + 1, SR * kPlaneW);
+            if (!nms_is_max(plane + i)) continue;
+        }
         const uint32_t slot = atomic_add_u32(counter, 1u);
         if (pass == 1) {
             if (base + slot < cap) staging[base + slot] = staged_entry<MODE>(rr, j, g);

@@ -85,16 +85,17 @@ class ShardedDetector:
                                   emission already lands in the result: it copies nothing.)
 
     and returns (points, global_offsets): `points` is the (cap_total, 2) int32 view of the result on rank 0 and None
-    elsewhere; global_offsets is an int64 (F + 1,) device tensor on every rank.  Local buffers alternate between calls,
-    so the exchange of batch k overlaps the detection of batch k + 1.  `fence()` makes both valid for work enqueued
+    elsewhere; global_offsets is an int64 (F + 1,) device tensor on every rank.  Local buffers rotate between calls,
+    so the exchange of batch k overlaps the detection of the following batches.  `fence()` makes both valid for work enqueued
     afterwards on the current stream (also the other ranks' points: it ends in an all-reduce).
     """
 
-    def __init__(self, detector, n_frames: int, cap_total: int, cap_local: Optional[int] = None, group=None):
+    def __init__(self, detector, n_frames: int, cap_total: int, cap_local: Optional[int] = None, group=None,
+                 depth: int = 4):
         import torch
         import torch.distributed as dist
 
-        self.det, self.group = detector, group
+        self.det, self.group, self.depth = detector, group, max(2, int(depth))
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.n_frames, self.cap_total = int(n_frames), int(cap_total)
         self.lo, self.hi = frame_shard(self.n_frames, self.rank, self.world)
@@ -108,11 +109,14 @@ class ShardedDetector:
         self._xstream = torch.cuda.Stream(device=self.device)
         self._turn = 0
         # per buffer: the rank's block of the all-gather (its local offsets) and, except on rank 0, its local points
-        self._mine = [torch.zeros(self.block, dtype=torch.int64, device=self.device) for _ in range(2)]
-        self._local = [None, None]
+        # (`depth` of each: the all-gather is a collective, so the ranks' exchanges run in lock step; a few batches of
+        # slack keep a rank that is ahead from waiting for the slowest one)
+        self._mine = [torch.zeros(self.block, dtype=torch.int64, device=self.device) for _ in range(self.depth)]
+        self._local = [None] * self.depth
         if self.rank != 0:
-            self._local = [torch.empty((max(1, self.cap_local), 2), dtype=torch.int32, device=self.device) for _ in range(2)]
-        self._done = [None, None]  # exchange-stream events: buffer i may be written again
+            self._local = [torch.empty((max(1, self.cap_local), 2), dtype=torch.int32, device=self.device)
+                           for _ in range(self.depth)]
+        self._done = [None] * self.depth  # exchange-stream events: buffer i may be written again
         # rank 0 allocates the result and broadcasts its IPC handle; the others map it (peer access over NVLink)
         handle = torch.zeros(64, dtype=torch.uint8, device=self.device)
         self._ptr = C.c_void_p()
@@ -144,10 +148,10 @@ class ShardedDetector:
         if f != self.hi - self.lo:
             raise ValueError(f"rank {self.rank} owns frames [{self.lo}, {self.hi}) but got {f} frames")
         i = self._turn
-        self._turn ^= 1
+        self._turn = (i + 1) % self.depth
         main = torch.cuda.current_stream(self.device)
         if self._done[i] is not None:
-            main.wait_event(self._done[i])  # the exchange that last used buffer i (two batches ago) is over
+            main.wait_event(self._done[i])  # the exchange that last used buffer i (`depth` batches ago) is over
         mine = self._mine[i]
         # rank 0 emits straight into the result (its points start at 0); the others into a local buffer
         out_ptr = self._ptr.value if self.rank == 0 else self._local[i].data_ptr()

@@ -126,9 +126,13 @@ extern "C" {
 int64_t fdf_emulate_detect(const uint8_t *img, uint32_t w, uint32_t h, uint32_t pitch, uint8_t t, uint8_t n,
                            uint8_t nms, int sr, fdf_oracle_point *out, size_t cap, int *fallbacks) {
     uint2 *o = reinterpret_cast<uint2 *>(out);
+    fdf::check_failure_line() = 0;
     if (fallbacks) fallbacks[0] = fallbacks[1] = 0;  // chunks that took the dense path: [0] every-pixel test, [1] plane scan
-#define CASE(M, S) \
-    if (nms == M && sr == S) return emulate<M, S>(img, (int)w, (int)h, (int)pitch, t, n, o, cap, fallbacks);
+#define CASE(M, S)                                                                                     \
+    if (nms == M && sr == S) {                                                                         \
+        const int64_t k = emulate<M, S>(img, (int)w, (int)h, (int)pitch, t, n, o, cap, fallbacks);     \
+        return fdf::check_failure_line() != 0 ? -1000 - fdf::check_failure_line() : k; /* an index check failed */ \
+    }
     CASE(0, 32) CASE(0, 48) CASE(0, 64) CASE(1, 32) CASE(1, 48) CASE(1, 64) CASE(2, 32) CASE(2, 48) CASE(2, 64)
 #undef CASE
     return -1;

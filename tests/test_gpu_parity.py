@@ -128,6 +128,33 @@ def test_capacity_overflow_reports_needed_size(detector, oracle_mod):
     assert ei.value.status == 4
 
 
+def test_capacity_equal_to_the_exact_count_and_one_less(detector, oracle_mod):
+    """ADVICE r1 (staging overflow): the unordered staging area is sized from the caller's capacity, so the tightest
+    legal capacity (== the number of keypoints) is the case where a silent overflow would drop points.  It must give
+    the full list with no device flag; one less must be FDF_ERR_CAPACITY carrying the true count -- for sparse and
+    for dense (noise: dense path, hundreds of keypoints per chunk) content, every NMS mode."""
+    import feature_detector_fast_b200 as fdf
+
+    for kind, t in ((0, 16), (1, 3)):
+        frames = np.stack([oracle_mod.synth_frame(1296, 300, seed=31, frame=f, kind=kind, amp=5) for f in range(3)])
+        for nms in (0, 1, 2):
+            want = [oracle_mod.port_detect(frames[f], t, 9, nms) for f in range(3)]
+            k = sum(len(x) for x in want)
+            assert k > 50
+            pts, offs = detector.detect_batch(frames, _cfg(t, 9, nms), cap=k)
+            assert offs[-1] == k and detector.device_flags() == 0
+            for f in range(3):
+                assert same_points(pts[int(offs[f]):int(offs[f + 1])], want[f])
+            with pytest.raises(fdf.FdfError) as ei:
+                detector.detect_batch(frames, _cfg(t, 9, nms), cap=k - 1)
+            assert ei.value.status == 4 and str(k) in str(ei.value)
+            with pytest.raises(fdf.FdfError) as ei:
+                detector.detect_batch(frames, _cfg(t, 9, nms), cap=1)
+            assert ei.value.status == 4 and str(k) in str(ei.value)
+            one = detector.detect_array(frames[1], _cfg(t, 9, nms), cap=len(want[1]))
+            assert same_points(one, want[1])
+
+
 def test_batch_csr_output(detector, oracle_mod):
     frames = np.stack([oracle_mod.synth_frame(400, 130, seed=77, frame=f, kind=0, amp=5) for f in range(9)])
     for nms in (0, 1, 2):

@@ -38,7 +38,14 @@ def dev_async():
     det.detect_device(frames, cfg, points=pts, offsets=offs)
 
 
-print("fdf_detect (host buffers)          %.1f us" % timeit(lambda: det.detect_array(host, cfg)))
+print("fdf_detect (pageable host image)   %.1f us" % timeit(lambda: det.detect_array(host, cfg)))
+pinned = torch.empty((1080, 1920), dtype=torch.uint8, pin_memory=True)
+pinned.copy_(frames[0].cpu())
+pinned_np = pinned.numpy()
+print("fdf_detect (pinned host image)     %.1f us" % timeit(lambda: det.detect_array(pinned_np, cfg)))
+for nms in (0, 2):
+    c2 = fdf.Config(16, 9, fdf.NonMaximalSuppression(nms))
+    print("fdf_detect (pinned, nms %d)         %.1f us" % (nms, timeit(lambda: det.detect_array(pinned_np, c2))))
 print("fdf_detect_device + synchronize    %.1f us" % timeit(dev_sync))
 print("fdf_detect_device, back to back    %.1f us per call (enqueue-bound)" % timeit(dev_async))
 det.set_timing(8)
