@@ -199,12 +199,12 @@ FDF_HD Px16 load16(const uint8_t *p) {  // p 16-byte aligned                    
 }
 
 // Stage 2 (16-pixel groups that passed stage 1): both pairs.  cl / cr are the words left / right of the
-// centre row's 16 pixels; valid[k] has 0x80 in every byte that may be a centre at all (image border, chunk
-// halo).  Returns the candidate mask of the group: centre 4k + b  <->  bit 8b + 7 - k.
+// centre row's 16 pixels; `valid` is the group's mask of pixels that may be a centre at all (image border, chunk
+// halo), in the layout of the result.  Returns the candidate mask of the group: centre 4k + b  <->  bit 8b + 7 - k.
 // The east/west differences are computed once per pixel: H(x) = |p(x+3) - p(x)| is the east difference
 // of centre x and the west difference of centre x + 3.
 FDF_HD uint32_t candidate_mask16(const Px16 &c, const Px16 &n, const Px16 &s, uint32_t cl, uint32_t cr,
-                                 const uint32_t valid[4], uint32_t kbias) {
+                                 uint32_t valid, uint32_t kbias) {
     uint32_t h[5];  // h[k + 1] = H of word k, h[0] = H of the word left of the group
     h[0] = absdiff4(byte_perm(cl, c.w[0], 0x6543u), cl);
 #pragma unroll
@@ -217,14 +217,14 @@ FDF_HD uint32_t candidate_mask16(const Px16 &c, const Px16 &n, const Px16 &s, ui
     for (int k = 0; k < 4; k++) {
         const uint32_t a = absdiff4(n.w[k], c.w[k]) | absdiff4(s.w[k], c.w[k]);
         const uint32_t b = h[k + 1] | byte_perm(h[k], h[k + 1], 0x4321u);  // H(x) | H(x-3)
-        const uint32_t fb = (exceeds4(b, kbias)) & valid[k];
-        r[k] = exceeds4(a, kbias) & fb;  // only bit 7 of valid bytes survives
+        r[k] = exceeds4(a, kbias) & exceeds4(b, kbias) & 0x80808080u;  // only bit 7 of every byte is meaningful
     }
-    return mad32(r[0], 1u, r[1] >> 1) + mad32(r[2] >> 2, 1u, r[3] >> 3);
+    return (mad32(r[0], 1u, r[1] >> 1) + mad32(r[2] >> 2, 1u, r[3] >> 3)) & valid;
 }
 
-// candidate-mask bit -> pixel index inside the group
+// candidate-mask bit -> pixel index inside the group, and back
 FDF_HD int mask_bit_to_px(int p) { return 4 * (7 - (p & 7)) + (p >> 3); }
+FDF_HD int px_to_mask_bit(int px) { return 8 * (px & 3) + 7 - (px >> 2); }
 
 // ---- exact test + scores on 16 "dual" words (the form the detection kernel uses) ---------------------------
 //

@@ -398,7 +398,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         cur = atomicAdd(p.ticket, 1u);
         s_ticket[0] = cur;
     }
-    if (tid < 3 * kVtabWords) vtabs[tid] = valid_word<MODE>(W, vtab_chunk(tid / kVtabWords, NC), tid % kVtabWords);
+    if (tid < 3 * kVtabWords) vtabs[tid] = valid_group_mask<MODE>(W, vtab_chunk(tid / kVtabWords, NC), tid % kVtabWords);
     auto clear_plane = [&](int i0, int n) {  // by n threads, i0 = index of this one
         uint4 *pz = reinterpret_cast<uint4 *>(plane);
         for (int i = i0; i < L.plane_bytes / 16; i += n) pz[i] = make_uint4(0u, 0u, 0u, 0u);

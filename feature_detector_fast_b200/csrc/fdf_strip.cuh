@@ -59,10 +59,11 @@ FDF_HD ChunkGeo make_geo(int w, int h, int strip, int chunk, int sr) {
 
 // ---- which tile columns may hold a centre (fast_simd.rs:369-371, 559-562) ------------------------------
 // Scored columns of a chunk: its own columns plus the one-column score halo the 3x3 NMS needs, inside the
-// image's centre range [3, w-3).  The table has one word per 4 tile columns with 0x80 in every valid byte; it
-// depends on the chunk only through "first / middle / last chunk of the row", so the kernel builds the
-// three variants once (kVtabWords words each).
-constexpr int kVtabWords = kTileW / 4;
+// image's centre range [3, w-3).  The table has one word per 16-pixel group: the group's candidate mask
+// (candidate_mask16's bit layout) with every valid centre set -- 16 words, read with one conflict-free LDS by stage 2;
+// it depends on the chunk only through "first / middle / last chunk of the row", so the kernel builds the three
+// variants once (kVtabWords words each).
+constexpr int kVtabWords = kTileW / 16;
 
 // scored tile columns [lo, hi) of a chunk
 struct ColRange {
@@ -80,12 +81,12 @@ FDF_HD ColRange scored_cols(int w, int chunk) {
 }
 
 template <int MODE>
-FDF_HD uint32_t valid_word(int w, int chunk, int word) {
+FDF_HD uint32_t valid_group_mask(int w, int chunk, int q) {
     const ColRange cr = scored_cols<MODE>(w, chunk);
     uint32_t v = 0u;
-    for (int b = 0; b < 4; b++) {
-        const int j = 4 * word + b;
-        if (j >= cr.lo && j < cr.hi) v |= 0x80u << (8 * b);
+    for (int px = 0; px < 16; px++) {
+        const int j = 16 * q + px;
+        if (j >= cr.lo && j < cr.hi) v |= 1u << px_to_mask_bit(px);
     }
     return v;
 }
@@ -207,9 +208,7 @@ FDF_HD uint32_t stage2_mask(int rr, int q, const uint8_t *tile, const uint32_t *
     // only reaches centres the validity table excludes (tile columns 0..2 and 253..255)
     const uint32_t cl = *reinterpret_cast<const uint32_t *>(rowp - 4);
     const uint32_t cr = *reinterpret_cast<const uint32_t *>(rowp + 16);
-    const uint4 vv = *reinterpret_cast<const uint4 *>(vtab + 4 * q);
-    const uint32_t valid[4] = {vv.x, vv.y, vv.z, vv.w};
-    return candidate_mask16(load16(rowp), load16(rowp - 3 * kTileW), load16(rowp + 3 * kTileW), cl, cr, valid, kbias);
+    return candidate_mask16(load16(rowp), load16(rowp - 3 * kTileW), load16(rowp + 3 * kTileW), cl, cr, vtab[q], kbias);
 }
 
 // one queue entry per set bit of the group's candidate mask, at queue[slot ...]

@@ -37,7 +37,7 @@ int64_t emulate(const uint8_t *img, int w, int h, int pitch, int t, int n, uint2
     std::vector<uint8_t> ents((size_t)kFilterWarps * kWarpQueueCap);
     alignas(16) uint32_t vtab[3][kVtabWords];  // validity tables: first / middle / last chunk of a row
     for (int v = 0; v < 3; v++)
-        for (int i = 0; i < kVtabWords; i++) vtab[v][i] = valid_word<MODE>(w, vtab_chunk(v, NC), i);
+        for (int i = 0; i < kVtabWords; i++) vtab[v][i] = valid_group_mask<MODE>(w, vtab_chunk(v, NC), i);
     std::vector<uint32_t> bits((size_t)OUT_R * WW), staged;
     const uint32_t kbias = filter_kbias((uint32_t)t);
     unsigned long long total = 0;
@@ -225,7 +225,7 @@ int64_t fdf_core_check(uint64_t iterations, uint64_t seed) {
                 uint32_t cl, cr;
                 memcpy(&cl, &rows[1][0], 4);
                 memcpy(&cr, &rows[1][20], 4);
-                const uint32_t all[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
+                const uint32_t all = 0xf0f0f0f0u;
                 const uint32_t kb = filter_kbias((uint32_t)t);
                 if (vertical_any(pc, pn, ps, kb) == 0u) bad++;
                 const uint32_t m = candidate_mask16(pc, pn, ps, cl, cr, all, kb);
