@@ -328,11 +328,12 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     }
     FDF_CUDA(ctx, fdf::launch_detect((int)p.mode, (int)p.sr, tmap, p, stream, ctx->info));
     if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[1], stream));
-    FDF_CUDA(ctx, fdf::launch_scan(p, stream));
+    const bool own_scan = fdf::gather_scans_itself(p);  // (one image or a handful: one launch less)
+    if (!own_scan) FDF_CUDA(ctx, fdf::launch_scan(p, stream));
     if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[2], stream));
     FDF_CUDA(ctx, fdf::launch_gather(p, stream, ctx->info));
     if (ev) FDF_CUDA(ctx, cudaEventRecord(ev[3], stream));
-    ctx->launches += 3;  // detection, scan, gather
+    ctx->launches += own_scan ? 2 : 3;  // detection, scan, gather
     return FDF_OK;
 }
 

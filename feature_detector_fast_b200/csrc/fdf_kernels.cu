@@ -629,9 +629,13 @@ struct StripRecord {
     uint32_t total;
 };
 
-__global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const DetectParams p, uint32_t n_items) {
+// own_scan != 0 (n_items <= kGatherThreads: one image or a handful): there was no scan launch; every CTA scans the
+// strip counts itself (one per thread) and CTA 0 writes the CSR frame offsets -- one launch less on the latency path.
+__global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const DetectParams p, uint32_t n_items,
+                                                                    uint32_t own_scan) {
     extern __shared__ __align__(16) uint32_t gsm[];
     __shared__ uint32_t warp_sums[kGatherThreads / 32];
+    __shared__ uint32_t s_item_dst[kGatherThreads];
     __shared__ unsigned long long s_run_base[kGatherMaxChunks];
     __shared__ uint32_t s_run_count[kGatherMaxChunks];
     __shared__ StripRecord s_rec;
@@ -656,9 +660,31 @@ __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const Detect
             r_base = r_count != 0u ? p.run_base[slot] : 0ull;
         } else if (tid == NC) {
             r_count = p.item_count[item];
-            r_base = p.item_dst[item];
+            r_base = own_scan ? (unsigned long long)s_item_dst[item] : p.item_dst[item];
         }
     };
+    if (own_scan) {
+        const uint32_t v = (uint32_t)tid < n_items ? p.item_count[tid] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0u;
+#pragma unroll
+        for (int w2 = 0; w2 < kGatherThreads / 32; w2++)
+            if (w2 < warp) before += warp_sums[w2];
+        const uint32_t excl = before + incl - v;
+        s_item_dst[tid] = excl;
+        if (blockIdx.x == 0 && (uint32_t)tid < n_items) {
+            if ((uint32_t)tid % p.strips_per_frame == 0u) p.offsets[(uint32_t)tid / p.strips_per_frame] = excl;
+            if ((uint32_t)tid == n_items - 1u) p.offsets[p.n_frames] = (unsigned long long)excl + v;
+        }
+        __syncthreads();  // (also: warp_sums is free again)
+    }
     fetch(blockIdx.x);
     // (row, column) of the first level-1 word of each round of this thread: fixed for the whole kernel
     const int row_first = (32 * tid) / WW, col_first = 32 * tid - row_first * WW;
@@ -952,6 +978,10 @@ cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const Detec
     return cudaErrorInvalidValue;
 }
 
+bool gather_scans_itself(const DetectParams &p) {
+    return (unsigned long long)p.n_frames * p.strips_per_frame <= (unsigned long long)kGatherThreads;
+}
+
 cudaError_t launch_scan(const DetectParams &p, cudaStream_t stream) {
     const unsigned long long items = (unsigned long long)p.n_frames * p.strips_per_frame;
     if (items == 0 || items > 0x7fffffffull) return cudaErrorInvalidValue;
@@ -975,7 +1005,8 @@ cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream, DeviceInfo
     }
     unsigned long long grid = (unsigned long long)info.sms * (unsigned)info.gather_per_sm;
     if (grid > items) grid = items;
-    fdf_gather_kernel<<<(unsigned)grid, kGatherThreads, smem, stream>>>(p, (uint32_t)items);
+    fdf_gather_kernel<<<(unsigned)grid, kGatherThreads, smem, stream>>>(p, (uint32_t)items,
+                                                                        gather_scans_itself(p) ? 1u : 0u);
     return cudaGetLastError();
 }
 

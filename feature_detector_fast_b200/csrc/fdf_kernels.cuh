@@ -87,6 +87,7 @@ cudaError_t init_device_info(DeviceInfo &info);  // (on the current device)
 
 size_t detect_smem_bytes(int mode, int sr);
 size_t gather_smem_bytes(int mode, int sr, uint32_t words_per_row);
+bool gather_scans_itself(const DetectParams &p);  // few strips: no scan launch, the gather kernel scans the counts
 
 // Enqueues the detection kernel for (mode, sr) on `stream`.  tmap describes the frames as a 3-D
 // u8 tensor (x, y, frame) with box (kTileW, tile_rows(sr), 1).

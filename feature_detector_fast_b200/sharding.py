@@ -95,8 +95,17 @@ class ShardedDetector:
         import torch
         import torch.distributed as dist
 
-        self.det, self.group, self.depth = detector, group, max(2, int(depth))
+        self.det, self.depth = detector, max(2, int(depth))
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        # The per-batch all-gather gets a communicator of its own on a HIGH-PRIORITY stream: the detection kernel is
+        # persistent and fills every SM, so a normal-priority NCCL kernel that becomes ready a few microseconds after
+        # the next batch's detection was launched waits for that whole launch.  With priority its (few) CTAs are
+        # placed first whenever CTA slots free up.  Same for the exchange stream the push kernel runs on.
+        if dist.get_backend(group) == "nccl":
+            ranks = dist.get_process_group_ranks(group if group is not None else dist.group.WORLD)
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            group = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+        self.group = group
         self.n_frames, self.cap_total = int(n_frames), int(cap_total)
         self.lo, self.hi = frame_shard(self.n_frames, self.rank, self.world)
         self.cap_local = int(cap_local) if cap_local is not None else self.cap_total
@@ -106,7 +115,7 @@ class ShardedDetector:
         self._all = torch.zeros(self.world * self.block, dtype=torch.int64, device=self.device)
         self.global_offsets = torch.zeros(self.n_frames + 1, dtype=torch.int64, device=self.device)
         self._fence = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self._xstream = torch.cuda.Stream(device=self.device)
+        self._xstream = torch.cuda.Stream(device=self.device, priority=-1)
         self._turn = 0
         # per buffer: the rank's block of the all-gather (its local offsets) and, except on rank 0, its local points
         # (`depth` of each: the all-gather is a collective, so the ranks' exchanges run in lock step; a few batches of

@@ -46,6 +46,10 @@ print("fdf_detect (pinned host image)     %.1f us" % timeit(lambda: det.detect_a
 for nms in (0, 2):
     c2 = fdf.Config(16, 9, fdf.NonMaximalSuppression(nms))
     print("fdf_detect (pinned, nms %d)         %.1f us" % (nms, timeit(lambda: det.detect_array(pinned_np, c2))))
+for sr in (64, 48, 32):
+    det.set_tuning(strip_rows=sr)
+    print("fdf_detect (pinned, strip rows %d)  %.1f us" % (sr, timeit(lambda: det.detect_array(pinned_np, cfg))))
+det.set_tuning()
 print("fdf_detect_device + synchronize    %.1f us" % timeit(dev_sync))
 print("fdf_detect_device, back to back    %.1f us per call (enqueue-bound)" % timeit(dev_async))
 det.set_timing(8)
