@@ -150,17 +150,24 @@ class Detector:
         if frames.dtype != np.uint8 or frames.ndim != 3 or not frames.flags.c_contiguous:
             raise TypeError("frames must be a C-contiguous (F, H, W) uint8 array")
         f, h, w = frames.shape
+        worst = f * max(0, w - 6) * max(0, h - 6)
+        # as in detect_array: without a caller's capacity start at 1 keypoint per 16 pixels and grow on FDF_ERR_CAPACITY
+        grow = cap is None and out is None
         if cap is None:
-            cap = f * max(0, w - 6) * max(0, h - 6) if out is None else len(out)
-        buf = out if out is not None else self._scratch(max(cap, 1))
+            cap = min(worst, max(4096, worst // 16)) if out is None else len(out)
         offsets = np.zeros(f + 1, np.uint64)
-        st = self._lib.fdf_detect_batch(self._ctx, frames.ctypes.data, f, w, h, w, w * h, int(config.threshold),
-                                        int(config.count), int(config.non_maximal_supression), buf.ctypes.data,
-                                        int(cap), offsets.ctypes.data)
-        if st != 0:
-            _raise(self._lib, self._ctx, st)
-        k = int(offsets[f])
-        return (buf[:k] if out is not None else buf[:k].copy()), offsets
+        while True:
+            buf = out if out is not None else self._scratch(max(cap, 1))
+            st = self._lib.fdf_detect_batch(self._ctx, frames.ctypes.data, f, w, h, w, w * h, int(config.threshold),
+                                            int(config.count), int(config.non_maximal_supression), buf.ctypes.data,
+                                            int(cap), offsets.ctypes.data)
+            if st == 4 and grow and int(offsets[f]) > cap:  # FDF_ERR_CAPACITY: offsets[F] is the number found
+                cap = int(offsets[f])
+                continue
+            if st != 0:
+                _raise(self._lib, self._ctx, st)
+            k = int(offsets[f])
+            return (buf[:k] if out is not None else buf[:k].copy()), offsets
 
     def detect_batch_pinned(self, frames_ptr: int, n_frames: int, w: int, h: int, config: Config, out_ptr: int,
                             cap: int, offsets_ptr: int) -> None:
