@@ -101,10 +101,12 @@ class ShardedDetector:
         # persistent and fills every SM, so a normal-priority NCCL kernel that becomes ready a few microseconds after
         # the next batch's detection was launched waits for that whole launch.  With priority its (few) CTAs are
         # placed first whenever CTA slots free up.  Same for the exchange stream the push kernel runs on.
+        self._own_group = False
         if dist.get_backend(group) == "nccl":
             ranks = dist.get_process_group_ranks(group if group is not None else dist.group.WORLD)
             opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
             group = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+            self._own_group = True
         self.group = group
         self.n_frames, self.cap_total = int(n_frames), int(cap_total)
         self.lo, self.hi = frame_shard(self.n_frames, self.rank, self.world)
@@ -215,6 +217,9 @@ class ShardedDetector:
                 self.points = None
                 self.det._lib.fdf_shared_close(self.det._ctx, self._ptr)
             self._ptr = C.c_void_p()
+            if self._own_group:
+                dist.destroy_process_group(self.group)
+                self._own_group = False
 
 
 class _RawCudaBuffer:

@@ -468,3 +468,47 @@ def test_randomised_shapes_contents_and_configs(detector, oracle_mod):
         if case % 10 == 0:
             assert same_points(got, oracle_mod.detect(img, t, n, nms)), (case, w, h, style, t, n, nms)
     assert detector.device_flags() == 0
+
+
+def test_shard_push_assembles_the_batch_result_on_one_gpu(detector, oracle_mod):
+    """The multi-GPU exchange step (fdf_shard_push, include/fdf.h) with the ranks simulated on ONE GPU: the batch is cut
+    into sharding.frame_shard blocks (uneven, and one rank without frames), every "rank" detects its block into a local
+    buffer with local offsets, the blocks are laid out as the all-gather would, and every rank's push writes into the
+    same result buffer.  The assembled points and global offsets must equal one detection of the whole batch.
+    (tests/test_multi_gpu.py does the same with real ranks, NCCL and peer memory when two GPUs are visible.)"""
+    import ctypes as C
+
+    import torch
+
+    import feature_detector_fast_b200 as fdf
+    from feature_detector_fast_b200 import sharding
+
+    lib, ctx = detector._lib, detector._ctx
+    for n_frames, world in ((7, 3), (2, 3), (5, 1)):
+        frames = detector.synth_frames(n_frames, 656, 210, seed=91, kind=0)
+        for nms in (0, 1):
+            cfg = _cfg(18, 9, nms)
+            want_pts, want_offs = detector.detect_device(frames, cfg)
+            torch.cuda.synchronize()
+            total = int(want_offs[-1])
+            block = sharding.shard_block(n_frames, world)
+            all_offs = torch.zeros(world * block, dtype=torch.int64, device="cuda")
+            local = []
+            for r in range(world):
+                lo, hi = sharding.frame_shard(n_frames, r, world)
+                pts = torch.zeros((max(1, total), 2), dtype=torch.int32, device="cuda")
+                if hi > lo:
+                    _, offs = detector.detect_device(frames[lo:hi], cfg, points=pts,
+                                                     offsets=all_offs[r * block: r * block + hi - lo + 1])
+                local.append(pts)
+            result = torch.full((total + 3, 2), -1, dtype=torch.int32, device="cuda")
+            for r in range(world):
+                goffs = torch.zeros(n_frames + 1, dtype=torch.int64, device="cuda")
+                st = lib.fdf_shard_push(ctx, all_offs.data_ptr(), block, world, r, n_frames, local[r].data_ptr(),
+                                        result.data_ptr(), total, goffs.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream)
+                assert st == 0, lib.fdf_last_error(ctx)
+                torch.cuda.synchronize()
+                assert torch.equal(goffs, want_offs), (n_frames, world, r)
+            assert torch.equal(result[:total], want_pts[:total]), (n_frames, world, nms)
+            assert bool((result[total:] == -1).all())  # nothing written past the batch
