@@ -75,6 +75,19 @@ struct fdf_ctx {
     size_t pinned_head_bytes = 0;
     uint8_t *pinned_in = nullptr;
     size_t pinned_in_bytes = 0;
+    uint32_t *flags_copy_next = nullptr;  // fdf_detect -> fdf_detect_device: where the next launch copies its flags
+    size_t single_hint = 0;               // keypoints of the previous fdf_detect call (sizes the first copy back)
+    // the tensor map of the previous launch (cuTensorMapEncodeTiled costs a microsecond or two per call)
+    struct TmapKey {
+        const void *base = nullptr;
+        uint32_t w = 0, h = 0, n = 0, pitch = 0;
+        uint64_t stride = 0;
+        int sr = 0;
+        bool operator==(const TmapKey &o) const {
+            return base == o.base && w == o.w && h == o.h && n == o.n && pitch == o.pitch && stride == o.stride && sr == o.sr;
+        }
+    } tmap_key;
+    CUtensorMap tmap_cached;
     uint64_t launches = 0;
     fdf::DeviceInfo info;        // SM count, kernel occupancies, experiment knobs: looked up once in fdf_create
     int force_sr = 0;            // FDF_FORCE_SR (experiments / tests): strip height override, read once in fdf_create
@@ -290,10 +303,18 @@ fdf_status prepare_detect(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_fram
     const cuuint64_t strides[2] = {pitch, frame_stride};
     const cuuint32_t box[3] = {(cuuint32_t)fdf::kTileW, (cuuint32_t)fdf::tile_rows(sr), 1u};
     const cuuint32_t elem_strides[3] = {1u, 1u, 1u};
+    fdf_ctx::TmapKey key;
+    key.base = d_frames, key.w = w, key.h = h, key.n = n_frames, key.pitch = pitch, key.stride = frame_stride, key.sr = sr;
+    if (key == ctx->tmap_key) {
+        tmap = ctx->tmap_cached;
+        return FDF_OK;
+    }
     CUresult cr = ctx->encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(d_frames), dims, strides,
                               box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(ctx, FDF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+    ctx->tmap_key = key;
+    ctx->tmap_cached = tmap;
     return FDF_OK;
 }
 }  // namespace
@@ -313,12 +334,16 @@ fdf_status fdf_detect_device(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_f
     st = prepare_detect(ctx, d_frames, n_frames, w, h, pitch, frame_stride, threshold, count, nms, cap, stream, p, tmap,
                         &empty);
     if (st != FDF_OK) return st;
+    uint32_t *flags_copy = ctx->flags_copy_next;
+    ctx->flags_copy_next = nullptr;
     if (empty) {
         FDF_CUDA(ctx, cudaMemsetAsync(d_offsets, 0, ((size_t)n_frames + 1) * sizeof(uint64_t), stream));
+        if (flags_copy) FDF_CUDA(ctx, cudaMemsetAsync(flags_copy, 0, sizeof(uint32_t), stream));
         return FDF_OK;
     }
     p.out = reinterpret_cast<uint2 *>(d_out);
     p.offsets = reinterpret_cast<unsigned long long *>(d_offsets);
+    p.flags_copy = flags_copy;
 
     cudaEvent_t *ev = nullptr;
     if (!ctx->timing_events.empty()) {
@@ -591,7 +616,11 @@ fdf_status fdf_detect(fdf_ctx *ctx, const uint8_t *img, uint32_t w, uint32_t h, 
 
     const uint32_t dpitch = (w + 15u) & ~15u;
     const size_t worst = (size_t)(w - 6) * (size_t)(h - 6), dcap = cap < worst ? cap : worst;
-    const size_t first = dcap < kSingleFirstPoints ? dcap : kSingleFirstPoints;
+    // points that come back with the first (usually only) copy: 1.5 x the previous call's count + 1024, at least 4096
+    size_t first = ctx->single_hint + ctx->single_hint / 2 + 1024;
+    if (first < 4096) first = 4096;
+    if (first > kSingleFirstPoints) first = kSingleFirstPoints;
+    if (first > dcap) first = dcap;
     FDF_CUDA(ctx, ctx->staged_frames.reserve((size_t)dpitch * h));
     FDF_CUDA(ctx, ctx->single_block.reserve(kSingleHead + (dcap ? dcap : 1) * sizeof(fdf_point)));
     if ((st = reserve_pinned(ctx, &ctx->pinned_head, &ctx->pinned_head_bytes, kSingleHead + kSingleFirstPoints * sizeof(fdf_point))) != FDF_OK)
@@ -622,17 +651,19 @@ fdf_status fdf_detect(fdf_ctx *ctx, const uint8_t *img, uint32_t w, uint32_t h, 
         }
     }
     // ---- the kernels ----
+    ctx->flags_copy_next = reinterpret_cast<uint32_t *>(block + 16);  // (the gather kernel puts the launch's flags there)
     st = fdf_detect_device(ctx, ctx->staged_frames.ptr, 1, w, h, dpitch, (uint64_t)dpitch * h, threshold, count, nms,
                            d_points, dcap, d_offsets, ctx->stream);
+    ctx->flags_copy_next = nullptr;
     if (st != FDF_OK) return st;
     // ---- offsets + flags + the first points: one copy, one synchronisation ----
-    FDF_CUDA(ctx, cudaMemcpyAsync(block + 16, ctx->workspace.ptr + 4, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     FDF_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_head, block, kSingleHead + first * sizeof(fdf_point), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     FDF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const uint64_t found = reinterpret_cast<const uint64_t *>(ctx->pinned_head)[1];
     const uint32_t flags = *reinterpret_cast<const uint32_t *>(ctx->pinned_head + 16);
     *n_out = (size_t)found;
+    ctx->single_hint = (size_t)found;
     if (flags & ~4u) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x (look-back or pipeline wait timed out)", flags);
     if (found > cap) return fail(ctx, FDF_ERR_CAPACITY, "%llu keypoints found, capacity %zu", (unsigned long long)found, cap);
     if (flags) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x (staging buffer overflow)", flags);

@@ -646,6 +646,8 @@ __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const Detect
     const int nsum = (nwords + 31) / 32;  // level-2 words
     uint32_t *bits = gsm, *summary = gsm + nsum * 32;
     for (int i = tid; i < nsum * 33; i += kGatherThreads) gsm[i] = 0u;
+    // (the detection kernel is complete: its flags are final, and this kernel only repeats bit 2 where that one set it)
+    if (blockIdx.x == 0 && tid == 0 && p.flags_copy != nullptr) *p.flags_copy = *p.flags;
 
     // records of a strip: thread c < NC holds chunk c's run, thread NC the strip's total and destination
     unsigned long long r_base = 0ull;

@@ -61,6 +61,8 @@ struct DetectParams {
     unsigned long long *scan_status;  // look-back words of the scan kernel's tiles (zeroed per launch)
     uint32_t *ticket;                 // strip tickets of the detection kernel (zeroed per launch)
     uint32_t *scan_ticket;            // tile tickets of the scan kernel (zeroed per launch)
+    uint32_t *flags_copy;             // optional: the gather kernel copies *flags here (single-image path: the flags
+                                      // then come home with the offsets and points in one copy)
     uint32_t *flags;                  // zeroed per launch; bit 0 look-back timeout, bit 1 TMA wait timeout,
                                       // bit 2 staging buffer overflow (entries dropped)
 };
