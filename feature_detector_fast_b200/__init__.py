@@ -14,6 +14,7 @@ from .api import (  # noqa: F401
     FdfError,
     FdfPanic,
     NonMaximalSuppression,
+    Pipe,
     Point,
     default_detector,
     detect,
@@ -27,6 +28,7 @@ __all__ = [
     "FdfError",
     "FdfPanic",
     "NonMaximalSuppression",
+    "Pipe",
     "Point",
     "default_detector",
     "detect",

@@ -65,6 +65,17 @@ def load_library() -> C.CDLL:
         lib.fdf_shared_open.argtypes = [vp, vp, C.POINTER(vp)]
         lib.fdf_shared_close.restype = C.c_int
         lib.fdf_shared_close.argtypes = [vp, vp]
+    if hasattr(lib, "fdf_pipe_create"):
+        lib.fdf_pipe_create.restype = C.c_int
+        lib.fdf_pipe_create.argtypes = [vp, u32, u32, u32, sz, C.POINTER(vp)]
+        lib.fdf_pipe_destroy.restype = None
+        lib.fdf_pipe_destroy.argtypes = [vp]
+        lib.fdf_pipe_submit.restype = C.c_int
+        lib.fdf_pipe_submit.argtypes = [vp, vp, u32, u32, u32, u8, u8, u8]
+        lib.fdf_pipe_collect.restype = C.c_int
+        lib.fdf_pipe_collect.argtypes = [vp, vp, sz, C.POINTER(sz)]
+        lib.fdf_pipe_in_flight.restype = u32
+        lib.fdf_pipe_in_flight.argtypes = [vp]
     lib.fdf_rgb8_to_luma8_device.restype = C.c_int
     lib.fdf_rgb8_to_luma8_device.argtypes = [vp, vp, u32, u32, u32, u32, u64, vp, u32, u64, vp]
     lib.fdf_rgb8_to_grey_sum3_device.restype = C.c_int

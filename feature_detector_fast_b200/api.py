@@ -258,6 +258,10 @@ class Detector:
             _raise(self._lib, self._ctx, st)
         return float(ms[0]), float(ms[1]), float(ms[2])
 
+    def pipe(self, depth: int, max_w: int, max_h: int, cap: Optional[int] = None) -> "Pipe":
+        """fdf_pipe_create: a streaming detector with up to `depth` images of at most max_w x max_h in flight."""
+        return Pipe(self, depth, max_w, max_h, cap)
+
     def device_flags(self) -> int:
         flags = C.c_uint32(0)
         st = self._lib.fdf_check_device_flags(self._ctx, C.byref(flags))
@@ -268,6 +272,68 @@ class Detector:
     @property
     def kernel_launches(self) -> int:
         return int(self._lib.fdf_kernel_launches(self._ctx))
+
+
+class Pipe:
+    """fdf_pipe_*: the streaming form of `detect` -- up to `depth` images in flight, results first in, first out.
+
+        pipe = detector.pipe(depth=4, max_w=1920, max_h=1080)
+        for img in frames:
+            if pipe.in_flight == pipe.depth:
+                handle(pipe.collect())
+            pipe.submit(img, cfg)
+        while pipe.in_flight:
+            handle(pipe.collect())
+
+    A pageable image may be reused as soon as submit returns; an image in pinned memory is read by the DMA engine
+    directly and must stay untouched until its collect."""
+
+    def __init__(self, detector: "Detector", depth: int, max_w: int, max_h: int, cap: Optional[int] = None):
+        self._det, self._lib = detector, detector._lib
+        self.depth = int(depth)
+        worst = max(0, max_w - 6) * max(0, max_h - 6)
+        self.cap = int(cap) if cap is not None else min(worst, max(4096, worst // 16))
+        self._pipe = C.c_void_p()
+        st = self._lib.fdf_pipe_create(detector._ctx, self.depth, int(max_w), int(max_h), self.cap, C.byref(self._pipe))
+        if st != 0:
+            _raise(self._lib, detector._ctx, st)
+        self._buf = np.zeros((max(self.cap, 1), 2), np.uint32)
+        self._keep = []  # the submitted arrays, until collected (pinned images are read asynchronously)
+
+    @property
+    def in_flight(self) -> int:
+        return int(self._lib.fdf_pipe_in_flight(self._pipe)) if self._pipe.value else 0
+
+    def submit(self, img, config: Config) -> None:
+        a = _as_gray(img)
+        h, w = a.shape
+        st = self._lib.fdf_pipe_submit(self._pipe, a.ctypes.data, w, h, a.strides[0], int(config.threshold),
+                                       int(config.count), int(config.non_maximal_supression))
+        if st != 0:
+            _raise(self._lib, self._det._ctx, st)
+        self._keep.append(a)
+
+    def collect(self) -> np.ndarray:
+        """Keypoints of the oldest image in flight, (K, 2) uint32 (x, y) in the reference's order."""
+        n = C.c_size_t(0)
+        st = self._lib.fdf_pipe_collect(self._pipe, self._buf.ctypes.data, self.cap, C.byref(n))
+        if st != 3 and self._keep:  # (status 3 = nothing was in flight)
+            self._keep.pop(0)
+        if st != 0:
+            _raise(self._lib, self._det._ctx, st)
+        return self._buf[: n.value].copy()
+
+    def close(self) -> None:
+        if getattr(self, "_pipe", None) is not None and self._pipe.value:
+            self._lib.fdf_pipe_destroy(self._pipe)
+            self._pipe = C.c_void_p()
+            self._keep = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _tls = threading.local()

@@ -151,6 +151,7 @@ const char *fdf_status_string(fdf_status status) {
         case FDF_ERR_CUDA: return "CUDA error";
         case FDF_ERR_NO_DEVICE: return "no usable sm_100 device";
         case FDF_ERR_INTERNAL: return "device-side consistency check failed";
+        case FDF_ERR_BUSY: return "pipe full: collect an image first";
     }
     return "unknown status";
 }
@@ -671,6 +672,153 @@ fdf_status fdf_detect(fdf_ctx *ctx, const uint8_t *img, uint32_t w, uint32_t h, 
     memcpy(out, ctx->pinned_head + kSingleHead, (n < first ? n : first) * sizeof(fdf_point));
     if (n > first)  // (rare: more than 32 K keypoints in one image)
         FDF_CUDA(ctx, cudaMemcpy(out + first, d_points + first, (n - first) * sizeof(fdf_point), cudaMemcpyDeviceToHost));
+    return FDF_OK;
+}
+
+// ---- streaming form of fdf_detect ------------------------------------------------------------------
+struct fdf_pipe {
+    struct Slot {
+        uint8_t *pinned_in = nullptr;   // staging for pageable images
+        uint8_t *pinned_out = nullptr;  // [offsets u64 x 2 | flags @16 | pad to 64 | points]
+        uint8_t *d_frame = nullptr;
+        uint8_t *d_block = nullptr;     // same layout as pinned_out
+        cudaEvent_t landed = nullptr, kernels = nullptr, done = nullptr;
+        size_t first = 0;               // points that come back with the asynchronous copy
+        bool empty = false;             // image smaller than 7 x 7: no device work
+    };
+    fdf_ctx *ctx = nullptr;
+    uint32_t depth = 0, max_w = 0, max_h = 0, head = 0, tail = 0, in_flight = 0;
+    size_t cap = 0, hint = 0;
+    std::vector<Slot> slots;
+};
+
+fdf_status fdf_pipe_create(fdf_ctx *ctx, uint32_t depth, uint32_t max_w, uint32_t max_h, size_t cap, fdf_pipe **out_pipe) {
+    if (!ctx || !out_pipe) return FDF_ERR_INVALID_ARGUMENT;
+    *out_pipe = nullptr;
+    if (depth == 0 || depth > 64 || max_w == 0 || max_h == 0)
+        return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "pipe needs 1..64 slots and a non-empty maximum image size");
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    fdf_pipe *pipe = new (std::nothrow) fdf_pipe();
+    if (!pipe) return fail(ctx, FDF_ERR_INTERNAL, "out of host memory");
+    pipe->ctx = ctx, pipe->depth = depth, pipe->max_w = max_w, pipe->max_h = max_h, pipe->cap = cap;
+    pipe->slots.resize(depth);
+    const size_t frame_bytes = (size_t)((max_w + 15u) & ~15u) * max_h;
+    const size_t block_bytes = kSingleHead + (cap ? cap : 1) * sizeof(fdf_point);
+    for (auto &s : pipe->slots) {
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&s.pinned_in), frame_bytes);
+        if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void **>(&s.pinned_out), block_bytes);
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s.d_frame), frame_bytes);
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s.d_block), block_bytes);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.landed, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.kernels, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            fdf_pipe_destroy(pipe);
+            return fail(ctx, FDF_ERR_CUDA, "pipe allocation failed: %s", cudaGetErrorString(e));
+        }
+    }
+    *out_pipe = pipe;
+    return FDF_OK;
+}
+
+void fdf_pipe_destroy(fdf_pipe *pipe) {
+    if (!pipe) return;
+    cudaSetDevice(pipe->ctx->device);
+    cudaStreamSynchronize(pipe->ctx->copy_stream);
+    cudaStreamSynchronize(pipe->ctx->stream);
+    cudaStreamSynchronize(pipe->ctx->back_stream);
+    for (auto &s : pipe->slots) {
+        if (s.pinned_in) cudaFreeHost(s.pinned_in);
+        if (s.pinned_out) cudaFreeHost(s.pinned_out);
+        if (s.d_frame) cudaFree(s.d_frame);
+        if (s.d_block) cudaFree(s.d_block);
+        if (s.landed) cudaEventDestroy(s.landed);
+        if (s.kernels) cudaEventDestroy(s.kernels);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    delete pipe;
+}
+
+uint32_t fdf_pipe_in_flight(const fdf_pipe *pipe) { return pipe ? pipe->in_flight : 0u; }
+
+fdf_status fdf_pipe_submit(fdf_pipe *pipe, const uint8_t *img, uint32_t w, uint32_t h, uint32_t pitch, uint8_t threshold,
+                           uint8_t count, uint8_t nms) {
+    if (!pipe) return FDF_ERR_INVALID_ARGUMENT;
+    fdf_ctx *ctx = pipe->ctx;
+    fdf_status st = check_config(ctx, count, nms);
+    if (st != FDF_OK) return st;
+    if (pipe->in_flight == pipe->depth) return fail(ctx, FDF_ERR_BUSY, "%u images in flight: collect one first", pipe->depth);
+    if (w > pipe->max_w || h > pipe->max_h)
+        return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "image %u x %u exceeds the pipe's %u x %u", w, h, pipe->max_w, pipe->max_h);
+    fdf_pipe::Slot &s = pipe->slots[pipe->tail];
+    s.empty = w < 7 || h < 7;  // nothing can be a keypoint
+    if (!s.empty) {
+        if (!img) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null image pointer");
+        if (pitch < w) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "pitch %u < width %u", pitch, w);
+        FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+        const uint32_t dpitch = (w + 15u) & ~15u;
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, img) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();  // (an unregistered pointer is not an error here)
+        if (pinned) {
+            FDF_CUDA(ctx, cudaMemcpy2DAsync(s.d_frame, dpitch, img, pitch, w, h, cudaMemcpyHostToDevice, ctx->copy_stream));
+        } else {
+            if (pitch == dpitch) {
+                memcpy(s.pinned_in, img, (size_t)(h - 1) * pitch + w);
+            } else {
+                for (uint32_t r = 0; r < h; r++) memcpy(s.pinned_in + (size_t)r * dpitch, img + (size_t)r * pitch, w);
+            }
+            FDF_CUDA(ctx, cudaMemcpyAsync(s.d_frame, s.pinned_in, (size_t)dpitch * h, cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+        FDF_CUDA(ctx, cudaEventRecord(s.landed, ctx->copy_stream));
+        FDF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s.landed, 0));
+        const size_t worst = (size_t)(w - 6) * (size_t)(h - 6), dcap = pipe->cap < worst ? pipe->cap : worst;
+        ctx->flags_copy_next = reinterpret_cast<uint32_t *>(s.d_block + 16);
+        st = fdf_detect_device(ctx, s.d_frame, 1, w, h, dpitch, (uint64_t)dpitch * h, threshold, count, nms,
+                               reinterpret_cast<fdf_point *>(s.d_block + kSingleHead), dcap,
+                               reinterpret_cast<uint64_t *>(s.d_block), ctx->stream);
+        ctx->flags_copy_next = nullptr;
+        if (st != FDF_OK) return st;
+        FDF_CUDA(ctx, cudaEventRecord(s.kernels, ctx->stream));
+        FDF_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, s.kernels, 0));
+        s.first = pipe->hint + pipe->hint / 2 + 1024;
+        if (s.first < 4096) s.first = 4096;
+        if (s.first > dcap) s.first = dcap;
+        FDF_CUDA(ctx, cudaMemcpyAsync(s.pinned_out, s.d_block, kSingleHead + s.first * sizeof(fdf_point),
+                                      cudaMemcpyDeviceToHost, ctx->back_stream));
+        FDF_CUDA(ctx, cudaEventRecord(s.done, ctx->back_stream));
+    }
+    pipe->tail = (pipe->tail + 1u) % pipe->depth;
+    pipe->in_flight++;
+    return FDF_OK;
+}
+
+fdf_status fdf_pipe_collect(fdf_pipe *pipe, fdf_point *out, size_t cap, size_t *n_out) {
+    if (!pipe) return FDF_ERR_INVALID_ARGUMENT;
+    fdf_ctx *ctx = pipe->ctx;
+    if (!n_out) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null n_out");
+    *n_out = 0;
+    if (pipe->in_flight == 0) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "no image in flight");
+    if (!out && cap > 0) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "null output pointer");
+    fdf_pipe::Slot &s = pipe->slots[pipe->head];
+    pipe->head = (pipe->head + 1u) % pipe->depth;  // (the image is retired whatever happens below)
+    pipe->in_flight--;
+    if (s.empty) return FDF_OK;
+    FDF_CUDA(ctx, cudaSetDevice(ctx->device));
+    FDF_CUDA(ctx, cudaEventSynchronize(s.done));
+    const uint64_t found = reinterpret_cast<const uint64_t *>(s.pinned_out)[1];
+    const uint32_t flags = *reinterpret_cast<const uint32_t *>(s.pinned_out + 16);
+    *n_out = (size_t)found;
+    pipe->hint = (size_t)found;
+    if (flags & ~4u) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x (look-back or pipeline wait timed out)", flags);
+    if (found > pipe->cap) return fail(ctx, FDF_ERR_CAPACITY, "%llu keypoints found, the pipe was created for %zu", (unsigned long long)found, pipe->cap);
+    if (found > cap) return fail(ctx, FDF_ERR_CAPACITY, "%llu keypoints found, capacity %zu", (unsigned long long)found, cap);
+    if (flags) return fail(ctx, FDF_ERR_INTERNAL, "device flags 0x%x (staging buffer overflow)", flags);
+    const size_t n = (size_t)found;
+    memcpy(out, s.pinned_out + kSingleHead, (n < s.first ? n : s.first) * sizeof(fdf_point));
+    if (n > s.first)  // (more than the asynchronous copy brought back: fetch the rest now)
+        FDF_CUDA(ctx, cudaMemcpy(out + s.first, reinterpret_cast<const fdf_point *>(s.d_block + kSingleHead) + s.first,
+                                 (n - s.first) * sizeof(fdf_point), cudaMemcpyDeviceToHost));
     return FDF_OK;
 }
 

@@ -43,7 +43,8 @@ typedef enum fdf_status {
     FDF_ERR_CAPACITY = 4,        /* output buffer too small; *n_out / offsets[n_frames] hold the needed size */
     FDF_ERR_CUDA = 5,            /* a CUDA call failed; see fdf_last_error() */
     FDF_ERR_NO_DEVICE = 6,       /* no usable sm_100 device */
-    FDF_ERR_INTERNAL = 7         /* device-side consistency check failed (a pipeline wait timed out, staging overflow) */
+    FDF_ERR_INTERNAL = 7,        /* device-side consistency check failed (a pipeline wait timed out, staging overflow) */
+    FDF_ERR_BUSY = 8             /* fdf_pipe_submit: `depth` images are in flight already, collect one first */
 } fdf_status;
 
 /* One context per host thread and device: owns a stream, the scan workspace and the staging
@@ -148,6 +149,30 @@ fdf_status fdf_rgb8_to_luma8_device(fdf_ctx *ctx, const uint8_t *d_rgb, uint32_t
 fdf_status fdf_rgb8_to_grey_sum3_device(fdf_ctx *ctx, const uint8_t *d_rgb, uint32_t n_frames, uint32_t w, uint32_t h,
                                         uint32_t rgb_pitch, uint64_t rgb_frame_stride, uint8_t *d_grey,
                                         uint32_t grey_pitch, uint64_t grey_frame_stride, void *stream);
+
+/*
+ * Streaming form of fdf_detect ("batch / streaming host API with pinned-buffer pool and overlap of
+ * H2D || kernel || D2H"; the reference's `detect`, lib.rs:62-64, is synchronous and has no counterpart).  A pipe keeps
+ * up to `depth` images in flight on its context: fdf_pipe_submit enqueues host->device copy, the three kernels and
+ * the device->host copy of one image on three streams and returns without waiting; fdf_pipe_collect waits for the
+ * OLDEST submitted image and hands its keypoints out (first in, first out), exactly what fdf_detect would have
+ * returned for it.  Each of the `depth` slots owns pinned host buffers and device buffers for an image of up to
+ * max_w x max_h and `cap` keypoints, allocated once in fdf_pipe_create.
+ *   - a pageable image is copied into the slot's pinned buffer before submit returns: the caller may reuse it at once;
+ *     an image in pinned memory (cudaHostAlloc / cudaHostRegister) is read by the DMA engine directly and must stay
+ *     untouched until the matching collect;
+ *   - submit with `depth` images in flight returns FDF_ERR_BUSY (nothing is enqueued);
+ *   - collect with nothing in flight returns FDF_ERR_INVALID_ARGUMENT; a failed collect (FDF_ERR_CAPACITY: the
+ *     caller's `cap`, or the pipe's, is smaller than *n_out; FDF_ERR_INTERNAL) still retires the image.
+ * A pipe uses its context's streams and workspace: like every other call on a context it belongs to one host thread.
+ */
+typedef struct fdf_pipe fdf_pipe;
+fdf_status fdf_pipe_create(fdf_ctx *ctx, uint32_t depth, uint32_t max_w, uint32_t max_h, size_t cap, fdf_pipe **out_pipe);
+void fdf_pipe_destroy(fdf_pipe *pipe);
+fdf_status fdf_pipe_submit(fdf_pipe *pipe, const uint8_t *img, uint32_t w, uint32_t h, uint32_t pitch, uint8_t threshold,
+                           uint8_t count, uint8_t nms);
+fdf_status fdf_pipe_collect(fdf_pipe *pipe, fdf_point *out, size_t cap, size_t *n_out);
+uint32_t fdf_pipe_in_flight(const fdf_pipe *pipe);
 
 /*
  * main.rs:53-67 in one call: an interleaved RGB8 image in HOST memory (h rows of 3 w bytes, rgb_pitch bytes

@@ -7,12 +7,18 @@ pub struct fdf_ctx {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+pub struct fdf_pipe {
+    _private: [u8; 0],
+}
+
 /// `fdf_point` == `crate::Point` (`#[repr(C)] { x: u32, y: u32 }`).
 pub type fdf_point = crate::Point;
 
 pub const FDF_OK: c_int = 0;
 pub const FDF_ERR_INVALID_COUNT: c_int = 1;
 pub const FDF_ERR_CAPACITY: c_int = 4;
+pub const FDF_ERR_BUSY: c_int = 8;
 
 extern "C" {
     pub fn fdf_create(device: c_int, out_ctx: *mut *mut fdf_ctx) -> c_int;
@@ -103,6 +109,46 @@ extern "C" {
         cap: usize,
         n_out: *mut usize,
     ) -> c_int;
+    // streaming form of fdf_detect: up to `depth` images in flight, results first in, first out
+    pub fn fdf_pipe_create(
+        ctx: *mut fdf_ctx,
+        depth: u32,
+        max_w: u32,
+        max_h: u32,
+        cap: usize,
+        out_pipe: *mut *mut fdf_pipe,
+    ) -> c_int;
+    pub fn fdf_pipe_destroy(pipe: *mut fdf_pipe);
+    pub fn fdf_pipe_submit(
+        pipe: *mut fdf_pipe,
+        img: *const u8,
+        w: u32,
+        h: u32,
+        pitch: u32,
+        threshold: u8,
+        count: u8,
+        nms: u8,
+    ) -> c_int;
+    pub fn fdf_pipe_collect(pipe: *mut fdf_pipe, out: *mut fdf_point, cap: usize, n_out: *mut usize) -> c_int;
+    pub fn fdf_pipe_in_flight(pipe: *const fdf_pipe) -> u32;
+    // sharded batches (one process per GPU): the exchange step and the peer-mapped result buffer
+    pub fn fdf_shard_push(
+        ctx: *mut fdf_ctx,
+        d_all_offsets: *const u64,
+        block: u32,
+        n_ranks: u32,
+        rank: u32,
+        total_frames: u32,
+        d_points: *const fdf_point,
+        d_result: *mut fdf_point,
+        cap_total: usize,
+        d_global_offsets: *mut u64,
+        stream: *mut c_void,
+    ) -> c_int;
+    pub fn fdf_shared_alloc(ctx: *mut fdf_ctx, bytes: usize, d_ptr: *mut *mut c_void, handle: *mut u8) -> c_int;
+    pub fn fdf_shared_open(ctx: *mut fdf_ctx, handle: *const u8, d_ptr: *mut *mut c_void) -> c_int;
+    pub fn fdf_shared_close(ctx: *mut fdf_ctx, d_ptr: *mut c_void) -> c_int;
+    pub fn fdf_set_tuning(ctx: *mut fdf_ctx, strip_rows: c_int, sub_batch_mb: u32) -> c_int;
     pub fn fdf_last_error(ctx: *const fdf_ctx) -> *const c_char;
     pub fn fdf_status_string(status: c_int) -> *const c_char;
 }

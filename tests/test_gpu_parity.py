@@ -512,3 +512,58 @@ def test_shard_push_assembles_the_batch_result_on_one_gpu(detector, oracle_mod):
                 assert torch.equal(goffs, want_offs), (n_frames, world, r)
             assert torch.equal(result[:total], want_pts[:total]), (n_frames, world, nms)
             assert bool((result[total:] == -1).all())  # nothing written past the batch
+
+
+def test_pipe_streams_images_first_in_first_out(detector, oracle_mod):
+    """fdf_pipe_* (streaming host API): images of different sizes, contents and configs kept in flight,
+    collected in submission order, each list identical to what fdf_detect returns for the same image; submit on a full
+    pipe is FDF_ERR_BUSY, collect on an empty one an argument error, an image beyond the pipe's size is refused; pinned
+    and pageable sources; an image too small to hold a keypoint; a result larger than the first asynchronous copy."""
+    import torch
+
+    import feature_detector_fast_b200 as fdf
+
+    shapes = [(640, 360, 0, 16), (333, 77, 0, 12), (6, 40, 0, 16), (512, 300, 1, 3), (640, 360, 0, 20), (97, 211, 0, 9),
+              (640, 352, 0, 16)]
+    imgs = [oracle_mod.synth_frame(w, h, seed=5, frame=i, kind=k, amp=5) for i, (w, h, k, _) in enumerate(shapes)]
+    cfgs = [_cfg(t, 9 + i % 3, i % 3) for i, (_, _, _, t) in enumerate(shapes)]
+    pinned = torch.empty((352, 640), dtype=torch.uint8, pin_memory=True)  # the last image lives in pinned memory
+    pinned.copy_(torch.from_numpy(imgs[-1]))
+    imgs[-1] = pinned.numpy()
+    want = [detector.detect_array(a, c) for a, c in zip(imgs, cfgs)]
+    assert len(want[3]) > 4096 + 1024  # the noise image needs the second, synchronous copy on its first appearance
+    pipe = detector.pipe(depth=3, max_w=640, max_h=360, cap=max(len(x) for x in want))
+    try:
+        with pytest.raises(fdf.FdfError) as ei:
+            pipe.collect()
+        assert ei.value.status == 3
+        with pytest.raises(fdf.FdfError) as ei:
+            pipe.submit(np.zeros((361, 640), np.uint8), cfgs[0])
+        assert ei.value.status == 3 and pipe.in_flight == 0
+        with pytest.raises(fdf.FdfPanic):
+            pipe.submit(imgs[0], _cfg(16, 8, 0))
+        got = []
+        for rounds in range(2):  # twice: every slot is reused
+            for a, c in zip(imgs, cfgs):
+                if pipe.in_flight == pipe.depth:
+                    with pytest.raises(fdf.FdfError) as ei:
+                        pipe.submit(a, c)
+                    assert ei.value.status == 8  # FDF_ERR_BUSY, nothing enqueued
+                    assert pipe.in_flight == pipe.depth
+                    got.append(pipe.collect())
+                pipe.submit(a, c)
+            while pipe.in_flight:
+                got.append(pipe.collect())
+        assert len(got) == 2 * len(imgs)
+        for i, g in enumerate(got):
+            assert same_points(g, want[i % len(imgs)]), i
+        assert detector.device_flags() == 0
+        # a pipe created for fewer keypoints than an image has: FDF_ERR_CAPACITY with the number found, image retired
+        small = detector.pipe(depth=2, max_w=640, max_h=360, cap=100)
+        small.submit(imgs[0], cfgs[0])
+        with pytest.raises(fdf.FdfError) as ei:
+            small.collect()
+        assert ei.value.status == 4 and str(len(want[0])) in str(ei.value) and small.in_flight == 0
+        small.close()
+    finally:
+        pipe.close()
