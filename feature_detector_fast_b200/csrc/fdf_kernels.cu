@@ -29,8 +29,11 @@
 //                       + decoupled look-back between scan tiles -- giving every strip's final offset and
 //                       the CSR frame offsets;
 //   fdf_gather_kernel : persistent CTAs, one strip at a time: scatters the strip's runs into a two-level bit plane in
-//                       shared memory and expands it, row-major, to (x, y) points at the strip's final offset (for a
-//                       sharded batch: at the rank's place in the batch result, which may be another GPU's memory).
+//                       shared memory and expands it, row-major, to (x, y) points at the strip's final offset.  With
+//                       at most kGatherThreads strips in the batch (one image) it also does the scan itself: no
+//                       fdf_scan_kernel launch.
+//   fdf_shard_push_kernel (sharded batches, one process per GPU): global CSR offsets from the all-gathered local ones,
+//                       and the rank's points copied to their place in the batch result in rank 0's memory (NVLink).
 // (Doing the look-back inside the detection kernel was measured at +45 % kernel time: with ~450 strips
 // in flight every strip ends up waiting for all in-flight predecessors.  Keeping the strip bit plane inside
 // the detection kernel cost 30 KB of shared memory per CTA, i.e. one resident CTA per SM.  Structural variants that
