@@ -164,7 +164,8 @@ fdf_status fdf_rgb8_to_grey_sum3_device(fdf_ctx *ctx, const uint8_t *d_rgb, uint
  *   - submit with `depth` images in flight returns FDF_ERR_BUSY (nothing is enqueued);
  *   - collect with nothing in flight returns FDF_ERR_INVALID_ARGUMENT; a failed collect (FDF_ERR_CAPACITY: the
  *     caller's `cap`, or the pipe's, is smaller than *n_out; FDF_ERR_INTERNAL) still retires the image.
- * A pipe uses its context's streams and workspace: like every other call on a context it belongs to one host thread.
+ * A pipe uses its context's streams and workspace: like every other call on a context it belongs to one host thread,
+ * and it must be destroyed before its context.
  */
 typedef struct fdf_pipe fdf_pipe;
 fdf_status fdf_pipe_create(fdf_ctx *ctx, uint32_t depth, uint32_t max_w, uint32_t max_h, size_t cap, fdf_pipe **out_pipe);
