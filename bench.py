@@ -396,6 +396,8 @@ def main():
     ap.add_argument("--no-by-config", action="store_true")
     ap.add_argument("--strong-frames", type=int, default=FRAMES_PER_GPU,
                     help="total frames of the strong-scaling batch (default: the 512 of config 5)")
+    ap.add_argument("--idle-sm-stride", type=int, default=37,
+                    help="N > 1: the detection kernel leaves every n-th SM to the exchange kernels (0 = none)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
@@ -446,7 +448,8 @@ def main():
         def step():
             det.detect_device(frames, cfg, points=points, offsets=offsets)
     else:
-        sd = sharding.ShardedDetector(det, n_total, cap_total=n_total * per_frame_cap, cap_local=cap)
+        sd = sharding.ShardedDetector(det, n_total, cap_total=n_total * per_frame_cap, cap_local=cap,
+                                      idle_sm_stride=args.idle_sm_stride)
 
         def step():
             sd.detect(frames, cfg)
@@ -563,7 +566,8 @@ def main():
     elif strong_total % world == 0 and strong_total // world <= F:
         fs = strong_total // world
         s_frames = frames[:fs]  # (frame content does not matter for the timing; the check above covered correctness)
-        sds = sharding.ShardedDetector(det, strong_total, cap_total=strong_total * per_frame_cap, cap_local=fs * per_frame_cap)
+        sds = sharding.ShardedDetector(det, strong_total, cap_total=strong_total * per_frame_cap,
+                                       cap_local=fs * per_frame_cap, idle_sm_stride=args.idle_sm_stride)
         s_steps = max(20, args.steps)
         for _ in range(3):
             sds.detect(s_frames, cfg)
@@ -579,6 +583,7 @@ def main():
                   "host_enqueue_us_per_step": round(host_us, 1),
                   "value": round(strong_total * W * H / (s_ms / s_steps * 1e-3) / 1e6, 1),
                   "ms_per_step": round(s_ms / s_steps, 4),
+                  "idle_sm_stride": args.idle_sm_stride,
                   "note": "one 512-frame batch, looped; every step ends in one batch result on rank 0"}
         sds.close()
 
@@ -667,8 +672,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(F),
             "details": {"keypoints_per_step_rank0": local_found, "keypoints_per_step_all_ranks": found,
-                        "collective": ("one all_gather of the ranks' local CSR offsets (NCCL); points are written by the "
-                                       "emission kernels straight into rank 0's result over NVLink") if world > 1
+                        "collective": ("one all_gather of the ranks' local CSR offsets (NCCL) + one push kernel per rank "
+                                       "that copies its points into rank 0's result over NVLink, both on an exchange "
+                                       "stream; the detection kernel leaves every %d-th SM to them" % args.idle_sm_stride)
+                        if world > 1
                         else "none (1 GPU)"},
             "fps_1080p_equiv": round(mpix * 1e6 / (1920 * 1080), 1),
             "fps_4k": round(mpix * 1e6 / (W * H), 1),

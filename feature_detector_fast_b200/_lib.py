@@ -89,6 +89,9 @@ def load_library() -> C.CDLL:
     if hasattr(lib, "fdf_set_tuning"):
         lib.fdf_set_tuning.restype = C.c_int
         lib.fdf_set_tuning.argtypes = [vp, C.c_int, u32]
+    if hasattr(lib, "fdf_set_idle_sms"):
+        lib.fdf_set_idle_sms.restype = C.c_int
+        lib.fdf_set_idle_sms.argtypes = [vp, u32]
     lib.fdf_set_timing.restype = C.c_int
     lib.fdf_set_timing.argtypes = [vp, u32]
     lib.fdf_get_timing.restype = C.c_int

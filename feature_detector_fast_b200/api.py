@@ -258,6 +258,12 @@ class Detector:
             _raise(self._lib, self._ctx, st)
         return float(ms[0]), float(ms[1]), float(ms[2])
 
+    def set_idle_sms(self, sm_stride: int = 0) -> None:
+        """fdf_set_idle_sms: the detection kernel leaves every sm_stride-th SM to other kernels (0 = uses all)."""
+        st = self._lib.fdf_set_idle_sms(self._ctx, int(sm_stride))
+        if st != 0:
+            _raise(self._lib, self._ctx, st)
+
     def pipe(self, depth: int, max_w: int, max_h: int, cap: Optional[int] = None) -> "Pipe":
         """fdf_pipe_create: a streaming detector with up to `depth` images of at most max_w x max_h in flight."""
         return Pipe(self, depth, max_w, max_h, cap)

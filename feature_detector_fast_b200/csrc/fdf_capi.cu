@@ -90,6 +90,7 @@ struct fdf_ctx {
     CUtensorMap tmap_cached;
     uint64_t launches = 0;
     fdf::DeviceInfo info;        // SM count, kernel occupancies, experiment knobs: looked up once in fdf_create
+    uint32_t idle_sm_stride = 0; // fdf_set_idle_sms: every n-th SM is left to other kernels by the detection kernel
     int force_sr = 0;            // FDF_FORCE_SR (experiments / tests): strip height override, read once in fdf_create
     unsigned long long sub_batch_bytes = 128ull << 20;  // fdf_detect_batch sub-batch size (FDF_SUB_BATCH_MB, read once)
     std::vector<void *> shared_owned, shared_opened;  // fdf_shared_alloc / fdf_shared_open
@@ -258,6 +259,7 @@ fdf_status prepare_detect(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_fram
     p.count = count;
     p.mode = (uint32_t)mode;
     p.sr = (uint32_t)sr;
+    p.idle_sm_stride = ctx->idle_sm_stride;
     p.cap = cap;
 
     if (fdf::gather_smem_bytes(mode, sr, p.words_per_row) > 200 * 1024 || w > 65535u ||
@@ -445,6 +447,13 @@ fdf_status fdf_set_tuning(fdf_ctx *ctx, int strip_rows, uint32_t sub_batch_mb) {
     if (sub_batch_mb > 65536u) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "sub_batch_mb out of range");
     ctx->force_sr = strip_rows;
     ctx->sub_batch_bytes = (unsigned long long)(sub_batch_mb ? sub_batch_mb : 128u) << 20;
+    return FDF_OK;
+}
+
+fdf_status fdf_set_idle_sms(fdf_ctx *ctx, uint32_t sm_stride) {
+    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
+    if (sm_stride == 1u) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "sm_stride 1 would leave no SM to the detection kernel");
+    ctx->idle_sm_stride = sm_stride;
     return FDF_OK;
 }
 

@@ -308,6 +308,11 @@ __device__ __forceinline__ unsigned long long open_run(unsigned long long *s_blo
 template <int MODE, int SR>
 __global__ void __launch_bounds__(kThreads, SR >= 48 ? 3 : 4)
 fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p) {
+    if (p.idle_sm_stride != 0u) {  // SMs kept free for the exchange kernels of a sharded batch (fdf_set_idle_sms)
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (smid % p.idle_sm_stride == p.idle_sm_stride - 1u) return;  // (block-uniform; the strips go by ticket)
+    }
     constexpr LayoutSizes L = layout_sizes(SR);
     constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;  // score halo (rows and columns) needed by the 3x3 NMS
     constexpr int OUT_R = out_rows(MODE, SR);

@@ -48,6 +48,7 @@ struct DetectParams {
     uint32_t words_per_row;  // ceil(w / 32): bit-plane words per row (gather kernel)
     uint32_t threshold, count;
     uint32_t mode, sr;       // (the gather kernel is not templated)
+    uint32_t idle_sm_stride; // > 0: detection CTAs on SMs with %smid % stride == stride - 1 return at once (fdf_set_idle_sms)
     unsigned long long cap;  // capacity of out, in points
     unsigned long long staging_cap;   // capacity of staging: 2 cap + one block per CTA (blocks are not used to the end)
     uint2 *out;              // fdf_point[cap], packed over the whole batch, row-major per frame

@@ -91,12 +91,16 @@ class ShardedDetector:
     """
 
     def __init__(self, detector, n_frames: int, cap_total: int, cap_local: Optional[int] = None, group=None,
-                 depth: int = 4):
+                 depth: int = 4, idle_sm_stride: int = 37):
         import torch
         import torch.distributed as dist
 
         self.det, self.depth = detector, max(2, int(depth))
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        # The detection kernel leaves every idle_sm_stride-th SM (4 of 148 for 37) to the exchange kernels: otherwise
+        # every all-gather and push waits for a whole persistent detection launch to drain (fdf_set_idle_sms).
+        self._idle_sm_stride = int(idle_sm_stride) if self.world > 1 else 0
+        detector.set_idle_sms(self._idle_sm_stride)
         # The per-batch all-gather gets a communicator of its own on a HIGH-PRIORITY stream: the detection kernel is
         # persistent and fills every SM, so a normal-priority NCCL kernel that becomes ready a few microseconds after
         # the next batch's detection was launched waits for that whole launch.  With priority its (few) CTAs are
@@ -119,6 +123,7 @@ class ShardedDetector:
         self._fence = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._xstream = torch.cuda.Stream(device=self.device, priority=-1)
         self._turn = 0
+        self.trace = None  # set to [] to record (batch start, detection done, all-gather start / end, push end) events
         # per buffer: the rank's block of the all-gather (its local offsets) and, except on rank 0, its local points
         # (`depth` of each: the all-gather is a collective, so the ranks' exchanges run in lock step; a few batches of
         # slack keep a rank that is ahead from waiting for the slowest one)
@@ -164,6 +169,11 @@ class ShardedDetector:
         if self._done[i] is not None:
             main.wait_event(self._done[i])  # the exchange that last used buffer i (`depth` batches ago) is over
         mine = self._mine[i]
+        tr = None
+        if self.trace is not None:
+            tr = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            self.trace.append(tr)
+            tr[0].record(main)
         # rank 0 emits straight into the result (its points start at 0); the others into a local buffer
         out_ptr = self._ptr.value if self.rank == 0 else self._local[i].data_ptr()
         out_cap = self.cap_total if self.rank == 0 else self.cap_local
@@ -178,10 +188,16 @@ class ShardedDetector:
             mine.zero_()
         ready = torch.cuda.Event()
         ready.record(main)
+        if tr:
+            tr[1].record(main)
         xs = self._xstream
         xs.wait_event(ready)
         with torch.cuda.stream(xs):
+            if tr:
+                tr[2].record(xs)
             dist.all_gather_into_tensor(self._all, mine, group=self.group)
+            if tr:
+                tr[3].record(xs)
             st = lib.fdf_shard_push(det._ctx, self._all.data_ptr(), self.block, self.world, self.rank, self.n_frames,
                                     None if self.rank == 0 else self._local[i].data_ptr(),
                                     None if self.rank == 0 else self._ptr.value, self.cap_total,
@@ -190,6 +206,8 @@ class ShardedDetector:
                 _raise(lib, det._ctx, st)
             self._done[i] = torch.cuda.Event()
             self._done[i].record(xs)
+            if tr:
+                tr[4].record(xs)
         return self.points, self.global_offsets
 
     def fence(self) -> None:
@@ -220,6 +238,7 @@ class ShardedDetector:
             if self._own_group:
                 dist.destroy_process_group(self.group)
                 self._own_group = False
+            self.det.set_idle_sms(0)
 
 
 class _RawCudaBuffer:

@@ -201,6 +201,15 @@ uint64_t fdf_kernel_launches(const fdf_ctx *ctx);
  * FDF_SUB_BATCH_MB give the initial values when the context is created; they are not read afterwards. */
 fdf_status fdf_set_tuning(fdf_ctx *ctx, int strip_rows, uint32_t sub_batch_mb);
 
+/* Leave SMs free beside the detection kernel.  That kernel is persistent and fills every SM (three CTAs each, all of
+ * the registers and shared memory), so any other kernel that becomes ready while it runs -- the all-gather of a
+ * communication library, fdf_shard_push -- waits for the whole launch to drain: measured on 8 GPUs, every exchange then
+ * takes one detection period and the ranks run in lock step behind it.  With sm_stride = n > 0 the detection CTAs that
+ * land on every n-th SM (%smid % n == n - 1) return at once; the strips are handed out by ticket, so the other CTAs
+ * do all the work (throughput -1/n) and the idle SMs take the exchange kernels immediately.  0 = use every SM
+ * (default).  Results never depend on it. */
+fdf_status fdf_set_idle_sms(fdf_ctx *ctx, uint32_t sm_stride);
+
 /* Per-kernel device timing for benchmarks.  fdf_set_timing(ctx, n) makes every following
  * fdf_detect_device-family call record CUDA events around its three launches into slot
  * (call index mod n); n = 0 switches it off.  fdf_get_timing synchronises on the slot's last event and

@@ -567,3 +567,24 @@ def test_pipe_streams_images_first_in_first_out(detector, oracle_mod):
         small.close()
     finally:
         pipe.close()
+
+
+def test_idle_sms_do_not_change_the_result(detector, oracle_mod):
+    """fdf_set_idle_sms (the detection kernel leaves every n-th SM to the exchange kernels of a sharded batch): the CTAs
+    that land there return before taking a ticket, the others do all the strips -- same points, same order, no flag."""
+    import torch
+
+    frames = detector.synth_frames(6, 3840, 2160, seed=404, kind=0)
+    cfg = _cfg(20, 9, 1)
+    want_pts, want_offs = detector.detect_device(frames, cfg)
+    torch.cuda.synchronize()
+    k = int(want_offs[-1])
+    try:
+        for stride in (24, 2, 148):
+            detector.set_idle_sms(stride)
+            pts, offs = detector.detect_device(frames, cfg)
+            torch.cuda.synchronize()
+            assert torch.equal(offs, want_offs) and torch.equal(pts[:k], want_pts[:k]), stride
+            assert detector.device_flags() == 0
+    finally:
+        detector.set_idle_sms(0)
