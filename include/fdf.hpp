@@ -89,4 +89,48 @@ inline std::vector<Point> detect(const GrayImage &img, const Config &config) {
     return std::vector<Point>(c.scratch.begin(), c.scratch.begin() + (ptrdiff_t)n);
 }
 
+// Streaming form (no counterpart in the reference, whose `detect` is synchronous): up to `depth` images in flight on
+// this thread's context, results first in, first out (C ABI: fdf_pipe_*, include/fdf.h).
+//     Pipe pipe(4, 1920, 1080);
+//     for (const GrayImage &img : frames) {
+//         if (pipe.in_flight() == pipe.depth()) handle(pipe.collect());
+//         pipe.submit(img, config);
+//     }
+//     while (pipe.in_flight()) handle(pipe.collect());
+class Pipe {
+public:
+    Pipe(uint32_t depth, uint32_t max_width, uint32_t max_height, size_t cap = 0) : depth_(depth) {
+        const size_t worst = (max_width > 6 && max_height > 6) ? (size_t)(max_width - 6) * (max_height - 6) : 0;
+        cap_ = cap ? cap : (worst / 16 > 4096 ? worst / 16 : (worst < 4096 ? worst : 4096));
+        detail::Context &c = detail::thread_context();
+        fdf_status st = fdf_pipe_create(c.ctx, depth, max_width, max_height, cap_, &pipe_);
+        if (st != FDF_OK) throw std::runtime_error(std::string("fdf_pipe_create: ") + fdf_last_error(c.ctx));
+        out_.resize(cap_ + 1);
+    }
+    ~Pipe() { fdf_pipe_destroy(pipe_); }
+    Pipe(const Pipe &) = delete;
+    Pipe &operator=(const Pipe &) = delete;
+    uint32_t depth() const { return depth_; }
+    uint32_t in_flight() const { return fdf_pipe_in_flight(pipe_); }
+    void submit(const GrayImage &img, const Config &config) {
+        if (config.count < 9) throw std::logic_error("number of consecutive pixels needs to exceed 9");
+        if (config.count > 16) throw std::logic_error("index out of bounds: consecutive count above 16");
+        fdf_status st = fdf_pipe_submit(pipe_, img.as_raw().data(), img.width(), img.height(), img.width(),
+                                        config.threshold, config.count, (uint8_t)config.non_maximal_supression);
+        if (st != FDF_OK) throw std::runtime_error(std::string("fdf_pipe_submit: ") + fdf_last_error(detail::thread_context().ctx));
+    }
+    std::vector<Point> collect() {
+        size_t n = 0;
+        fdf_status st = fdf_pipe_collect(pipe_, reinterpret_cast<fdf_point *>(out_.data()), cap_, &n);
+        if (st != FDF_OK) throw std::runtime_error(std::string("fdf_pipe_collect: ") + fdf_last_error(detail::thread_context().ctx));
+        return std::vector<Point>(out_.begin(), out_.begin() + (ptrdiff_t)n);
+    }
+
+private:
+    fdf_pipe *pipe_ = nullptr;
+    uint32_t depth_;
+    size_t cap_ = 0;
+    std::vector<Point> out_;
+};
+
 }  // namespace feature_detector_fast

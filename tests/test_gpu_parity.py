@@ -527,6 +527,10 @@ def test_pipe_streams_images_first_in_first_out(detector, oracle_mod):
               (640, 352, 0, 16)]
     imgs = [oracle_mod.synth_frame(w, h, seed=5, frame=i, kind=k, amp=5) for i, (w, h, k, _) in enumerate(shapes)]
     cfgs = [_cfg(t, 9 + i % 3, i % 3) for i, (_, _, _, t) in enumerate(shapes)]
+    wide = np.zeros((77, 400), np.uint8)  # the second image is a strided view (pitch 400 > width 333)
+    wide[:, :333] = imgs[1]
+    imgs[1] = wide[:, :333]
+    assert imgs[1].strides[0] == 400
     pinned = torch.empty((352, 640), dtype=torch.uint8, pin_memory=True)  # the last image lives in pinned memory
     pinned.copy_(torch.from_numpy(imgs[-1]))
     imgs[-1] = pinned.numpy()
