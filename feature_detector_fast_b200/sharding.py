@@ -101,6 +101,7 @@ class ShardedDetector:
         # every all-gather and push waits for a whole persistent detection launch to drain (fdf_set_idle_sms).
         self._idle_sm_stride = int(idle_sm_stride) if self.world > 1 else 0
         detector.set_idle_sms(self._idle_sm_stride)
+        detector._sharded_users = getattr(detector, "_sharded_users", 0) + 1  # (the last one to close gives the SMs back)
         # The per-batch all-gather gets a communicator of its own on a HIGH-PRIORITY stream: the detection kernel is
         # persistent and fills every SM, so a normal-priority NCCL kernel that becomes ready a few microseconds after
         # the next batch's detection was launched waits for that whole launch.  With priority its (few) CTAs are
@@ -238,7 +239,9 @@ class ShardedDetector:
             if self._own_group:
                 dist.destroy_process_group(self.group)
                 self._own_group = False
-            self.det.set_idle_sms(0)
+            self.det._sharded_users = max(0, getattr(self.det, "_sharded_users", 1) - 1)
+            if self.det._sharded_users == 0:
+                self.det.set_idle_sms(0)
 
 
 class _RawCudaBuffer:
