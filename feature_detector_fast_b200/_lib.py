@@ -89,6 +89,9 @@ def load_library() -> C.CDLL:
     if hasattr(lib, "fdf_set_tuning"):
         lib.fdf_set_tuning.restype = C.c_int
         lib.fdf_set_tuning.argtypes = [vp, C.c_int, u32]
+    if hasattr(lib, "fdf_set_item_parts"):
+        lib.fdf_set_item_parts.restype = C.c_int
+        lib.fdf_set_item_parts.argtypes = [vp, u32]
     if hasattr(lib, "fdf_set_idle_sms"):
         lib.fdf_set_idle_sms.restype = C.c_int
         lib.fdf_set_idle_sms.argtypes = [vp, u32]

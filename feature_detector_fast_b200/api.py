@@ -258,6 +258,12 @@ class Detector:
             _raise(self._lib, self._ctx, st)
         return float(ms[0]), float(ms[1]), float(ms[2])
 
+    def set_item_parts(self, parts: int = 0) -> None:
+        """fdf_set_item_parts: work items per strip of the detection kernel (0 = automatic, 1, 2, 4, 8)."""
+        st = self._lib.fdf_set_item_parts(self._ctx, int(parts))
+        if st != 0:
+            _raise(self._lib, self._ctx, st)
+
     def set_idle_sms(self, sm_stride: int = 0) -> None:
         """fdf_set_idle_sms: the detection kernel leaves every sm_stride-th SM to other kernels (0 = uses all)."""
         st = self._lib.fdf_set_idle_sms(self._ctx, int(sm_stride))

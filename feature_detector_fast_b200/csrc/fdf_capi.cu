@@ -90,6 +90,7 @@ struct fdf_ctx {
     CUtensorMap tmap_cached;
     uint64_t launches = 0;
     fdf::DeviceInfo info;        // SM count, kernel occupancies, experiment knobs: looked up once in fdf_create
+    uint32_t item_parts = 0;     // fdf_set_item_parts: work items per strip, 0 = chosen from the batch size
     uint32_t idle_sm_stride = 0; // fdf_set_idle_sms: every n-th SM is left to other kernels by the detection kernel
     int force_sr = 0;            // FDF_FORCE_SR (experiments / tests): strip height override, read once in fdf_create
     unsigned long long sub_batch_bytes = 128ull << 20;  // fdf_detect_batch sub-batch size (FDF_SUB_BATCH_MB, read once)
@@ -267,6 +268,19 @@ fdf_status prepare_detect(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_fram
         return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "image too wide (%u) for the strip bit plane", w);
     const unsigned long long items = (unsigned long long)n_frames * p.strips_per_frame;
     if (items > 0x7fffffffull) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "batch too large");
+    // Work items of the detection kernel: whole strips, except for small inputs (the 32-row kernels: fewer than 2 x 148
+    // strips of 64 rows in the batch), where every strip is cut into 2, 4 or 8 equal chunk ranges while that still
+    // raises the number of busy CTAs -- one 1080p image is 36 strips, i.e. 36 of 592 CTA slots and a chain of 8 chunks
+    // per CTA.  Only even splits, at least two chunks (= tile stages) per item.
+    {
+        const unsigned long long slots = (unsigned long long)ctx->info.sms * 4ull;
+        const uint32_t want = ctx->item_parts ? ctx->item_parts : 8u;
+        uint32_t parts = 1u;
+        while (sr == 32 && 2u * parts <= want && (ctx->item_parts != 0u || items * parts < slots) &&
+               p.chunks_per_strip % (2u * parts) == 0u && p.chunks_per_strip / (2u * parts) >= 2u)
+            parts *= 2u;
+        p.parts = parts;
+    }
 
     // workspace: [header 64 B: ticket, flags, scan ticket, cursor][scan status][zeroed up to here per launch]
     //            [item_dst][run_base][item_count][run_count]
@@ -285,7 +299,7 @@ fdf_status prepare_detect(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_fram
     // of the grid.  Overflow is not silent: the kernels raise flag bit 2.
     {
         unsigned long long ctas = (unsigned long long)ctx->info.sms * 4ull;  // (at most 4 resident CTAs per SM)
-        if (ctas > items) ctas = items;
+        if (ctas > items * p.parts) ctas = items * p.parts;  // (every CTA that gets a ticket opens a block)
         p.staging_cap = 2ull * cap + (ctas + 1ull) * (unsigned long long)fdf::kStageBlock;
     }
     FDF_CUDA(ctx, ctx->staging.reserve((size_t)p.staging_cap));
@@ -300,6 +314,8 @@ fdf_status prepare_detect(fdf_ctx *ctx, const uint8_t *d_frames, uint32_t n_fram
     p.item_count = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + cnt_off);
     p.run_count = reinterpret_cast<uint32_t *>(ctx->workspace.ptr + rcnt_off);
     p.staging = ctx->staging.ptr;
+    if (p.parts > 1u)  // the items of a strip add their counts up
+        FDF_CUDA(ctx, cudaMemsetAsync(p.item_count, 0, (size_t)items * sizeof(uint32_t), stream));
 
     // frames as a 3-D u8 tensor (x, y, frame); box = one tile; out-of-bounds elements read as 0
     const cuuint64_t dims[3] = {w, h, n_frames};
@@ -447,6 +463,14 @@ fdf_status fdf_set_tuning(fdf_ctx *ctx, int strip_rows, uint32_t sub_batch_mb) {
     if (sub_batch_mb > 65536u) return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "sub_batch_mb out of range");
     ctx->force_sr = strip_rows;
     ctx->sub_batch_bytes = (unsigned long long)(sub_batch_mb ? sub_batch_mb : 128u) << 20;
+    return FDF_OK;
+}
+
+fdf_status fdf_set_item_parts(fdf_ctx *ctx, uint32_t parts) {
+    if (!ctx) return FDF_ERR_INVALID_ARGUMENT;
+    if (parts != 0u && parts != 1u && parts != 2u && parts != 4u && parts != 8u)
+        return fail(ctx, FDF_ERR_INVALID_ARGUMENT, "parts must be 0 (automatic), 1, 2, 4 or 8");
+    ctx->item_parts = parts;
     return FDF_OK;
 }
 

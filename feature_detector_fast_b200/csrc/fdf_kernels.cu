@@ -345,7 +345,14 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = (int)p.w, H = (int)p.h;
     const int NC = (int)p.chunks_per_strip;
-    const uint32_t total_items = p.n_frames * p.strips_per_frame;
+    // A work item is one strip, or -- for small batches, where whole strips leave most CTAs idle or make a long tail --
+    // one of p.parts equal column ranges of a strip (NCI chunks each; the host only splits evenly and keeps
+    // NCI >= kTileStages).  Chunks are independent, so nothing but the ticket arithmetic changes.
+    // Only the 32-row kernels (the ones small inputs run) carry the split: for the others `parts` is the constant 1 and
+    // the arithmetic below folds away -- it cost the large-batch kernel 2.5 % when it was there at run time.
+    const uint32_t parts = SR == 32 ? p.parts : 1u;
+    const int NCI = NC / (int)parts;
+    const uint32_t total_items = p.n_frames * p.strips_per_frame * parts;
     const bool is_filter = warp < kFilterWarps;
     const int ttid = tid - kFilterThreads;  // thread index inside the test group
     // the thread that draws tickets, requests tiles and keeps the run records: lane 0 of the LAST test warp, which gets
@@ -355,30 +362,32 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
 
     uint32_t cur = 0u, nxt = 0xffffffffu;
     bool have_nxt = false;
-    const int ahead = NC >= kTileStages ? kTileStages : NC;  // tiles requested this many chunks ahead (never beyond the next strip)
+    const int ahead = NCI >= kTileStages ? kTileStages : NCI;  // tiles requested this many chunks ahead (never beyond the next item)
 
-    // request the tile of chunk c of the current strip (c < NC) or of chunk c - NC of the next strip; `it` is the
-    // current strip's sequence number in this CTA.  When the work is exhausted the barrier is completed without
+    // request the tile of chunk c of the current item (c < NCI) or of chunk c - NCI of the next item; `it` is the
+    // current item's sequence number in this CTA.  When the work is exhausted the barrier is completed without
     // a tile, so that the filter warps wake up and see the end ticket.
     auto request_tile = [&](int c, uint32_t stream_index, uint32_t it) {
         uint32_t item = cur;
-        if (c >= NC) {
-            if (c - NC >= NC) return;
+        if (c >= NCI) {
+            if (c - NCI >= NCI) return;
             if (!have_nxt) {
                 nxt = atomicAdd(p.ticket, 1u);
                 have_nxt = true;
                 s_ticket[(it + 1u) & 1u] = nxt;
             }
             item = nxt;
-            c -= NC;
+            c -= NCI;
         }
         const uint32_t stage = stream_index % (uint32_t)kTileStages;
         if (item >= total_items) {
             mbar_arrive(&full_bar[stage]);
             return;
         }
-        const uint32_t frame = item / p.strips_per_frame;
-        const uint32_t strip = item - frame * p.strips_per_frame;
+        const uint32_t sg = item / parts;  // strip in (frame, strip) order
+        c += (int)(item - sg * parts) * NCI;  // chunk of the strip
+        const uint32_t frame = sg / p.strips_per_frame;
+        const uint32_t strip = sg - frame * p.strips_per_frame;
         const int ty0 = first_out_row(MODE) + (int)strip * OUT_R - HS - 3;  // image row of tile row 0
         mbar_expect_tx(&full_bar[stage], (uint32_t)L.tile_bytes);
         tma_load_3d(tiles + stage * L.tile_bytes, &tmap, c * kChunkW - kTileLead, ty0, (int)frame, &full_bar[stage]);
@@ -430,7 +439,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
 #endif
     cur = s_ticket[0];
     if (t0)
-        for (int c = 0; c < ahead; c++) request_tile(c, (uint32_t)c, 0u);  // (ahead <= NC: all of the first strip)
+        for (int c = 0; c < ahead; c++) request_tile(c, (uint32_t)c, 0u);  // (ahead <= NCI: all of the first item)
 
     const int t = (int)p.threshold, n = (int)p.count;
     uint32_t gc = 0;   // chunks processed by this CTA so far
@@ -440,9 +449,12 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         // ================================ filter warps =================================================
         const uint32_t kbias = filter_kbias(p.threshold);
         for (uint32_t it = 0; cur < total_items; it++) {
-            const uint32_t frame = cur / p.strips_per_frame;
-            const uint32_t strip = cur - frame * p.strips_per_frame;
-            for (int c = 0; c < NC; c++, gc++) {
+            const uint32_t sg = cur / parts;
+            const int c0 = (int)(cur - sg * parts) * NCI;
+            const uint32_t frame = sg / p.strips_per_frame;
+            const uint32_t strip = sg - frame * p.strips_per_frame;
+            for (int ci = 0; ci < NCI; ci++, gc++) {
+                const int c = c0 + ci;  // chunk of the strip
                 const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
                 const uint8_t *tile = tiles + qb * L.tile_bytes;
                 mbar_wait(&full_bar[qb], qpar, p.flags, s_abort);  // the tile has landed (also: queue qb is free again)
@@ -479,17 +491,23 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         if (count != 0u) p.run_base[slot] = *s_base;
         p.run_count[slot] = count;
         const uint32_t tot = *s_total + count;
-        if (last) p.item_count[cur] = tot;
+        if (last) {  // (a strip cut into parts: the counts of its items add up; the host zeroed them)
+            if (parts == 1u) p.item_count[cur] = tot;
+            else if (tot != 0u) atomicAdd(&p.item_count[cur / parts], tot);
+        }
         *s_total = last ? 0u : tot;
     };
     for (uint32_t it = 0; cur < total_items; it++) {
-        const uint32_t frame = cur / p.strips_per_frame;
-        const uint32_t strip = cur - frame * p.strips_per_frame;
-        for (int c = 0; c < NC; c++, gc++) {
+        const uint32_t sg = cur / parts;
+        const int c0 = (int)(cur - sg * parts) * NCI;
+        const uint32_t frame = sg / p.strips_per_frame;
+        const uint32_t strip = sg - frame * p.strips_per_frame;
+        for (int ci = 0; ci < NCI; ci++, gc++) {
+            const int c = c0 + ci;  // chunk of the strip
             const uint8_t *tile = tiles + qb * L.tile_bytes;
             uint16_t *queue = queues + qb * kQueueCap;
             const ChunkGeo g = make_geo<MODE>(W, H, (int)strip, c, SR);
-            const uint32_t slot = cur * (uint32_t)NC + (uint32_t)c;
+            const uint32_t slot = sg * (uint32_t)NC + (uint32_t)c;
             if (tag == 1u && gc != 0u) {  // every 15 chunks: restart the tags on a cleared plane
                 clear_plane(ttid, kTestThreads);
                 bar_test_group();
@@ -505,7 +523,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                 bar_test_group();  // every score of this chunk is in the plane and its keypoint list is complete
                 if (t0) {
                     qcount[qb] = 0u;
-                    request_tile(c + ahead, gc + (uint32_t)ahead, it);
+                    request_tile(ci + ahead, gc + (uint32_t)ahead, it);
                 }
                 FDF_CLK(6)
                 dropped = emit_list<MODE, SR>(ttid, kTestThreads, kcount[gc & 1u], klist, plane, scount, *s_base,
@@ -516,7 +534,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                     const uint32_t count = *scount;
                     *scount = 0u;
                     kcount[gc & 1u] = 0u;  // (next used two chunks from now)
-                    close_run(slot, count, c == NC - 1);
+                    close_run(slot, count, ci == NCI - 1);
                     s_block[0] = *s_base + count;  // give the unused tail back
                     *s_base = open_run(s_block, p);
                 }
@@ -529,7 +547,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                 bar_test_group();  // every score of this chunk is in the plane; tile and queue are free
                 if (t0) {
                     qcount[qb] = 0u;
-                    request_tile(c + ahead, gc + (uint32_t)ahead, it);
+                    request_tile(ci + ahead, gc + (uint32_t)ahead, it);
                 }
                 nms_dense<MODE, SR>(ttid, kTestThreads, 0, plane, scount, 0ull, p.staging_cap, p.staging, g, tag);
                 bar_test_group();
@@ -546,7 +564,7 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                 bar_test_group();
                 if (t0) {
                     *scount = 0u;
-                    close_run(slot, kn, c == NC - 1);
+                    close_run(slot, kn, ci == NCI - 1);
                     *s_base = open_run(s_block, p);
                 }
             }
@@ -972,7 +990,8 @@ cudaError_t launch_detect(int mode, int sr, const CUtensorMap &tmap, const Detec
     if (info.ctas_limit >= 1 && info.ctas_limit < per_sm) per_sm = info.ctas_limit;
     // persistent grid: as many CTAs as can be resident at once (each loops over tickets)
     unsigned long long grid = (unsigned long long)info.sms * (unsigned)per_sm;
-    if (grid > items) grid = items;
+    const unsigned long long tickets = items * (sr == 32 && p.parts > 1u ? p.parts : 1u);  // (only the 32-row kernels split)
+    if (grid > tickets) grid = tickets;
 #define FDF_CASE(M, S) \
     if (mode == M && sr == S) return launch_t<M, S>(tmap, p, stream, (unsigned)grid);
     FDF_CASE(0, 32)

@@ -45,6 +45,7 @@ struct DetectParams {
     uint32_t w, h, n_frames;
     uint32_t strips_per_frame;
     uint32_t chunks_per_strip;
+    uint32_t parts;          // work items per strip of the detection kernel (1, 2, 4 or 8 equal chunk ranges; divides chunks_per_strip)
     uint32_t words_per_row;  // ceil(w / 32): bit-plane words per row (gather kernel)
     uint32_t threshold, count;
     uint32_t mode, sr;       // (the gather kernel is not templated)

@@ -201,6 +201,13 @@ uint64_t fdf_kernel_launches(const fdf_ctx *ctx);
  * FDF_SUB_BATCH_MB give the initial values when the context is created; they are not read afterwards. */
 fdf_status fdf_set_tuning(fdf_ctx *ctx, int strip_rows, uint32_t sub_batch_mb);
 
+/* Work items of the detection kernel (tests and experiments; results never depend on it).  The kernel's CTAs draw
+ * (frame, strip) tickets.  A small input -- one image: 36 strips for 592 CTA slots -- is cut finer: every strip becomes
+ * 2, 4 or 8 equal ranges of chunks, each a ticket of its own.  parts = 0: automatic (default: split while there are
+ * fewer items than CTA slots); 1, 2, 4, 8: at most that many.  Only the 32-row-strip kernels (small inputs) split, only
+ * evenly and with at least two chunks per item. */
+fdf_status fdf_set_item_parts(fdf_ctx *ctx, uint32_t parts);
+
 /* Leave SMs free beside the detection kernel.  That kernel is persistent and fills every SM (three CTAs each, all of
  * the registers and shared memory), so any other kernel that becomes ready while it runs -- the all-gather of a
  * communication library, fdf_shard_push -- waits for the whole launch to drain: measured on 8 GPUs, every exchange then

@@ -149,6 +149,7 @@ extern "C" {
     pub fn fdf_shared_open(ctx: *mut fdf_ctx, handle: *const u8, d_ptr: *mut *mut c_void) -> c_int;
     pub fn fdf_shared_close(ctx: *mut fdf_ctx, d_ptr: *mut c_void) -> c_int;
     pub fn fdf_set_tuning(ctx: *mut fdf_ctx, strip_rows: c_int, sub_batch_mb: u32) -> c_int;
+    pub fn fdf_set_item_parts(ctx: *mut fdf_ctx, parts: u32) -> c_int;
     pub fn fdf_set_idle_sms(ctx: *mut fdf_ctx, sm_stride: u32) -> c_int;
     pub fn fdf_last_error(ctx: *const fdf_ctx) -> *const c_char;
     pub fn fdf_status_string(status: c_int) -> *const c_char;

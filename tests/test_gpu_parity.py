@@ -592,3 +592,39 @@ def test_idle_sms_do_not_change_the_result(detector, oracle_mod):
             assert detector.device_flags() == 0
     finally:
         detector.set_idle_sms(0)
+
+
+def test_item_parts_do_not_change_the_result(detector, oracle_mod):
+    """fdf_set_item_parts: the detection kernel's work items are whole strips or 2 / 4 / 8 equal chunk ranges of a strip
+    (automatic for small batches).  Same points, same order, same offsets for every split -- sparse and dense content,
+    every NMS mode, widths whose chunk count does and does not divide, one image and a batch."""
+    import torch
+
+    cases = [(detector.synth_frames(3, 3840, 2160, seed=77, kind=0), 20),    # 16 chunks per strip
+             (detector.synth_frames(1, 1920, 1080, seed=78, kind=0), 16),    # 8 chunks, one image
+             (detector.synth_frames(2, 1936, 200, seed=79, kind=1), 3),      # noise: dense path
+             (detector.synth_frames(2, 1456, 300, seed=80, kind=0)[:, :, :1450], 12)]  # 7 chunks: cannot be split evenly
+    try:
+        for frames, t in cases:
+            for nms in (0, 1, 2):
+                cfg = _cfg(t, 9, nms)
+                detector.set_item_parts(1)
+                want_pts, want_offs = detector.detect_device(frames, cfg)
+                torch.cuda.synchronize()
+                k = int(want_offs[-1])
+                assert k > 0
+                for parts in (2, 4, 8, 0):
+                    detector.set_item_parts(parts)
+                    pts, offs = detector.detect_device(frames, cfg)
+                    torch.cuda.synchronize()
+                    assert torch.equal(offs, want_offs), (tuple(frames.shape), nms, parts)
+                    assert torch.equal(pts[:k], want_pts[:k]), (tuple(frames.shape), nms, parts)
+                    assert detector.device_flags() == 0
+        # and against the CPU oracle for one split case
+        detector.set_item_parts(4)
+        f = cases[1][0]
+        pts, offs = detector.detect_device(f, _cfg(16, 9, 1))
+        torch.cuda.synchronize()
+        assert same_points(pts[: int(offs[1])].cpu().numpy(), oracle_mod.port_detect(f[0].cpu().numpy(), 16, 9, 1))
+    finally:
+        detector.set_item_parts(0)
