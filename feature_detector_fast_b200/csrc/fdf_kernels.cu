@@ -313,6 +313,9 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         if (smid % p.idle_sm_stride == p.idle_sm_stride - 1u) return;  // (block-uniform; the strips go by ticket)
     }
+    // A small grid (one image) leaves most of the GPU empty: let the grid behind it (the gather kernel, launched with
+    // programmatic stream serialisation) be placed right away; it waits at its griddepcontrol.wait for this grid's end.
+    if (SR == 32 && gridDim.x < 2u * 148u) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     constexpr LayoutSizes L = layout_sizes(SR);
     constexpr int HS = (MODE == NMS_OFF) ? 0 : 1;  // score halo (rows and columns) needed by the 3x3 NMS
     constexpr int OUT_R = out_rows(MODE, SR);
@@ -672,6 +675,10 @@ __global__ void __launch_bounds__(kGatherThreads) fdf_gather_kernel(const Detect
     const int nsum = (nwords + 31) / 32;  // level-2 words
     uint32_t *bits = gsm, *summary = gsm + nsum * 32;
     for (int i = tid; i < nsum * 33; i += kGatherThreads) gsm[i] = 0u;
+    // Programmatic dependent launch: this grid may have been started while the kernel in front of it (detection, or the
+    // scan) was still running -- everything above touched only shared memory.  From here on that kernel's results are
+    // complete and visible.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // (the detection kernel is complete: its flags are final, and this kernel only repeats bit 2 where that one set it)
     if (blockIdx.x == 0 && tid == 0 && p.flags_copy != nullptr) *p.flags_copy = *p.flags;
 
@@ -1034,9 +1041,20 @@ cudaError_t launch_gather(const DetectParams &p, cudaStream_t stream, DeviceInfo
     }
     unsigned long long grid = (unsigned long long)info.sms * (unsigned)info.gather_per_sm;
     if (grid > items) grid = items;
-    fdf_gather_kernel<<<(unsigned)grid, kGatherThreads, smem, stream>>>(p, (uint32_t)items,
-                                                                        gather_scans_itself(p) ? 1u : 0u);
-    return cudaGetLastError();
+    // launched with programmatic stream serialisation: its CTAs may be placed and run their prologue (bitmap clear)
+    // while the kernel in front drains; griddepcontrol.wait in the kernel keeps the data dependence (one launch gap
+    // less on the single-image latency path)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)kGatherThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fdf_gather_kernel, p, (uint32_t)items, gather_scans_itself(p) ? 1u : 0u);
 }
 
 cudaError_t launch_shard_push(const unsigned long long *all_offsets, uint32_t block, uint32_t n_ranks, uint32_t rank,
