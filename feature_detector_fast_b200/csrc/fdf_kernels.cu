@@ -529,8 +529,16 @@ fdf_detect_kernel(const __grid_constant__ CUtensorMap tmap, const DetectParams p
                     request_tile(ci + ahead, gc + (uint32_t)ahead, it);
                 }
                 FDF_CLK(6)
-                dropped = emit_list<MODE, SR>(ttid, kTestThreads, kcount[gc & 1u], klist, plane, scount, *s_base,
-                                              p.staging_cap, p.staging, g);
+                // In the NMS modes the last test warp stays out of this pass: its lane 0 has just spent ~1000 cycles on the
+                // tile request, and a chunk's ~170 keypoints are one block of 32 per warp -- with a share of its own it
+                // would start that block late and hold up the barrier below (profiles/r02_v19_timeline_3ctas.txt, "last
+                // test warp alone"; -0.6 %).  Off mode lists five times as many keypoints and needs all six (+3 % without).
+                if (MODE == NMS_OFF)
+                    dropped = emit_list<MODE, SR>(ttid, kTestThreads, kcount[gc & 1u], klist, plane, scount, *s_base,
+                                                  p.staging_cap, p.staging, g);
+                else if (twarp < kTestWarps - 1)
+                    dropped = emit_list<MODE, SR>(ttid, kTestThreads - 32, kcount[gc & 1u], klist, plane, scount, *s_base,
+                                                  p.staging_cap, p.staging, g);
                 FDF_CLK(7)
                 bar_test_group();  // the run is complete; the keypoint list is free
                 if (t0) {
